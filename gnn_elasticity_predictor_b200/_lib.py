@@ -1,0 +1,89 @@
+"""ctypes binding of ``libalignn_b200.so`` -- the C ABI declared in ``include/alignn_b200.h``.
+
+There is NO CPU fallback: if the library is missing and cannot be built, or a kernel is asked to
+run on a non-CUDA tensor, a ``RuntimeError`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
+
+from . import build as _build
+
+_LOCK = threading.Lock()
+_LIB = None
+
+_P = c_void_p
+
+# name -> (restype, argtypes); mirrors include/alignn_b200.h one to one
+SIGNATURES = {
+    "alignn_abi_version": (c_int, []),
+    "alignn_error_string": (c_char_p, [c_int]),
+    "alignn_plan_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "alignn_build_plan": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "alignn_conv_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int,
+                                c_float, c_uint64, c_uint64, _P]),
+    "alignn_conv_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                c_int64, c_int64, c_int, c_int, c_int, c_float, c_uint64, c_uint64, _P]),
+    "alignn_gate_ln_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_float,
+                                   c_float, c_uint64, c_uint64, _P]),
+    "alignn_gate_ln_bwd_partial_rows": (c_int64, []),
+    "alignn_gate_ln_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int,
+                                   c_float, c_uint64, c_uint64, _P]),
+    "alignn_segment_mean_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P]),
+    "alignn_segment_mean_bwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P]),
+}
+
+ABI_VERSION = 3
+F32, BF16 = 0, 1
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load(rebuild_if_stale: bool = True):
+    """Load (building first if needed) the shared library; raises ``RuntimeError`` on failure."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    with _LOCK:
+        if _LIB is not None:
+            return _LIB
+        path = _build.LIB_PATH
+        need_build = not os.path.exists(path)
+        if not need_build and rebuild_if_stale and not _build.is_current():
+            need_build = True
+        if need_build:
+            try:
+                _build.build()
+            except Exception as exc:  # noqa: BLE001
+                if not os.path.exists(path):
+                    raise RuntimeError(
+                        "libalignn_b200.so is missing and could not be built; the ALIGNN hot path has no "
+                        f"CPU or PyTorch fallback ({exc})") from exc
+        try:
+            lib = ctypes.CDLL(path)
+        except OSError as exc:
+            raise RuntimeError(f"cannot load {path}: {exc} (no fallback path exists)") from exc
+        for name, (res, args) in SIGNATURES.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError as exc:
+                raise RuntimeError(f"{path} does not export {name}; rebuild with "
+                                   "`python -m gnn_elasticity_predictor_b200.build --force`") from exc
+            fn.restype = res
+            fn.argtypes = args
+        got = lib.alignn_abi_version()
+        if got != ABI_VERSION:
+            raise RuntimeError(f"{path}: ABI version {got}, binding expects {ABI_VERSION}; rebuild the library")
+        _LIB = lib
+        return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().alignn_error_string(rc)
+        raise RuntimeError(f"{what} failed: {msg.decode() if msg else rc} (code {rc})")

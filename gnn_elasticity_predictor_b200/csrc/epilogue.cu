@@ -1,0 +1,490 @@
+// Fused node epilogue: beta-gated skip + LayerNorm + ReLU + dropout + residual (forward, backward).
+//
+// Replaces the tail of PyG TransformerConv.forward (beta gate against the skip projection) and
+// `x + Dropout(ReLU(LayerNorm(out)))` of EdgeUpdateBlock / NodeUpdateBlock
+// (reference scripts/train.py:316-317, 335-336).  The [rows, 3*hidden] concat that PyG feeds to
+// lin_beta is never materialised: the gate logit is three fused dot products.
+//
+// HBM-bound elementwise/row-reduction work: each operand row is read once with 128-bit loads, row
+// statistics live in registers (xor-shuffle reductions over the row's lanes), parameter gradients
+// are accumulated in registers by a persistent grid and reduced in a fixed order (no atomics).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace alignn {
+
+constexpr int EPI_THREADS = 256;
+constexpr int EPI_WARPS = EPI_THREADS / 32;
+constexpr int EPI_PARTIAL_BLOCKS = 296;  // 2 x 148 SMs: persistent grid of the backward
+constexpr int EPI_GEN_WARPS = 4;
+
+// dropout keep-scales of 8 consecutive elements starting at a multiple of 8
+__device__ __forceinline__ void dropout8(uint64_t seed, uint64_t offset, uint64_t first, float p,
+                                         float inv_keep, float *out) {
+    const Philox4 r0 = philox4x32_10(seed, offset, first >> 2);
+    const Philox4 r1 = philox4x32_10(seed, offset, (first >> 2) + 1);
+    const uint32_t bits[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float u = (float)(bits[c] >> 8) * (1.0f / 16777216.0f);
+        out[c] = u < p ? 0.0f : inv_keep;
+    }
+}
+
+template <typename T, int LANES>
+__global__ void __launch_bounds__(EPI_THREADS)
+gate_ln_fwd_kernel(const float *__restrict__ agg, const T *__restrict__ xr, const float *__restrict__ x,
+                   const float *__restrict__ wbeta, const float *__restrict__ gamma,
+                   const float *__restrict__ bias, float *__restrict__ y, T *__restrict__ y_lp,
+                   float *__restrict__ beta_out, float *__restrict__ mean_out, float *__restrict__ rstd_out,
+                   int64_t n_rows, int hidden, float eps, float p_drop, float inv_keep, uint64_t seed,
+                   uint64_t offset) {
+    constexpr int RPW = 32 / LANES;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % LANES;
+    const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t row = warp_id * RPW + lane / LANES;
+    const bool ok = row < n_rows;
+    const int ch = sub * 8;
+    F8 af, sf, xf;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) af.v[c] = sf.v[c] = xf.v[c] = 0.f;
+    if (ok) {
+        af = ld8(agg + row * hidden + ch);
+        sf = ld8(xr + row * hidden + ch);
+        xf = ld8(x + row * hidden + ch);
+    }
+    const F8 w1 = ld8(wbeta + ch), w2 = ld8(wbeta + hidden + ch), w3 = ld8(wbeta + 2 * hidden + ch);
+    float zp = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        zp += w1.v[c] * af.v[c] + w2.v[c] * sf.v[c] + w3.v[c] * (af.v[c] - sf.v[c]);
+    const float zl = group_sum<LANES>(zp);
+    const float beta = 1.0f / (1.0f + expf(-zl));
+    F8 o;
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        o.v[c] = beta * sf.v[c] + (1.0f - beta) * af.v[c];
+        sum += o.v[c];
+    }
+    const float mean = group_sum<LANES>(sum) / (float)hidden;
+    float sq = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float d = o.v[c] - mean;
+        sq = fmaf(d, d, sq);
+    }
+    const float var = group_sum<LANES>(sq) / (float)hidden;
+    const float rstd = 1.0f / sqrtf(var + eps);
+    if (!ok) return;
+    const F8 gm = ld8(gamma + ch), bs = ld8(bias + ch);
+    float keep[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) keep[c] = 1.f;
+    if (p_drop > 0.f) dropout8(seed, offset, (uint64_t)row * hidden + ch, p_drop, inv_keep, keep);
+    F8 out;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float yv = (o.v[c] - mean) * rstd * gm.v[c] + bs.v[c];
+        out.v[c] = xf.v[c] + fmaxf(yv, 0.f) * keep[c];
+    }
+    st8(y + row * hidden + ch, out);
+    if (y_lp) st8(y_lp + row * hidden + ch, out);
+    if (sub == 0) {
+        beta_out[row] = beta;
+        mean_out[row] = mean;
+        rstd_out[row] = rstd;
+    }
+}
+
+template <typename T, int LANES>
+__global__ void __launch_bounds__(EPI_THREADS)
+gate_ln_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ agg, const T *__restrict__ xr,
+                   const float *__restrict__ wbeta, const float *__restrict__ gamma,
+                   const float *__restrict__ bias, const float *__restrict__ beta_in,
+                   const float *__restrict__ mean_in, const float *__restrict__ rstd_in,
+                   float *__restrict__ dagg, T *__restrict__ dxr, float *__restrict__ partials,
+                   int64_t n_rows, int hidden, float p_drop, float inv_keep, uint64_t seed, uint64_t offset) {
+    constexpr int RPW = 32 / LANES;
+    __shared__ float red[EPI_WARPS][5][LANES * 8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane % LANES;
+    const int ch = sub * 8;
+    const int64_t slots = (int64_t)gridDim.x * EPI_WARPS * RPW;
+    const int64_t slot = ((int64_t)blockIdx.x * EPI_WARPS + warp) * RPW + lane / LANES;
+    const int64_t iters = (n_rows + slots - 1) / slots;
+
+    const F8 w1 = ld8(wbeta + ch), w2 = ld8(wbeta + hidden + ch), w3 = ld8(wbeta + 2 * hidden + ch);
+    const F8 gm = ld8(gamma + ch), bs = ld8(bias + ch);
+    F8 a1, a2, a3, ag, ab;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) a1.v[c] = a2.v[c] = a3.v[c] = ag.v[c] = ab.v[c] = 0.f;
+    const float inv_h = 1.0f / (float)hidden;
+
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t row = slot + it * slots;
+        const bool ok = row < n_rows;
+        F8 gf, af, sf;
+        float beta = 0.f, mean = 0.f, rstd = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) gf.v[c] = af.v[c] = sf.v[c] = 0.f;
+        if (ok) {
+            gf = ld8(dy + row * hidden + ch);
+            af = ld8(agg + row * hidden + ch);
+            sf = ld8(xr + row * hidden + ch);
+            beta = __ldg(beta_in + row);
+            mean = __ldg(mean_in + row);
+            rstd = __ldg(rstd_in + row);
+        }
+        float keep[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) keep[c] = 1.f;
+        if (p_drop > 0.f && ok) dropout8(seed, offset, (uint64_t)row * hidden + ch, p_drop, inv_keep, keep);
+        F8 xh, dxh;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float o = beta * sf.v[c] + (1.0f - beta) * af.v[c];
+            xh.v[c] = (o - mean) * rstd;
+            const float yv = xh.v[c] * gm.v[c] + bs.v[c];
+            const float dyv = yv > 0.f ? gf.v[c] * keep[c] : 0.f;
+            ag.v[c] = fmaf(dyv, xh.v[c], ag.v[c]);
+            ab.v[c] += dyv;
+            dxh.v[c] = dyv * gm.v[c];
+            s1 += dxh.v[c];
+            s2 = fmaf(dxh.v[c], xh.v[c], s2);
+        }
+        const float m1 = group_sum<LANES>(s1) * inv_h;
+        const float m2 = group_sum<LANES>(s2) * inv_h;
+        F8 dof;
+        float bp = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            dof.v[c] = rstd * (dxh.v[c] - m1 - xh.v[c] * m2);
+            bp = fmaf(dof.v[c], sf.v[c] - af.v[c], bp);
+        }
+        const float dbeta = group_sum<LANES>(bp);
+        const float dz = dbeta * beta * (1.0f - beta);
+        if (ok) {
+            F8 da, ds;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                da.v[c] = (1.0f - beta) * dof.v[c] + dz * (w1.v[c] + w3.v[c]);
+                ds.v[c] = beta * dof.v[c] + dz * (w2.v[c] - w3.v[c]);
+                a1.v[c] = fmaf(dz, af.v[c], a1.v[c]);
+                a2.v[c] = fmaf(dz, sf.v[c], a2.v[c]);
+                a3.v[c] = fmaf(dz, af.v[c] - sf.v[c], a3.v[c]);
+            }
+            st8(dagg + row * hidden + ch, da);
+            st8(dxr + row * hidden + ch, ds);
+        }
+    }
+    // fold the row groups of a warp (fixed butterfly order), then the warps of the block (fixed order)
+    if (RPW > 1) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+#pragma unroll
+            for (int off = 16; off >= LANES; off >>= 1) {
+                a1.v[c] += __shfl_xor_sync(FULL, a1.v[c], off);
+                a2.v[c] += __shfl_xor_sync(FULL, a2.v[c], off);
+                a3.v[c] += __shfl_xor_sync(FULL, a3.v[c], off);
+                ag.v[c] += __shfl_xor_sync(FULL, ag.v[c], off);
+                ab.v[c] += __shfl_xor_sync(FULL, ab.v[c], off);
+            }
+        }
+    }
+    if (lane < LANES) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            red[warp][0][ch + c] = a1.v[c];
+            red[warp][1][ch + c] = a2.v[c];
+            red[warp][2][ch + c] = a3.v[c];
+            red[warp][3][ch + c] = ag.v[c];
+            red[warp][4][ch + c] = ab.v[c];
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 5 * hidden; i += EPI_THREADS) {
+        const int which = i / hidden, c = i % hidden;
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < EPI_WARPS; ++w) s += red[w][which][c];
+        partials[((int64_t)blockIdx.x * 5 + which) * hidden + c] = s;
+    }
+}
+
+__global__ void reduce_partials_kernel(const float *__restrict__ partials, float *__restrict__ out, int n_blocks,
+                                       int width) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= width) return;
+    float s = 0.f;
+    for (int b = 0; b < n_blocks; ++b) s += partials[(int64_t)b * width + i];
+    out[i] = s;
+}
+
+// ---- generic (any hidden): one warp per row, lanes stride channels -----------------------------------
+template <typename T>
+__global__ void __launch_bounds__(EPI_GEN_WARPS * 32)
+gate_ln_fwd_generic_kernel(const float *__restrict__ agg, const T *__restrict__ xr, const float *__restrict__ x,
+                           const float *__restrict__ wbeta, const float *__restrict__ gamma,
+                           const float *__restrict__ bias, float *__restrict__ y, T *__restrict__ y_lp,
+                           float *__restrict__ beta_out, float *__restrict__ mean_out,
+                           float *__restrict__ rstd_out, int64_t n_rows, int hidden, float eps, float p_drop,
+                           float inv_keep, uint64_t seed, uint64_t offset) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * EPI_GEN_WARPS + warp;
+    if (row >= n_rows) return;
+    const float *ar = agg + row * hidden;
+    const T *sr = xr + row * hidden;
+    float zp = 0.f;
+    for (int c = lane; c < hidden; c += 32) {
+        const float a = ar[c], s = ldf(sr + c);
+        zp += wbeta[c] * a + wbeta[hidden + c] * s + wbeta[2 * hidden + c] * (a - s);
+    }
+    const float beta = 1.0f / (1.0f + expf(-warp_sum(zp)));
+    float sum = 0.f;
+    for (int c = lane; c < hidden; c += 32) sum += beta * ldf(sr + c) + (1.0f - beta) * ar[c];
+    const float mean = warp_sum(sum) / (float)hidden;
+    float sq = 0.f;
+    for (int c = lane; c < hidden; c += 32) {
+        const float d = beta * ldf(sr + c) + (1.0f - beta) * ar[c] - mean;
+        sq = fmaf(d, d, sq);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)hidden + eps);
+    for (int c = lane; c < hidden; c += 32) {
+        const float o = beta * ldf(sr + c) + (1.0f - beta) * ar[c];
+        const float yv = (o - mean) * rstd * gamma[c] + bias[c];
+        float keep = 1.f;
+        if (p_drop > 0.f) keep = dropout_scale(seed, offset, (uint64_t)row * hidden + c, p_drop, inv_keep);
+        const float out = x[row * hidden + c] + fmaxf(yv, 0.f) * keep;
+        y[row * hidden + c] = out;
+        if (y_lp) stf(y_lp + row * hidden + c, out);
+    }
+    if (lane == 0) {
+        beta_out[row] = beta;
+        mean_out[row] = mean;
+        rstd_out[row] = rstd;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(EPI_GEN_WARPS * 32)
+gate_ln_bwd_generic_kernel(const float *__restrict__ dy, const float *__restrict__ agg, const T *__restrict__ xr,
+                           const float *__restrict__ wbeta, const float *__restrict__ gamma,
+                           const float *__restrict__ bias, const float *__restrict__ beta_in,
+                           const float *__restrict__ mean_in, const float *__restrict__ rstd_in,
+                           float *__restrict__ dagg, T *__restrict__ dxr, float *__restrict__ partials,
+                           int64_t n_rows, int hidden, float p_drop, float inv_keep, uint64_t seed,
+                           uint64_t offset) {
+    extern __shared__ float acc[];  // [EPI_GEN_WARPS][5][hidden]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *mine = acc + (size_t)warp * 5 * hidden;
+    for (int i = lane; i < 5 * hidden; i += 32) mine[i] = 0.f;
+    __syncwarp();
+    const int64_t stride = (int64_t)gridDim.x * EPI_GEN_WARPS;
+    const float inv_h = 1.0f / (float)hidden;
+    for (int64_t row = (int64_t)blockIdx.x * EPI_GEN_WARPS + warp; row < n_rows; row += stride) {
+        const float *ar = agg + row * hidden, *gr = dy + row * hidden;
+        const T *sr = xr + row * hidden;
+        const float beta = beta_in[row], mean = mean_in[row], rstd = rstd_in[row];
+        float s1 = 0.f, s2 = 0.f;
+        for (int c = lane; c < hidden; c += 32) {
+            const float o = beta * ldf(sr + c) + (1.0f - beta) * ar[c];
+            const float xh = (o - mean) * rstd;
+            const float yv = xh * gamma[c] + bias[c];
+            float keep = 1.f;
+            if (p_drop > 0.f) keep = dropout_scale(seed, offset, (uint64_t)row * hidden + c, p_drop, inv_keep);
+            const float dyv = yv > 0.f ? gr[c] * keep : 0.f;
+            mine[3 * hidden + c] = fmaf(dyv, xh, mine[3 * hidden + c]);
+            mine[4 * hidden + c] += dyv;
+            const float dxh = dyv * gamma[c];
+            s1 += dxh;
+            s2 = fmaf(dxh, xh, s2);
+        }
+        const float m1 = warp_sum(s1) * inv_h, m2 = warp_sum(s2) * inv_h;
+        float bp = 0.f;
+        for (int c = lane; c < hidden; c += 32) {
+            const float s = ldf(sr + c), a = ar[c];
+            const float o = beta * s + (1.0f - beta) * a;
+            const float xh = (o - mean) * rstd;
+            const float yv = xh * gamma[c] + bias[c];
+            float keep = 1.f;
+            if (p_drop > 0.f) keep = dropout_scale(seed, offset, (uint64_t)row * hidden + c, p_drop, inv_keep);
+            const float dxh = (yv > 0.f ? gr[c] * keep : 0.f) * gamma[c];
+            const float dof = rstd * (dxh - m1 - xh * m2);
+            bp = fmaf(dof, s - a, bp);
+        }
+        const float dbeta = warp_sum(bp);
+        const float dz = dbeta * beta * (1.0f - beta);
+        for (int c = lane; c < hidden; c += 32) {
+            const float s = ldf(sr + c), a = ar[c];
+            const float o = beta * s + (1.0f - beta) * a;
+            const float xh = (o - mean) * rstd;
+            const float yv = xh * gamma[c] + bias[c];
+            float keep = 1.f;
+            if (p_drop > 0.f) keep = dropout_scale(seed, offset, (uint64_t)row * hidden + c, p_drop, inv_keep);
+            const float dxh = (yv > 0.f ? gr[c] * keep : 0.f) * gamma[c];
+            const float dof = rstd * (dxh - m1 - xh * m2);
+            dagg[row * hidden + c] = (1.0f - beta) * dof + dz * (wbeta[c] + wbeta[2 * hidden + c]);
+            stf(dxr + row * hidden + c, beta * dof + dz * (wbeta[hidden + c] - wbeta[2 * hidden + c]));
+            mine[c] = fmaf(dz, a, mine[c]);
+            mine[hidden + c] = fmaf(dz, s, mine[hidden + c]);
+            mine[2 * hidden + c] = fmaf(dz, a - s, mine[2 * hidden + c]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 5 * hidden; i += EPI_GEN_WARPS * 32) {
+        float s = 0.f;
+        for (int w = 0; w < EPI_GEN_WARPS; ++w) s += acc[(size_t)w * 5 * hidden + i];
+        partials[(int64_t)blockIdx.x * 5 * hidden + i] = s;
+    }
+}
+
+static inline bool epi_fast(int hidden, int *lanes) {
+    if (hidden % 8) return false;
+    const int L = hidden / 8;
+    if (L > 32 || (L & (L - 1))) return false;
+    *lanes = L;
+    return true;
+}
+
+template <typename T, int LANES>
+static void launch_epi_fwd(const float *agg, const void *xr, const float *x, const float *wbeta, const float *gamma,
+                           const float *bias, float *y, void *y_lp, float *beta, float *mean, float *rstd,
+                           int64_t n_rows, int hidden, float eps, float p_drop, uint64_t seed, uint64_t offset,
+                           cudaStream_t st) {
+    const int rows_per_block = EPI_WARPS * (32 / LANES);
+    const unsigned grid = (unsigned)((n_rows + rows_per_block - 1) / rows_per_block);
+    const float inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+    gate_ln_fwd_kernel<T, LANES><<<grid, EPI_THREADS, 0, st>>>(agg, (const T *)xr, x, wbeta, gamma, bias, y, (T *)y_lp,
+                                                               beta, mean, rstd, n_rows, hidden, eps, p_drop, inv_keep,
+                                                               seed, offset);
+}
+
+template <typename T>
+static int dispatch_epi_fwd(const float *agg, const void *xr, const float *x, const float *wbeta, const float *gamma,
+                            const float *bias, float *y, void *y_lp, float *beta, float *mean, float *rstd,
+                            int64_t n_rows, int hidden, float eps, float p_drop, uint64_t seed, uint64_t offset,
+                            cudaStream_t st) {
+    int lanes = 0;
+#define EPI_FWD(L) launch_epi_fwd<T, L>(agg, xr, x, wbeta, gamma, bias, y, y_lp, beta, mean, rstd, n_rows, hidden, eps, p_drop, seed, offset, st)
+    if (epi_fast(hidden, &lanes)) {
+        switch (lanes) {
+            case 32: EPI_FWD(32); break;
+            case 16: EPI_FWD(16); break;
+            case 8: EPI_FWD(8); break;
+            case 4: EPI_FWD(4); break;
+            case 2: EPI_FWD(2); break;
+            default: EPI_FWD(1); break;
+        }
+    } else {
+        const float inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+        const unsigned grid = (unsigned)((n_rows + EPI_GEN_WARPS - 1) / EPI_GEN_WARPS);
+        gate_ln_fwd_generic_kernel<T><<<grid, EPI_GEN_WARPS * 32, 0, st>>>(
+            agg, (const T *)xr, x, wbeta, gamma, bias, y, (T *)y_lp, beta, mean, rstd, n_rows, hidden, eps, p_drop,
+            inv_keep, seed, offset);
+    }
+#undef EPI_FWD
+    ALIGNN_LAUNCH_CHECK();
+    return ALIGNN_OK;
+}
+
+template <typename T, int LANES>
+static void launch_epi_bwd(const float *dy, const float *agg, const void *xr, const float *wbeta, const float *gamma,
+                           const float *bias, const float *beta, const float *mean, const float *rstd, float *dagg,
+                           void *dxr, float *partials, int64_t n_rows, int hidden, float p_drop, uint64_t seed,
+                           uint64_t offset, cudaStream_t st) {
+    const float inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+    gate_ln_bwd_kernel<T, LANES><<<EPI_PARTIAL_BLOCKS, EPI_THREADS, 0, st>>>(
+        dy, agg, (const T *)xr, wbeta, gamma, bias, beta, mean, rstd, dagg, (T *)dxr, partials, n_rows, hidden, p_drop,
+        inv_keep, seed, offset);
+}
+
+template <typename T>
+static int dispatch_epi_bwd(const float *dy, const float *agg, const void *xr, const float *wbeta, const float *gamma,
+                            const float *bias, const float *beta, const float *mean, const float *rstd, float *dagg,
+                            void *dxr, float *partials, float *dparams, int64_t n_rows, int hidden, float p_drop,
+                            uint64_t seed, uint64_t offset, cudaStream_t st) {
+    int lanes = 0;
+#define EPI_BWD(L) launch_epi_bwd<T, L>(dy, agg, xr, wbeta, gamma, bias, beta, mean, rstd, dagg, dxr, partials, n_rows, hidden, p_drop, seed, offset, st)
+    if (epi_fast(hidden, &lanes)) {
+        switch (lanes) {
+            case 32: EPI_BWD(32); break;
+            case 16: EPI_BWD(16); break;
+            case 8: EPI_BWD(8); break;
+            case 4: EPI_BWD(4); break;
+            case 2: EPI_BWD(2); break;
+            default: EPI_BWD(1); break;
+        }
+    } else {
+        const float inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+        const size_t smem = (size_t)EPI_GEN_WARPS * 5 * hidden * sizeof(float);
+        if (smem > 48 * 1024) {
+            cudaError_t err = cudaFuncSetAttribute(gate_ln_bwd_generic_kernel<T>,
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (err != cudaSuccess) return ALIGNN_ERR_CUDA_BASE + (int)err;
+        }
+        gate_ln_bwd_generic_kernel<T><<<EPI_PARTIAL_BLOCKS, EPI_GEN_WARPS * 32, smem, st>>>(
+            dy, agg, (const T *)xr, wbeta, gamma, bias, beta, mean, rstd, dagg, (T *)dxr, partials, n_rows, hidden,
+            p_drop, inv_keep, seed, offset);
+    }
+#undef EPI_BWD
+    ALIGNN_LAUNCH_CHECK();
+    const int width = 5 * hidden;
+    reduce_partials_kernel<<<(width + 255) / 256, 256, 0, st>>>(partials, dparams, EPI_PARTIAL_BLOCKS, width);
+    ALIGNN_LAUNCH_CHECK();
+    return ALIGNN_OK;
+}
+
+}  // namespace alignn
+
+using namespace alignn;
+
+extern "C" int64_t alignn_gate_ln_bwd_partial_rows(void) { return EPI_PARTIAL_BLOCKS; }
+
+extern "C" int alignn_gate_ln_fwd(const float *agg, const void *xr, const float *x,
+                                  const float *wbeta, const float *gamma, const float *bias,
+                                  float *y, void *y_lp, float *beta, float *mean, float *rstd,
+                                  int64_t n_rows, int hidden, int dtype, float eps,
+                                  float p_drop, uint64_t seed, uint64_t offset, void *stream) {
+    if (n_rows < 0 || hidden <= 0 || hidden > 2048) return ALIGNN_ERR_BAD_SHAPE;
+    if (!(p_drop >= 0.f && p_drop < 1.f)) return ALIGNN_ERR_BAD_ARG;
+    if (n_rows == 0) return ALIGNN_OK;
+    if (!agg || !xr || !x || !wbeta || !gamma || !bias || !y || !beta || !mean || !rstd) return ALIGNN_ERR_BAD_ARG;
+    if (!aligned16(agg) || !aligned16(xr) || !aligned16(x) || !aligned16(wbeta) || !aligned16(gamma) ||
+        !aligned16(bias) || !aligned16(y) || !aligned16(y_lp))
+        return ALIGNN_ERR_BAD_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == ALIGNN_F32)
+        return dispatch_epi_fwd<float>(agg, xr, x, wbeta, gamma, bias, y, y_lp, beta, mean, rstd, n_rows, hidden, eps,
+                                       p_drop, seed, offset, st);
+    if (dtype == ALIGNN_BF16)
+        return dispatch_epi_fwd<__nv_bfloat16>(agg, xr, x, wbeta, gamma, bias, y, y_lp, beta, mean, rstd, n_rows,
+                                               hidden, eps, p_drop, seed, offset, st);
+    return ALIGNN_ERR_BAD_DTYPE;
+}
+
+extern "C" int alignn_gate_ln_bwd(const float *dy, const float *agg, const void *xr,
+                                  const float *wbeta, const float *gamma, const float *bias,
+                                  const float *beta, const float *mean, const float *rstd,
+                                  float *dagg, void *dxr, float *partials, float *dparams,
+                                  int64_t n_rows, int hidden, int dtype,
+                                  float p_drop, uint64_t seed, uint64_t offset, void *stream) {
+    if (n_rows < 0 || hidden <= 0 || hidden > 2048) return ALIGNN_ERR_BAD_SHAPE;
+    if (!(p_drop >= 0.f && p_drop < 1.f)) return ALIGNN_ERR_BAD_ARG;
+    if (!partials || !dparams || !wbeta || !gamma || !bias) return ALIGNN_ERR_BAD_ARG;
+    if (n_rows > 0 && (!dy || !agg || !xr || !beta || !mean || !rstd || !dagg || !dxr)) return ALIGNN_ERR_BAD_ARG;
+    if (!aligned16(dy) || !aligned16(agg) || !aligned16(xr) || !aligned16(wbeta) || !aligned16(gamma) ||
+        !aligned16(bias) || !aligned16(dagg) || !aligned16(dxr))
+        return ALIGNN_ERR_BAD_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == ALIGNN_F32)
+        return dispatch_epi_bwd<float>(dy, agg, xr, wbeta, gamma, bias, beta, mean, rstd, dagg, dxr, partials,
+                                       dparams, n_rows, hidden, p_drop, seed, offset, st);
+    if (dtype == ALIGNN_BF16)
+        return dispatch_epi_bwd<__nv_bfloat16>(dy, agg, xr, wbeta, gamma, bias, beta, mean, rstd, dagg, dxr, partials,
+                                               dparams, n_rows, hidden, p_drop, seed, offset, st);
+    return ALIGNN_ERR_BAD_DTYPE;
+}

@@ -1,0 +1,310 @@
+"""Drop-in replacements for the reference's ALIGNN model classes, backed by the sm_100a kernels.
+
+Same constructor signatures, attribute names, ``forward`` / ``embed`` contracts, error behaviour and
+``state_dict`` layout as the reference:
+
+* ``TransformerConv``        -- PyG 2.7.0 ``TransformerConv(..., edge_dim=H, beta=True)`` as built at
+                               reference ``scripts/train.py:308,326`` (sub-modules ``lin_key, lin_query,
+                               lin_value, lin_edge`` (no bias)``, lin_skip, lin_beta`` (no bias))
+* ``EdgeUpdateBlock``        -- ``scripts/train.py:303-317``
+* ``NodeUpdateBlock``        -- ``scripts/train.py:320-336``
+* ``AlignnRegressor``        -- ``scripts/train.py:339-401``
+* ``HeteroAlignnRegressor``  -- ``scripts/train.py:528-586``
+
+Numerics follow the reference's two regimes: fp32 (``predict.py`` / ``evaluate.py``; all projections
+in fp32 without TF32) and bf16 autocast (``train.py:632-636``: projections in bf16, attention
+statistics, aggregation, LayerNorm and the residual stream in fp32).  The regime is picked from the
+ambient ``torch.autocast`` state, or forced with ``model.compute_dtype = torch.bfloat16``.
+
+The dense projections currently go through cuBLAS (``torch.baddbmm`` / ``addmm``); everything between
+them is the hand-written path in ``csrc/``.  There is no CPU path: calling ``forward`` with CPU tensors
+raises ``RuntimeError``.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor, nn
+
+from . import ops
+from .ops import GraphPlan
+
+
+def _ambient_dtype(default: Optional[torch.dtype] = None) -> torch.dtype:
+    if default is not None:
+        return default
+    if torch.is_autocast_enabled("cuda"):
+        dt = torch.get_autocast_dtype("cuda")
+        if dt != torch.bfloat16:
+            raise RuntimeError(f"autocast dtype {dt} is not supported by the B200 path: use torch.bfloat16")
+        return dt
+    return torch.float32
+
+
+def _linear(x: Tensor, lin: nn.Linear, cd: torch.dtype) -> Tensor:
+    """``lin(x)`` in compute dtype ``cd`` irrespective of the ambient autocast state."""
+    with torch.autocast("cuda", enabled=False):
+        w = lin.weight.to(cd)
+        b = lin.bias.to(cd) if lin.bias is not None else None
+        return F.linear(x.to(cd), w, b)
+
+
+def _mlp2(seq: nn.Sequential, x: Tensor, cd: torch.dtype) -> Tensor:
+    """``Linear -> ReLU -> Linear`` encoder (reference ``train.py:350-364``)."""
+    return _linear(F.relu(_linear(x, seq[0], cd)), seq[2], cd)
+
+
+class TransformerConv(nn.Module):
+    """Edge-featured multi-head graph attention with a beta-gated skip (PyG ``TransformerConv``).
+
+    ``forward(x, edge_index, edge_attr)`` keeps PyG's call signature and returns the gated output
+    ``beta * lin_skip(x) + (1 - beta) * agg``.  The blocks below call :meth:`project_and_aggregate`
+    instead and fuse the gate with their LayerNorm/ReLU/residual epilogue.
+    """
+
+    def __init__(self, in_channels: int, out_channels: int, heads: int = 1, concat: bool = True, beta: bool = False,
+                 dropout: float = 0.0, edge_dim: Optional[int] = None, bias: bool = True, root_weight: bool = True):
+        super().__init__()
+        if not (concat and beta and root_weight and edge_dim is not None):
+            raise NotImplementedError(
+                "the B200 path implements the configuration the reference uses: concat=True, beta=True, "
+                "root_weight=True, edge_dim set (scripts/train.py:308,326)")
+        if heads * out_channels != in_channels:
+            raise NotImplementedError("the residual blocks of the reference require heads * out_channels == in_channels")
+        self.in_channels, self.out_channels, self.heads = in_channels, out_channels, heads
+        self.dropout = float(dropout)
+        self.edge_dim = edge_dim
+        hc = heads * out_channels
+        self.lin_key = nn.Linear(in_channels, hc)
+        self.lin_query = nn.Linear(in_channels, hc)
+        self.lin_value = nn.Linear(in_channels, hc)
+        self.lin_edge = nn.Linear(edge_dim, hc, bias=False)
+        self.lin_skip = nn.Linear(in_channels, hc, bias=bias)
+        self.lin_beta = nn.Linear(3 * hc, 1, bias=False)
+
+    def project_and_aggregate(self, x: Tensor, edge_attr: Tensor, plan: GraphPlan, cd: torch.dtype
+                              ) -> Tuple[Tensor, Tensor]:
+        """Returns ``(agg fp32 [N, H], x_r cd [N, H])``."""
+        with torch.autocast("cuda", enabled=False):
+            xb = x.to(cd)
+            # one batched GEMM for the four node projections -> [4, N, H] with contiguous slices
+            w4 = torch.stack([self.lin_query.weight, self.lin_key.weight, self.lin_value.weight,
+                              self.lin_skip.weight]).to(cd)
+            if self.lin_skip.bias is not None:
+                b_skip = self.lin_skip.bias
+            else:
+                b_skip = torch.zeros_like(self.lin_query.bias)
+            b4 = torch.stack([self.lin_query.bias, self.lin_key.bias, self.lin_value.bias, b_skip]).to(cd)
+            qkvs = torch.baddbmm(b4.unsqueeze(1), xb.unsqueeze(0).expand(4, -1, -1), w4.transpose(1, 2))
+            e = F.linear(edge_attr.to(cd), self.lin_edge.weight.to(cd))
+            p = self.dropout if self.training else 0.0
+            seed, offset = ops.next_dropout_key() if p > 0.0 else (0, 0)
+            agg = ops.conv_core(qkvs[0], qkvs[1], qkvs[2], e, plan, self.heads, p, seed, offset)
+        return agg, qkvs[3]
+
+    def forward(self, x: Tensor, edge_index: Tensor, edge_attr: Optional[Tensor] = None,
+                plan: Optional[GraphPlan] = None) -> Tensor:
+        if edge_attr is None:
+            raise RuntimeError("edge_attr is required (edge_dim is set)")
+        cd = _ambient_dtype(getattr(self, "compute_dtype", None))
+        if plan is None:
+            plan = ops.build_plan(edge_index, x.size(0), validate=True)
+        agg, xr = self.project_and_aggregate(x, edge_attr, plan, cd)
+        with torch.autocast("cuda", enabled=False):
+            xr32 = xr.float()
+            z = F.linear(torch.cat([agg, xr32, agg - xr32], dim=-1), self.lin_beta.weight.float())
+            beta = torch.sigmoid(z)
+            return beta * xr32 + (1.0 - beta) * agg
+
+
+def _fused_block_tail(conv: TransformerConv, norm: nn.LayerNorm, p_drop: float, training: bool, state: Tensor,
+                      agg: Tensor, xr: Tensor) -> Tensor:
+    p = p_drop if training else 0.0
+    seed, offset = ops.next_dropout_key() if p > 0.0 else (0, 0)
+    y, _ = ops.gate_ln_relu_residual(agg, xr, state, conv.lin_beta.weight, norm.weight, norm.bias, norm.eps, p,
+                                     seed, offset, want_lp=False)
+    return y
+
+
+class EdgeUpdateBlock(nn.Module):
+    """Line-graph conv block: bonds are nodes, bond angles are edges (reference ``train.py:303-317``)."""
+
+    def __init__(self, hidden: int, heads: int, dropout: float):
+        super().__init__()
+        if hidden % heads != 0:
+            raise ValueError("hidden size must be divisible by number of heads")
+        self.conv = TransformerConv(hidden, hidden // heads, heads=heads, edge_dim=hidden, dropout=dropout, beta=True)
+        self.norm = nn.LayerNorm(hidden)
+        self.dropout = nn.Dropout(dropout)
+
+    def forward(self, edge_state: Tensor, lg_edge_index: Tensor, angle_emb: Tensor,
+                plan: Optional[GraphPlan] = None, compute_dtype: Optional[torch.dtype] = None) -> Tensor:
+        if edge_state.numel() == 0 or angle_emb.numel() == 0 or lg_edge_index.numel() == 0:
+            return edge_state
+        cd = _ambient_dtype(compute_dtype)
+        if plan is None:
+            plan = ops.build_plan(lg_edge_index, edge_state.size(0), validate=True)
+        agg, xr = self.conv.project_and_aggregate(edge_state, angle_emb, plan, cd)
+        return _fused_block_tail(self.conv, self.norm, self.dropout.p, self.training, edge_state, agg, xr)
+
+
+class NodeUpdateBlock(nn.Module):
+    """Atom-graph conv block with projected bond states as edge attributes (reference ``train.py:320-336``)."""
+
+    def __init__(self, hidden_node: int, hidden_edge: int, heads: int, dropout: float):
+        super().__init__()
+        if hidden_node % heads != 0:
+            raise ValueError("hidden size must be divisible by number of heads")
+        self.edge_proj = nn.Linear(hidden_edge, hidden_edge)
+        self.conv = TransformerConv(hidden_node, hidden_node // heads, heads=heads, edge_dim=hidden_edge,
+                                    dropout=dropout, beta=True)
+        self.norm = nn.LayerNorm(hidden_node)
+        self.dropout = nn.Dropout(dropout)
+
+    def forward(self, node_state: Tensor, edge_index: Tensor, edge_state: Tensor,
+                plan: Optional[GraphPlan] = None, compute_dtype: Optional[torch.dtype] = None) -> Tensor:
+        if edge_state.numel() == 0 or edge_index.numel() == 0:
+            return node_state
+        cd = _ambient_dtype(compute_dtype)
+        if plan is None:
+            plan = ops.build_plan(edge_index, node_state.size(0), validate=True)
+        edge_attr = _linear(edge_state, self.edge_proj, cd)
+        agg, xr = self.conv.project_and_aggregate(node_state, edge_attr, plan, cd)
+        return _fused_block_tail(self.conv, self.norm, self.dropout.p, self.training, node_state, agg, xr)
+
+
+class AlignnRegressor(nn.Module):
+    """ALIGNN-style trunk + plain regression heads (reference ``train.py:339-401``)."""
+
+    def __init__(self, node_dim: int, edge_dim: int, angle_dim: int, global_dim: int, target_dim: int, hidden: int,
+                 layers: int, heads: int, dropout: float):
+        super().__init__()
+        if heads <= 0:
+            raise ValueError("heads must be positive")
+        if target_dim <= 0:
+            raise ValueError("target_dim must be positive")
+        if hidden % heads != 0:
+            raise ValueError("hidden size must be divisible by number of heads")
+        self.hidden = hidden
+        self.heads = heads
+        self.node_encoder = nn.Sequential(nn.Linear(node_dim, hidden), nn.ReLU(), nn.Linear(hidden, hidden))
+        self.edge_encoder = nn.Sequential(nn.Linear(edge_dim, hidden), nn.ReLU(), nn.Linear(hidden, hidden))
+        self.angle_encoder = nn.Sequential(nn.Linear(angle_dim, hidden), nn.ReLU(),
+                                           nn.Linear(hidden, hidden)) if angle_dim > 0 else None
+        self.edge_blocks = nn.ModuleList([EdgeUpdateBlock(hidden, heads, dropout) for _ in range(layers)])
+        self.node_blocks = nn.ModuleList([NodeUpdateBlock(hidden, hidden, heads, dropout) for _ in range(layers)])
+        self.dropout = nn.Dropout(dropout)
+        self.feat_proj = nn.Sequential(nn.Linear(hidden + global_dim, hidden), nn.ReLU(), nn.Dropout(dropout))
+        self.output_heads = nn.ModuleList([nn.Linear(hidden, 1) for _ in range(target_dim)])
+        self.compute_dtype: Optional[torch.dtype] = None   # None: follow torch.autocast
+        self.validate_indices = False                       # True: synchronising index-range check per batch
+
+    # -- trunk shared by forward / embed of both regressors ------------------------------------------------
+    def trunk(self, data, compute_dtype: Optional[torch.dtype] = None) -> Tensor:
+        cd = _ambient_dtype(compute_dtype if compute_dtype is not None else self.compute_dtype)
+        x = data.x
+        if not x.is_cuda:
+            raise RuntimeError("gnn_elasticity_predictor_b200 runs on CUDA (sm_100a) only; move the batch to the "
+                               "GPU first -- there is no CPU fallback path")
+        n_atoms, n_bonds = x.size(0), data.edge_index.size(1)
+        n_angles = data.lg_edge_index.size(1)
+        dev = x.device
+        with torch.autocast("cuda", enabled=False):
+            node_state = _mlp2(self.node_encoder, x, cd).float()
+            if data.edge_attr.numel() > 0:
+                edge_state = _mlp2(self.edge_encoder, data.edge_attr, cd).float()
+            else:
+                edge_state = torch.zeros(n_bonds, self.hidden, device=dev)
+            if self.angle_encoder is not None and data.lg_edge_attr.numel() > 0:
+                angle_emb = _mlp2(self.angle_encoder, data.lg_edge_attr, cd)
+            else:
+                angle_emb = torch.zeros(n_angles, self.hidden, device=dev, dtype=cd)
+
+            plans = getattr(data, "_alignn_plans", None)
+            if plans is None:
+                plans = self.build_plans(data)
+            lg_plan, g_plan, pool_plan = plans
+            for edge_block, node_block in zip(self.edge_blocks, self.node_blocks):
+                edge_state = edge_block(edge_state, data.lg_edge_index, angle_emb, plan=lg_plan, compute_dtype=cd)
+                node_state = node_block(node_state, data.edge_index, edge_state, plan=g_plan, compute_dtype=cd)
+
+            pooled = ops.segment_mean(node_state, pool_plan)
+            n_graphs = pooled.size(0)
+            global_x = data.global_x
+            if global_x.dim() == 1:
+                global_x = global_x.unsqueeze(0)
+            sg = data.sg_one_hot
+            if sg.dim() == 1:
+                sg = sg.unsqueeze(0)
+            feats = torch.cat([pooled, global_x.reshape(n_graphs, -1).float(), sg.reshape(n_graphs, -1).float()],
+                              dim=1)
+            shared = F.relu(_linear(self.dropout(feats), self.feat_proj[0], cd))
+            return self.feat_proj[2](shared)
+
+    def build_plans(self, data):
+        """CSR/CSC plans of the line graph and the atom graph + pooling plan: once per batch, reused by all
+        layers and by backward.  Cached on the batch object (``data._alignn_plans``) when possible."""
+        n_atoms, n_bonds = data.x.size(0), data.edge_index.size(1)
+        v = self.validate_indices
+        lg_plan = ops.build_plan(data.lg_edge_index, n_bonds, validate=v) if n_bonds > 0 else None
+        g_plan = ops.build_plan(data.edge_index, n_atoms, validate=v)
+        n_graphs = getattr(data, "num_graphs", None)
+        if n_graphs is None:
+            n_graphs = int(data.batch.max()) + 1 if data.batch.numel() > 0 else 0
+        pool_plan = ops.build_pool_plan(data.batch, int(n_graphs))
+        plans = (lg_plan, g_plan, pool_plan)
+        try:
+            object.__setattr__(data, "_alignn_plans", plans)
+        except Exception:  # noqa: BLE001 -- e.g. a PyG Batch refusing private attributes
+            pass
+        return plans
+
+    def forward(self, data) -> Tensor:
+        shared = self.trunk(data)
+        with torch.autocast("cuda", enabled=False):
+            w = torch.cat([h.weight for h in self.output_heads], dim=0).to(shared.dtype)
+            b = torch.cat([h.bias for h in self.output_heads], dim=0).to(shared.dtype)
+            return F.linear(shared, w, b)
+
+
+class HeteroAlignnRegressor(nn.Module):
+    """Wraps the trunk with per-target mean and log-variance heads (reference ``train.py:528-586``)."""
+
+    def __init__(self, base: AlignnRegressor, target_dim: int):
+        super().__init__()
+        self.base = base
+        width = base.feat_proj[0].out_features
+        self.mean_heads = nn.ModuleList([nn.Linear(width, 1) for _ in range(target_dim)])
+        self.logvar_heads = nn.ModuleList([nn.Linear(width, 1) for _ in range(target_dim)])
+
+    def _shared(self, data) -> Tensor:
+        return self.base.trunk(data)
+
+    def embed(self, data) -> Tensor:
+        return self._shared(data)
+
+    def forward(self, data) -> Tuple[Tensor, Tensor]:
+        shared = self._shared(data)
+        t = len(self.mean_heads)
+        with torch.autocast("cuda", enabled=False):
+            heads = list(self.mean_heads) + list(self.logvar_heads)
+            w = torch.cat([h.weight for h in heads], dim=0).to(shared.dtype)
+            b = torch.cat([h.bias for h in heads], dim=0).to(shared.dtype)
+            out = F.linear(shared, w, b)
+        return out[:, :t], out[:, t:]
+
+
+def gaussian_nll_loss(mean: Tensor, logvar: Tensor, target_z: Tensor, log_sigma_l2: float = 0.1,
+                      min_logvar_floor: float = -2.9) -> Tensor:
+    """The training loss of the reference's ``train_epoch_hetero`` without sample weights
+    (``scripts/train.py:655-681``; ``--log-sigma-l2`` default 0.1 at ``:1164``, floor ``:39``)."""
+    lv = torch.clamp(logvar, min=min_logvar_floor)
+    diff = mean - target_z.to(mean.dtype)
+    nll = 0.5 * (lv + diff.pow(2) / torch.exp(lv))
+    loss = nll.mean(dim=1).mean()
+    if log_sigma_l2 > 0.0:
+        loss = loss + float(log_sigma_l2) * (0.5 * lv).pow(2).mean()
+    return loss

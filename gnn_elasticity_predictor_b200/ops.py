@@ -1,0 +1,272 @@
+"""Autograd operators over the C ABI (``include/alignn_b200.h``).
+
+PyTorch is plumbing here: it owns device memory and the stream; every operator below is a thin
+``torch.autograd.Function`` that hands raw device pointers to ``libalignn_b200.so``.  No operator
+has a CPU, eager-PyTorch or Triton fallback -- non-CUDA inputs raise ``RuntimeError``.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+_DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+
+
+def _p(t: Optional[Tensor]):
+    if t is None or t.numel() == 0:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(*tensors: Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "gnn_elasticity_predictor_b200 runs on CUDA (sm_100a) only: got a "
+                f"{t.device.type} tensor and there is no CPU fallback path")
+
+
+def _dtype_code(t: Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise RuntimeError(f"unsupported operand dtype {t.dtype}: use float32 or bfloat16") from None
+
+
+def next_dropout_key() -> Tuple[int, int]:
+    """(seed, offset) for one dropout mask, drawn from torch's CPU generator (no device sync), so
+    ``torch.manual_seed`` makes training runs reproducible."""
+    r = torch.empty(2, dtype=torch.int64).random_()
+    return int(r[0]) & 0x7FFFFFFFFFFFFFFF, int(r[1]) & 0x7FFFFFFFFFFFFFFF
+
+
+# --------------------------------------------------------------------------------------------------
+# graph plan
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class GraphPlan:
+    """CSR (by target) + CSC (by source) views of one edge list; built once per batch."""
+    rowptr: Tensor
+    col: Tensor
+    eid: Tensor
+    rowptr_t: Tensor
+    col_t: Tensor
+    eid_t: Tensor
+    status: Tensor
+    n_nodes: int
+    n_edges: int
+
+    def check(self) -> None:
+        """Synchronising validation: raises if any edge referenced a node outside ``[0, n_nodes)``."""
+        if int(self.status.item()) != 0:
+            raise IndexError(f"edge_index contains indices outside [0, {self.n_nodes})")
+
+
+def build_plan(edge_index: Tensor, n_nodes: int, validate: bool = False) -> GraphPlan:
+    """Stable target-sort / source-sort of ``edge_index`` (int64 ``[2, E]``) on the device."""
+    _require_cuda(edge_index)
+    if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.size(0) != 2:
+        raise RuntimeError("edge_index must be an int64 tensor of shape [2, E]")
+    lib = _lib.load()
+    ei = edge_index.contiguous()
+    n_edges = int(ei.size(1))
+    n_nodes = int(n_nodes)
+    dev = ei.device
+    i32 = dict(dtype=torch.int32, device=dev)
+    rowptr = torch.empty(n_nodes + 1, **i32)
+    rowptr_t = torch.empty(n_nodes + 1, **i32)
+    col, eid, col_t, eid_t = (torch.empty(max(n_edges, 1), **i32) for _ in range(4))
+    status = torch.empty(1, **i32)
+    ws_bytes = int(lib.alignn_plan_workspace_bytes(n_edges, n_nodes))
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.alignn_build_plan(_p(ei), n_edges, n_nodes, _p(rowptr), _p(col), _p(eid), _p(rowptr_t),
+                                   _p(col_t), _p(eid_t), _p(status), _p(ws), ws_bytes, _stream())
+    _lib.check(rc, "alignn_build_plan")
+    plan = GraphPlan(rowptr, col[:n_edges], eid[:n_edges], rowptr_t, col_t[:n_edges], eid_t[:n_edges], status,
+                     n_nodes, n_edges)
+    if validate:
+        plan.check()
+    return plan
+
+
+# --------------------------------------------------------------------------------------------------
+# fused conv core
+# --------------------------------------------------------------------------------------------------
+class _ConvCore(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q: Tensor, k: Tensor, v: Tensor, e: Tensor, plan: GraphPlan, heads: int, p_drop: float,
+                seed: int, offset: int):
+        _require_cuda(q, k, v, e)
+        lib = _lib.load()
+        q, k, v, e = (t.contiguous() for t in (q, k, v, e))
+        if not (q.dtype == k.dtype == v.dtype == e.dtype):
+            raise RuntimeError("q, k, v, e must share one dtype")
+        n_nodes, hidden = q.shape
+        n_edges = int(e.size(0))
+        if n_nodes != plan.n_nodes or n_edges != plan.n_edges:
+            raise RuntimeError(f"plan is for {plan.n_nodes} nodes / {plan.n_edges} edges, operands have "
+                               f"{n_nodes} / {n_edges}")
+        f32 = dict(dtype=torch.float32, device=q.device)
+        agg = torch.empty(n_nodes, hidden, **f32)
+        stat_m = torch.empty(n_nodes, heads, **f32)
+        stat_z = torch.empty(n_nodes, heads, **f32)
+        with torch.cuda.device(q.device):
+            rc = lib.alignn_conv_fwd(_p(q), _p(k), _p(v), _p(e), _p(plan.rowptr), _p(plan.col), _p(plan.eid),
+                                     _p(agg), _p(stat_m), _p(stat_z), n_nodes, n_edges, hidden, heads,
+                                     _dtype_code(q), float(p_drop), seed, offset, _stream())
+        _lib.check(rc, "alignn_conv_fwd")
+        ctx.save_for_backward(q, k, v, e, agg, stat_m, stat_z)
+        ctx.plan, ctx.heads, ctx.p_drop, ctx.seed, ctx.offset = plan, heads, float(p_drop), seed, offset
+        return agg
+
+    @staticmethod
+    def backward(ctx, dagg: Tensor):
+        lib = _lib.load()
+        q, k, v, e, agg, stat_m, stat_z = ctx.saved_tensors
+        plan = ctx.plan
+        n_nodes, hidden = q.shape
+        n_edges = int(e.size(0))
+        dagg = dagg.contiguous().float()
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        de = torch.empty_like(e)
+        coef = torch.empty(max(n_edges, 1), 2 * ctx.heads, dtype=torch.float32, device=q.device)
+        with torch.cuda.device(q.device):
+            rc = lib.alignn_conv_bwd(_p(dagg), _p(agg), _p(q), _p(k), _p(v), _p(e), _p(stat_m), _p(stat_z),
+                                     _p(plan.rowptr), _p(plan.col), _p(plan.eid), _p(plan.rowptr_t), _p(plan.col_t),
+                                     _p(plan.eid_t), _p(dq), _p(dk), _p(dv), _p(de), _p(coef), n_nodes, n_edges,
+                                     hidden, ctx.heads, _dtype_code(q), ctx.p_drop, ctx.seed, ctx.offset, _stream())
+        _lib.check(rc, "alignn_conv_bwd")
+        return dq, dk, dv, de, None, None, None, None, None
+
+
+def conv_core(q: Tensor, k: Tensor, v: Tensor, e: Tensor, plan: GraphPlan, heads: int, p_drop: float = 0.0,
+              seed: int = 0, offset: int = 0) -> Tensor:
+    """``agg[i] = sum_j softmax_i(<q_i, k_j + e_ij>/sqrt(C)) (v_j + e_ij)`` per head; returns fp32 ``[N, H]``."""
+    return _ConvCore.apply(q, k, v, e, plan, int(heads), float(p_drop), int(seed), int(offset))
+
+
+# --------------------------------------------------------------------------------------------------
+# beta gate + LayerNorm + ReLU + dropout + residual
+# --------------------------------------------------------------------------------------------------
+class _GateLn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, agg: Tensor, xr: Tensor, x: Tensor, wbeta: Tensor, gamma: Tensor, bias: Tensor, eps: float,
+                p_drop: float, seed: int, offset: int, want_lp: bool):
+        _require_cuda(agg, xr, x, wbeta, gamma, bias)
+        lib = _lib.load()
+        agg = agg.contiguous().float()
+        xr = xr.contiguous()
+        x = x.contiguous().float()
+        wb = wbeta.detach().reshape(-1).contiguous().float()
+        gm, bs = gamma.detach().contiguous().float(), bias.detach().contiguous().float()
+        n_rows, hidden = agg.shape
+        f32 = dict(dtype=torch.float32, device=agg.device)
+        y = torch.empty(n_rows, hidden, **f32)
+        y_lp = torch.empty(n_rows, hidden, dtype=xr.dtype, device=agg.device) if want_lp else None
+        beta, mean, rstd = (torch.empty(n_rows, **f32) for _ in range(3))
+        with torch.cuda.device(agg.device):
+            rc = lib.alignn_gate_ln_fwd(_p(agg), _p(xr), _p(x), _p(wb), _p(gm), _p(bs), _p(y), _p(y_lp), _p(beta),
+                                        _p(mean), _p(rstd), n_rows, hidden, _dtype_code(xr), float(eps),
+                                        float(p_drop), seed, offset, _stream())
+        _lib.check(rc, "alignn_gate_ln_fwd")
+        ctx.save_for_backward(agg, xr, wb, gm, bs, beta, mean, rstd)
+        ctx.p_drop, ctx.seed, ctx.offset = float(p_drop), seed, offset
+        ctx.wbeta_shape, ctx.param_dtypes = wbeta.shape, (wbeta.dtype, gamma.dtype, bias.dtype)
+        if want_lp:
+            return y, y_lp
+        return y, None
+
+    @staticmethod
+    def backward(ctx, dy: Tensor, dy_lp: Optional[Tensor]):
+        lib = _lib.load()
+        agg, xr, wb, gm, bs, beta, mean, rstd = ctx.saved_tensors
+        n_rows, hidden = agg.shape
+        if dy is None:
+            dy = torch.zeros_like(agg)
+        dy = dy.contiguous().float()
+        if dy_lp is not None:
+            dy = dy + dy_lp.float()
+        f32 = dict(dtype=torch.float32, device=agg.device)
+        dagg = torch.empty(n_rows, hidden, **f32)
+        dxr = torch.empty_like(xr)
+        partials = torch.empty(int(lib.alignn_gate_ln_bwd_partial_rows()) * 5 * hidden, **f32)
+        dparams = torch.empty(5 * hidden, **f32)
+        with torch.cuda.device(agg.device):
+            rc = lib.alignn_gate_ln_bwd(_p(dy), _p(agg), _p(xr), _p(wb), _p(gm), _p(bs), _p(beta), _p(mean),
+                                        _p(rstd), _p(dagg), _p(dxr), _p(partials), _p(dparams), n_rows, hidden,
+                                        _dtype_code(xr), ctx.p_drop, ctx.seed, ctx.offset, _stream())
+        _lib.check(rc, "alignn_gate_ln_bwd")
+        wdt, gdt, bdt = ctx.param_dtypes
+        dwbeta = dparams[:3 * hidden].reshape(ctx.wbeta_shape).to(wdt)
+        dgamma = dparams[3 * hidden:4 * hidden].to(gdt)
+        dbias = dparams[4 * hidden:].to(bdt)
+        return dagg, dxr, dy, dwbeta, dgamma, dbias, None, None, None, None, None
+
+
+def gate_ln_relu_residual(agg: Tensor, xr: Tensor, x: Tensor, wbeta: Tensor, gamma: Tensor, bias: Tensor,
+                          eps: float = 1e-5, p_drop: float = 0.0, seed: int = 0, offset: int = 0,
+                          want_lp: bool = False):
+    """``x + dropout(relu(LayerNorm(beta*xr + (1-beta)*agg)))`` with ``beta = sigmoid(wbeta . [agg, xr, agg-xr])``.
+
+    Returns ``(y_fp32, y_lowprecision_or_None)``."""
+    return _GateLn.apply(agg, xr, x, wbeta, gamma, bias, float(eps), float(p_drop), int(seed), int(offset),
+                         bool(want_lp))
+
+
+# --------------------------------------------------------------------------------------------------
+# per-graph mean pooling
+# --------------------------------------------------------------------------------------------------
+class _SegmentMean(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, plan: GraphPlan):
+        _require_cuda(x)
+        lib = _lib.load()
+        x = x.contiguous().float()
+        n_graphs, hidden = plan.n_nodes, int(x.size(1))
+        pooled = torch.empty(n_graphs, hidden, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = lib.alignn_segment_mean_fwd(_p(x), _p(plan.rowptr), _p(plan.eid), _p(pooled), n_graphs, hidden,
+                                             _stream())
+        _lib.check(rc, "alignn_segment_mean_fwd")
+        ctx.plan, ctx.n_rows = plan, int(x.size(0))
+        return pooled
+
+    @staticmethod
+    def backward(ctx, dpooled: Tensor):
+        lib = _lib.load()
+        plan = ctx.plan
+        dpooled = dpooled.contiguous().float()
+        hidden = int(dpooled.size(1))
+        dx = torch.zeros(ctx.n_rows, hidden, dtype=torch.float32, device=dpooled.device)
+        with torch.cuda.device(dpooled.device):
+            rc = lib.alignn_segment_mean_bwd(_p(dpooled), _p(plan.rowptr), _p(plan.eid), _p(dx), plan.n_nodes,
+                                             hidden, _stream())
+        _lib.check(rc, "alignn_segment_mean_bwd")
+        return dx, None
+
+
+def build_pool_plan(batch: Tensor, num_graphs: int) -> GraphPlan:
+    """Plan over the ``batch`` vector (key = graph id) for :func:`segment_mean`."""
+    _require_cuda(batch)
+    n = int(batch.numel())
+    idx = torch.stack([torch.arange(n, device=batch.device, dtype=torch.int64), batch.to(torch.int64)])
+    # keys (row 1) live in [0, num_graphs); the "source" row holds node ids in [0, n): plan over max(n, B)
+    plan = build_plan(idx, max(n, int(num_graphs)))
+    plan.n_nodes = int(num_graphs)
+    return plan
+
+
+def segment_mean(x: Tensor, pool_plan: GraphPlan) -> Tensor:
+    """``global_mean_pool``: per-graph mean of node rows (fp32 ``[B, H]``)."""
+    return _SegmentMean.apply(x, pool_plan)
