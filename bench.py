@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""Benchmark of the ALIGNN message-passing hot path (BASELINE.json metric: train graphs/sec, fwd+bwd).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One step = one ensemble member's forward + Gaussian-NLL loss + backward (+ gradient all-reduce for N>1,
++ clip + AdamW) on one batch of synthetic crystals of BASELINE config 2's shape (256 x 32-atom cells,
+12 neighbours: N=8 192 atoms, E=98 304 bonds, L=1 081 344 angles; default arch H=256, 4+4 layers,
+4 heads; bf16 autocast).  Members cycle across steps (5-member ensemble, trained sequentially in the
+reference, train.py:2052).  N>1: weak scaling -- every rank runs its own 256-graph shard (N=8 is
+BASELINE config 3's global batch of 2 048), one NCCL all-reduce of the flat gradient bucket per step.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ALIGNN train graphs/sec (fwd+bwd)"
+UNIT = "graphs/s"
+ARCH = dict(node_dim=206, edge_dim=36, angle_dim=11, global_dim=289, target_dim=2, hidden=256, layers=4, heads=4)
+WORKLOADS = {
+    # name: (graphs per GPU, atoms per cell, neighbours)
+    "config2": (256, 32, 12),
+    "config1": (64, 16, 12),
+    "config4": (256, 200, 16),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="config2")
+    ap.add_argument("--lg-inc", choices=["pyg", "bonds"], default="pyg")
+    ap.add_argument("--dropout", type=float, default=0.15, help="reference default (train.py:1479)")
+    ap.add_argument("--dtype", choices=["bf16", "fp32"], default="bf16")
+    ap.add_argument("--members", type=int, default=5)
+    ap.add_argument("--cpu-sample-graphs", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-optimizer", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# algorithmic bytes of the conv core
+# ---------------------------------------------------------------------------------------------------------
+def conv_bytes(n_nodes, n_edges, hidden, heads, s, fwd=True):
+    so = 4
+    if fwd:
+        return s * hidden * (3 * n_nodes + n_edges) + so * hidden * n_nodes + 8 * heads * n_nodes + 4 * (2 * n_edges + n_nodes + 1)
+    return (s * hidden * (3 * n_nodes + n_edges) + so * hidden * n_nodes + s * hidden * (3 * n_nodes + n_edges)
+            + 8 * heads * n_nodes + 4 * (4 * n_edges + 2 * n_nodes))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's CPU path
+# ---------------------------------------------------------------------------------------------------------
+def run_cpu_reference(n_graphs, atoms, k, lg_inc, steps, warmup, threads=None):
+    """Times forward + loss + backward of the reference model on host cores (fp32, dropout 0).
+    Uses the reference's own classes when /root/reference is mounted (build container), else the
+    own-code port oracle/model_ref.py (the GPU box) -- `kind` says which."""
+    import oracle
+    from oracle import model_ref
+    from gnn_elasticity_predictor_b200.synthetic import synthetic_batch, zscore_targets
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    ref = oracle.load_reference_train_module()
+    kind = "reference" if ref is not None else "port"
+    torch.manual_seed(42)
+    if ref is not None:
+        model = ref.HeteroAlignnRegressor(ref.AlignnRegressor(dropout=0.0, **ARCH), ARCH["target_dim"])
+    else:
+        model = model_ref.HeteroAlignnRegressor(model_ref.AlignnRegressor(dropout=0.0, **ARCH), ARCH["target_dim"])
+    model.train()
+    batch = synthetic_batch(n_graphs, atoms, k, seed=0, lg_inc=lg_inc)
+    tz = zscore_targets(batch.y, batch.num_graphs)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        model.zero_grad(set_to_none=True)
+        mean, logvar = model(batch)
+        loss = model_ref.gaussian_nll_loss(mean, logvar, tz)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    med = statistics.median(times)
+    return {"value": n_graphs / med, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": f"{n_graphs} graphs x {atoms} atoms x {k} nbrs per step (L={batch.sizes['L']}), fp32, "
+                      f"{warmup} warm-up + {steps} timed fwd+loss+bwd, median",
+            "ms_per_step": med * 1e3}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_graphs, atoms, k = WORKLOADS[args.workload]
+    sample = min(args.cpu_sample_graphs, n_graphs)
+    steps = max(1, min(args.steps, 5))
+    warmup = max(1, min(args.warmup, 2))
+    res = run_cpu_reference(sample, atoms, k, args.lg_inc, steps, warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {n_graphs} graphs x {atoms}-atom cells x {k} nbrs per GPU "
+                               f"(bounded CPU sample: {sample} graphs per step)", "arch": ARCH, "lg_inc": args.lg_inc},
+        "cpu_baseline": {k2: res[k2] for k2 in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------------
+def main_b200(args):
+    import torch.distributed as dist
+    import gnn_elasticity_predictor_b200 as pkg
+    from gnn_elasticity_predictor_b200 import dp, ops
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device: the hot path has no CPU fallback")
+    rank, local_rank, world = dp.init_from_env("nccl")
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    n_graphs, atoms, k = WORKLOADS[args.workload]
+    cd = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+
+    # members (reference: --ensemble-size 5, seeds seed + 1007*i, train.py:2053)
+    members, buckets, optims = [], [], []
+    for m in range(args.members):
+        torch.manual_seed(42 + 1007 * m)
+        model = pkg.HeteroAlignnRegressor(pkg.AlignnRegressor(dropout=args.dropout, **ARCH), ARCH["target_dim"]).to(dev)
+        model.base.compute_dtype = cd
+        model.train()
+        members.append(model)
+        buckets.append(dp.FlatGradBucket(model.parameters()))
+        optims.append(torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True))
+
+    host_batches = [pkg.synthetic_batch(n_graphs, atoms, k, seed=1000 * rank + i, lg_inc=args.lg_inc).pin_memory()
+                    for i in range(2)]
+    sizes = host_batches[0].sizes
+    dev_batch = host_batches[0].to(dev)
+    target_z = pkg.zscore_targets(dev_batch.y, dev_batch.num_graphs)
+    loss_scale = 1.0 / world
+
+    def step(i, batch, tz):
+        m = i % args.members
+        model, bucket = members[m], buckets[m]
+        bucket.zero()
+        model.base.build_plans(batch)                 # CSR/CSC sort of this batch: part of every step
+        mean, logvar = model(batch)
+        loss = pkg.gaussian_nll_loss(mean.float(), logvar.float(), tz)
+        (loss * loss_scale).backward()
+        if world > 1:
+            bucket.all_reduce()
+        if not args.no_optimizer:
+            dp.global_grad_clip(bucket, 5.0)
+            optims[m].step()
+        return loss, mean, logvar
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing -----------------------------------------------------------------------------
+    for i in range(args.warmup):
+        step(i, dev_batch, target_z)
+    barrier()
+    ops.STATS.reset()
+    ops.STATS.events = True
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    for i in range(args.steps):
+        step(i, dev_batch, target_z)
+    t1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ops.STATS.events = False
+    elapsed_ms = t0.elapsed_time(t1)
+    launches = ops.STATS.kernels
+    durations = ops.STATS.durations_ms()
+    t = torch.tensor([elapsed_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = n_graphs * world * args.steps / (elapsed_ms / 1e3)
+
+    # ---- roofline of the dominant hand-written kernel (line-graph conv) ----------------------------------------
+    peak, peak_src = load_peaks()
+    s_bytes = 2 if cd == torch.bfloat16 else 4
+    kern = {}
+    for name in ("conv_fwd", "conv_bwd"):
+        recs = [(ms, meta) for ms, meta in durations.get(name, []) if meta and meta[1] == sizes["L"]]
+        if recs:
+            ms = statistics.mean(r[0] for r in recs)
+            nn_, ne_, h_, hd_, _ = recs[0][1]
+            b = conv_bytes(nn_, ne_, h_, hd_, s_bytes, fwd=(name == "conv_fwd"))
+            kern[name] = {"ms": ms, "bytes": b, "gbs": b / (ms * 1e-3) / 1e9, "launches_timed": len(recs)}
+    totals = {name: sum(ms for ms, _ in v) / args.steps for name, v in durations.items()}
+    roofline = None
+    if kern:
+        dom = max(kern, key=lambda n: kern[n]["ms"])
+        roofline = {"kernel": f"alignn_{dom} (line-graph conv, Nn={sizes['E']}, Ne={sizes['L']})", "bound": "hbm",
+                    "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": kern[dom]["gbs"] / peak,
+                    "peak_source": peak_src, "traffic": None, "algorithmic_bytes": kern[dom]["bytes"],
+                    "avg_launch_ms": kern[dom]["ms"],
+                    "others": {n: {"GB/s": round(v["gbs"], 1), "frac": round(v["gbs"] / peak, 4), "ms": round(v["ms"], 4)}
+                               for n, v in kern.items() if n != dom}}
+
+    # ---- end to end through the public API with host buffers -------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        copy_stream = torch.cuda.Stream()
+        main_stream = torch.cuda.current_stream()
+        h2d = host_batches[0].nbytes()
+        out_host = torch.empty(1 + 4 * n_graphs, dtype=torch.float32).pin_memory()
+
+        def upload(i):
+            with torch.cuda.stream(copy_stream):
+                b = host_batches[i % 2].to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return b, ev
+
+        def e2e_loop(n_steps):
+            nxt = upload(0)
+            for i in range(n_steps):
+                b, ev = nxt
+                main_stream.wait_event(ev)
+                if i + 1 < n_steps:
+                    nxt = upload(i + 1)            # next batch's H2D overlaps this step's compute
+                tz = pkg.zscore_targets(b.y, b.num_graphs)
+                loss, mean, logvar = step(i, b, tz)
+                packed = torch.cat([loss.detach().float().reshape(1), mean.detach().float().reshape(-1),
+                                    logvar.detach().float().reshape(-1)])
+                out_host.copy_(packed, non_blocking=True)
+                for tns in b.tensors().values():
+                    tns.record_stream(main_stream)
+                main_stream.synchronize()           # the trainer reads the loss every step (train.py:683-688)
+
+        e2e_loop(min(3, args.warmup))
+        barrier()
+        w0 = time.perf_counter()
+        e2e_loop(args.steps)
+        barrier()
+        w = time.perf_counter() - w0
+        tw = torch.tensor([w], device=dev)
+        if world > 1:
+            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        e2e = {"value": n_graphs * world * args.steps / float(tw.item()), "unit": UNIT,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_host.numel() * 4,
+               "ms_per_step": float(tw.item()) / args.steps * 1e3,
+               "how": "pinned host batch -> H2D (copy stream, next batch overlapped) -> plan + fwd + loss + bwd"
+                      + ("" if args.no_optimizer else " + clip + AdamW") + " -> D2H loss/mean/logvar + sync, every step"}
+
+    # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        res = run_cpu_reference(min(args.cpu_sample_graphs, n_graphs), atoms, k, args.lg_inc, steps=3, warmup=1)
+        cpu = {k2: res[k2] for k2 in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {
+                "workload": f"{args.workload}: {n_graphs} graphs x {atoms}-atom cells x {k} nbrs per GPU "
+                            f"(N={sizes['N']}, E={sizes['E']}, L={sizes['L']}), one ensemble member per step, "
+                            f"{args.members} members cycled",
+                "arch": ARCH, "dropout": args.dropout, "lg_inc": args.lg_inc, "global_batch": n_graphs * world,
+                "parallelism": f"dp{world}" if world > 1 else "single",
+                "step": "plan(CSR/CSC sort) + fwd + Gaussian NLL + bwd" + (" + NCCL allreduce(flat grads)" if world > 1 else "")
+                        + ("" if args.no_optimizer else " + global-norm clip 5.0 + AdamW(fused)"),
+                "l2": "per-step working set (>= 3 GB of edge projections) >> 126 MB L2; no explicit flush",
+                "projections": "cuBLAS via torch (bf16)" if cd == torch.bfloat16 else "cuBLAS via torch (fp32, TF32 off)",
+            },
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "kernel_ms_per_step": {k2: round(v, 4) for k2, v in sorted(totals.items())},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_b200(a)

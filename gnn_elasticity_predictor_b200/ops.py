@@ -43,6 +43,63 @@ def _dtype_code(t: Tensor) -> int:
         raise RuntimeError(f"unsupported operand dtype {t.dtype}: use float32 or bfloat16") from None
 
 
+# --------------------------------------------------------------------------------------------------
+# launch accounting + optional CUDA-event profiler (used by bench.py; zero cost when disabled)
+# --------------------------------------------------------------------------------------------------
+class LaunchStats:
+    """Counts kernels launched through the C ABI and, when ``events`` is on, brackets every call with
+    CUDA events on the launching stream so that per-kernel durations can be read after a sync."""
+
+    def __init__(self):
+        self.kernels = 0
+        self.calls = 0
+        self.events = False
+        self.records = []   # (name, meta, start_event, end_event)
+
+    def reset(self):
+        self.kernels = self.calls = 0
+        self.records = []
+
+    def durations_ms(self):
+        """name -> list of (ms, meta); call after torch.cuda.synchronize()."""
+        out = {}
+        for name, meta, a, b in self.records:
+            out.setdefault(name, []).append((a.elapsed_time(b), meta))
+        return out
+
+
+STATS = LaunchStats()
+
+
+class _Launch:
+    __slots__ = ("name", "n", "meta", "start")
+
+    def __init__(self, name: str, n_kernels: int, meta=None):
+        self.name, self.n, self.meta, self.start = name, n_kernels, meta, None
+
+    def __enter__(self):
+        STATS.kernels += self.n
+        STATS.calls += 1
+        if STATS.events:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.start is not None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
+            STATS.records.append((self.name, self.meta, self.start, end))
+        return False
+
+
+def _plan_kernels(n_edges: int, n_nodes: int) -> int:
+    if n_edges == 0:
+        return 0
+    passes = (max(int(n_nodes), 1).bit_length() + 7) // 8
+    return 1 + 2 * (4 * passes + 2)
+
+
 def next_dropout_key() -> Tuple[int, int]:
     """(seed, offset) for one dropout mask, drawn from torch's CPU generator (no device sync), so
     ``torch.manual_seed`` makes training runs reproducible."""
@@ -89,7 +146,7 @@ def build_plan(edge_index: Tensor, n_nodes: int, validate: bool = False) -> Grap
     status = torch.empty(1, **i32)
     ws_bytes = int(lib.alignn_plan_workspace_bytes(n_edges, n_nodes))
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _Launch("build_plan", _plan_kernels(n_edges, n_nodes), (n_nodes, n_edges)):
         rc = lib.alignn_build_plan(_p(ei), n_edges, n_nodes, _p(rowptr), _p(col), _p(eid), _p(rowptr_t),
                                    _p(col_t), _p(eid_t), _p(status), _p(ws), ws_bytes, _stream())
     _lib.check(rc, "alignn_build_plan")
@@ -121,7 +178,7 @@ class _ConvCore(torch.autograd.Function):
         agg = torch.empty(n_nodes, hidden, **f32)
         stat_m = torch.empty(n_nodes, heads, **f32)
         stat_z = torch.empty(n_nodes, heads, **f32)
-        with torch.cuda.device(q.device):
+        with torch.cuda.device(q.device), _Launch("conv_fwd", 1, (n_nodes, n_edges, hidden, heads, q.element_size())):
             rc = lib.alignn_conv_fwd(_p(q), _p(k), _p(v), _p(e), _p(plan.rowptr), _p(plan.col), _p(plan.eid),
                                      _p(agg), _p(stat_m), _p(stat_z), n_nodes, n_edges, hidden, heads,
                                      _dtype_code(q), float(p_drop), seed, offset, _stream())
@@ -141,7 +198,7 @@ class _ConvCore(torch.autograd.Function):
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
         de = torch.empty_like(e)
         coef = torch.empty(max(n_edges, 1), 2 * ctx.heads, dtype=torch.float32, device=q.device)
-        with torch.cuda.device(q.device):
+        with torch.cuda.device(q.device), _Launch("conv_bwd", 2, (n_nodes, n_edges, hidden, ctx.heads, q.element_size())):
             rc = lib.alignn_conv_bwd(_p(dagg), _p(agg), _p(q), _p(k), _p(v), _p(e), _p(stat_m), _p(stat_z),
                                      _p(plan.rowptr), _p(plan.col), _p(plan.eid), _p(plan.rowptr_t), _p(plan.col_t),
                                      _p(plan.eid_t), _p(dq), _p(dk), _p(dv), _p(de), _p(coef), n_nodes, n_edges,
@@ -175,7 +232,7 @@ class _GateLn(torch.autograd.Function):
         y = torch.empty(n_rows, hidden, **f32)
         y_lp = torch.empty(n_rows, hidden, dtype=xr.dtype, device=agg.device) if want_lp else None
         beta, mean, rstd = (torch.empty(n_rows, **f32) for _ in range(3))
-        with torch.cuda.device(agg.device):
+        with torch.cuda.device(agg.device), _Launch("gate_ln_fwd", 1, (n_rows, hidden, xr.element_size())):
             rc = lib.alignn_gate_ln_fwd(_p(agg), _p(xr), _p(x), _p(wb), _p(gm), _p(bs), _p(y), _p(y_lp), _p(beta),
                                         _p(mean), _p(rstd), n_rows, hidden, _dtype_code(xr), float(eps),
                                         float(p_drop), seed, offset, _stream())
@@ -202,7 +259,7 @@ class _GateLn(torch.autograd.Function):
         dxr = torch.empty_like(xr)
         partials = torch.empty(int(lib.alignn_gate_ln_bwd_partial_rows()) * 5 * hidden, **f32)
         dparams = torch.empty(5 * hidden, **f32)
-        with torch.cuda.device(agg.device):
+        with torch.cuda.device(agg.device), _Launch("gate_ln_bwd", 2, (n_rows, hidden, xr.element_size())):
             rc = lib.alignn_gate_ln_bwd(_p(dy), _p(agg), _p(xr), _p(wb), _p(gm), _p(bs), _p(beta), _p(mean),
                                         _p(rstd), _p(dagg), _p(dxr), _p(partials), _p(dparams), n_rows, hidden,
                                         _dtype_code(xr), ctx.p_drop, ctx.seed, ctx.offset, _stream())
@@ -235,7 +292,7 @@ class _SegmentMean(torch.autograd.Function):
         x = x.contiguous().float()
         n_graphs, hidden = plan.n_nodes, int(x.size(1))
         pooled = torch.empty(n_graphs, hidden, dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
+        with torch.cuda.device(x.device), _Launch("segment_mean_fwd", 1):
             rc = lib.alignn_segment_mean_fwd(_p(x), _p(plan.rowptr), _p(plan.eid), _p(pooled), n_graphs, hidden,
                                              _stream())
         _lib.check(rc, "alignn_segment_mean_fwd")
@@ -249,7 +306,7 @@ class _SegmentMean(torch.autograd.Function):
         dpooled = dpooled.contiguous().float()
         hidden = int(dpooled.size(1))
         dx = torch.zeros(ctx.n_rows, hidden, dtype=torch.float32, device=dpooled.device)
-        with torch.cuda.device(dpooled.device):
+        with torch.cuda.device(dpooled.device), _Launch("segment_mean_bwd", 1):
             rc = lib.alignn_segment_mean_bwd(_p(dpooled), _p(plan.rowptr), _p(plan.eid), _p(dx), plan.n_nodes,
                                              hidden, _stream())
         _lib.check(rc, "alignn_segment_mean_bwd")

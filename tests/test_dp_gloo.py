@@ -1,0 +1,108 @@
+"""Host-side data-parallel logic on CPU: world_size-2 gloo.  The compute inside each rank is the oracle model
+(tests may use it); what is under test is sharding, the flat gradient bucket, the single all-reduce, loss
+scaling and the global-norm clip: 2-rank result == 1-rank result on the same global batch."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gnn_elasticity_predictor_b200 import dp
+from gnn_elasticity_predictor_b200.synthetic import collate, make_crystal, zscore_targets
+from gnn_elasticity_predictor_b200.ensemble import ensemble_moments, lognormal_to_linear
+from oracle import model_ref
+
+CTOR = dict(node_dim=206, edge_dim=36, angle_dim=11, global_dim=289, target_dim=2, hidden=32, layers=1, heads=4)
+
+
+def _graphs():
+    gen = torch.Generator().manual_seed(0)
+    return [make_crystal(5 + (i % 3), 4, gen) for i in range(6)]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    torch.set_num_threads(1)
+    r, _, w = dp.init_from_env("gloo")
+    assert (r, w) == (rank, world)
+    graphs = _graphs()
+    weights = [int(g.lg_edge_index.size(1)) for g in graphs]
+    lo, hi = dp.shard_ranges(weights, world)[rank]
+    model = model_ref.build_hetero(dropout=0.0, seed=1, **CTOR)
+    bucket = dp.FlatGradBucket(model.parameters())
+    bucket.zero()
+    batch = collate(graphs[lo:hi], lg_inc="bonds")
+    mean, logvar = model(batch)
+    loss = model_ref.gaussian_nll_loss(mean, logvar, zscore_targets(batch.y, batch.num_graphs), log_sigma_l2=0.0)
+    (loss * dp.dp_loss_scale(hi - lo, len(graphs))).backward()
+    bucket.all_reduce()
+    norm = dp.global_grad_clip(bucket, 0.05)
+    torch.save({"flat": bucket.flat.clone(), "norm": norm, "range": (lo, hi)}, os.path.join(out_dir, f"r{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_equals_single_rank(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = (torch.load(tmp_path / f"r{i}.pt") for i in range(2))
+    assert r0["range"][1] == r1["range"][0] and r0["range"][0] == 0 and r1["range"][1] == 6
+    assert torch.equal(r0["flat"], r1["flat"])                     # identical on every rank after the collective
+    # single process, whole batch (log_sigma_l2=0 so that the loss is a plain mean over graphs)
+    graphs = _graphs()
+    model = model_ref.build_hetero(dropout=0.0, seed=1, **CTOR)
+    bucket = dp.FlatGradBucket(model.parameters())
+    bucket.zero()
+    batch = collate(graphs, lg_inc="bonds")
+    mean, logvar = model(batch)
+    model_ref.gaussian_nll_loss(mean, logvar, zscore_targets(batch.y, batch.num_graphs), log_sigma_l2=0.0).backward()
+    norm = dp.global_grad_clip(bucket, 0.05)
+    assert torch.allclose(norm, r0["norm"], rtol=1e-5)
+    assert torch.allclose(bucket.flat, r0["flat"], rtol=1e-4, atol=1e-7)
+    assert float(torch.linalg.vector_norm(bucket.flat)) <= 0.05 * (1 + 1e-5)
+
+
+def test_shard_ranges_balanced_and_contiguous():
+    w = [10] * 8
+    assert dp.shard_ranges(w, 4) == [(0, 2), (2, 4), (4, 6), (6, 8)]
+    r = dp.shard_ranges([100, 1, 1, 1, 1, 100], 2)
+    assert r[0][0] == 0 and r[-1][1] == 6 and r[0][1] == r[1][0]
+    loads = [sum([100, 1, 1, 1, 1, 100][a:b]) for a, b in r]
+    assert max(loads) <= 104
+    r = dp.shard_ranges([5, 5, 5], 8)
+    assert r[0][0] == 0 and r[-1][1] == 3 and all(a <= b for a, b in r)
+    assert sum(b - a for a, b in r) == 3
+    with pytest.raises(ValueError):
+        dp.shard_ranges(w, 0)
+
+
+def test_flat_bucket_views_and_alignment():
+    model = model_ref.build_hetero(dropout=0.0, seed=0, **CTOR)
+    bucket = dp.FlatGradBucket(model.parameters())
+    assert all(off % 4 == 0 for off in bucket.offsets)
+    for p, off in zip(bucket.params, bucket.offsets):
+        assert p.grad.data_ptr() == bucket.flat.data_ptr() + 4 * off
+    model.zero_grad(set_to_none=True)
+    bucket.zero()
+    assert all(p.grad is not None for p in bucket.params)
+    assert dp.member_placement(5, 8) == {0: [0], 1: [1], 2: [2], 3: [3], 4: [4], 5: [], 6: [], 7: []}
+    assert dp.member_placement(5, 2) == {0: [0, 2, 4], 1: [1, 3]}
+
+
+def test_ensemble_moments_match_oracle():
+    g = torch.Generator().manual_seed(0)
+    means = torch.randn(5, 7, 2, generator=g)
+    logvars = torch.randn(5, 7, 2, generator=g) * 2 - 2
+    mz, vz, sz = ensemble_moments(means, logvars)
+    omz, ovz, osz = model_ref.ensemble_moments(list(means), list(logvars))
+    assert torch.allclose(mz, omz) and torch.allclose(vz, ovz) and torch.allclose(sz, osz)
+    lin_mean, lin_std = lognormal_to_linear(mz, sz, torch.tensor([4.3228, 3.5567]), torch.tensor([0.9051, 0.9405]))
+    assert bool((lin_mean > 0).all()) and bool((lin_std >= 0).all())

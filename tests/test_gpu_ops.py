@@ -1,0 +1,254 @@
+"""GPU parity tests of the individual C-ABI operators against the oracle (run with -m gpu on a B200).
+
+Tolerances (BASELINE.json north_star): graph plan bit-exact; fp32 forward rel 1e-5, gradients rel 1e-4;
+bf16 rel 2e-2.  `rel` = max|a-b| / max|b| (conftest.rel_err)."""
+import math
+
+import pytest
+import torch
+
+import oracle
+from conftest import rel_err
+
+oracle.install_shim()
+from torch_geometric.utils import scatter, softmax  # noqa: E402  (oracle leaf ops)
+
+import gnn_elasticity_predictor_b200 as pkg  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def ref_conv_core(q, k, v, e, index, heads):
+    """oracle: PyG message + softmax + add-aggregation (fp64 on CPU)"""
+    n, hidden = q.shape
+    c = hidden // heads
+    src, dst = index[0], index[1]
+    qi = q.view(n, heads, c)[dst]
+    kj = k.view(n, heads, c)[src] + e.view(-1, heads, c)
+    alpha = softmax((qi * kj).sum(-1) / math.sqrt(c), dst, None, n)
+    msg = (v.view(n, heads, c)[src] + e.view(-1, heads, c)) * alpha.unsqueeze(-1)
+    return scatter(msg, dst, 0, dim_size=n, reduce="sum").view(n, hidden)
+
+
+def random_multigraph(n, e, seed, empty_tail=True):
+    g = torch.Generator().manual_seed(seed)
+    hi = max(1, (3 * n) // 4) if empty_tail else n
+    dst = torch.randint(0, hi, (e,), generator=g)
+    src = torch.randint(0, n, (e,), generator=g)
+    if e >= 6:
+        src[:3] = dst[:3]
+        src[3:6], dst[3:6] = src[0:3].clone(), dst[0:3].clone()
+    return torch.stack([src, dst])
+
+
+# ---- graph plan: bit-exact ----------------------------------------------------------------------------
+@pytest.mark.parametrize("n,e,seed", [(1, 0, 0), (5, 1, 1), (7, 50, 2), (300, 5000, 3), (98304, 1081344, 4),
+                                      (2_000_000, 300_000, 5), (70000, 4097, 6)])
+def test_plan_matches_stable_sort(n, e, seed):
+    index = random_multigraph(n, e, seed)
+    plan = pkg.build_plan(index.to(DEV), n, validate=True)
+    for key_row, other_row, rowptr, col, eid in ((1, 0, plan.rowptr, plan.col, plan.eid),
+                                                 (0, 1, plan.rowptr_t, plan.col_t, plan.eid_t)):
+        _, perm = torch.sort(index[key_row], stable=True)
+        counts = torch.bincount(index[key_row], minlength=n)
+        want_ptr = torch.cat([torch.zeros(1, dtype=torch.long), counts.cumsum(0)])
+        assert torch.equal(rowptr.cpu().long(), want_ptr)
+        assert torch.equal(eid.cpu().long(), perm)
+        assert torch.equal(col.cpu().long(), index[other_row][perm])
+    assert plan.rowptr.dtype == torch.int32 and plan.eid.dtype == torch.int32
+
+
+def test_plan_source_sorted_input_gives_identity_csc():
+    b = pkg.synthetic_batch(4, 16, 12, seed=0, lg_inc="bonds")
+    plan = pkg.build_plan(b.lg_edge_index.to(DEV), b.edge_index.size(1))
+    assert torch.equal(plan.eid_t.cpu().long(), torch.arange(b.lg_edge_index.size(1)))
+
+
+def test_plan_flags_out_of_range_and_drops_those_edges():
+    index = torch.tensor([[0, 1, 9, 2, -1], [1, 2, 0, 7, 0]])
+    plan = pkg.build_plan(index.to(DEV), 3)
+    assert int(plan.status.item()) == 1
+    with pytest.raises(IndexError):
+        plan.check()
+    assert plan.rowptr.cpu().tolist() == [0, 0, 1, 2]          # only edges 0 and 1 are in range
+    assert plan.eid.cpu().tolist()[:2] == [0, 1]
+
+
+# ---- conv core ------------------------------------------------------------------------------------------
+SHAPES = [(256, 4), (256, 1), (256, 8), (128, 4), (64, 4), (32, 1), (32, 4), (16, 2), (8, 1),
+          (48, 3), (96, 4), (40, 5), (320, 4), (512, 4)]
+
+
+@pytest.mark.parametrize("hidden,heads", SHAPES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_conv_core_forward_backward(hidden, heads, dtype):
+    n, e = 37, 400
+    index = random_multigraph(n, e, hidden + heads)
+    g = torch.Generator().manual_seed(1)
+    q, k, v = (torch.randn(n, hidden, generator=g) for _ in range(3))
+    ee = torch.randn(e, hidden, generator=g)
+    gout = torch.randn(n, hidden, generator=g)
+    # round operands to the storage dtype first so that both sides see identical inputs
+    q, k, v, ee = (t.to(dtype).float() for t in (q, k, v, ee))
+    ref_in = [t.double().requires_grad_(True) for t in (q, k, v, ee)]
+    ref = ref_conv_core(*ref_in, index, heads)
+    ref.backward(gout.double())
+
+    plan = pkg.build_plan(index.to(DEV), n)
+    dev_in = [t.to(DEV, dtype).requires_grad_(True) for t in (q, k, v, ee)]
+    out = pkg.conv_core(*dev_in, plan, heads)
+    assert out.dtype == torch.float32
+    out.backward(gout.to(DEV))
+    fwd_tol, bwd_tol = (1e-5, 1e-4) if dtype == torch.float32 else (2e-2, 2e-2)
+    if dtype == torch.float32:
+        assert rel_err(out.cpu(), ref) < fwd_tol
+    else:
+        assert rel_err(out.cpu(), ref) < 1e-5          # operands pre-rounded: forward accumulates in fp32
+    for got, want, name in zip(dev_in, ref_in, "qkve"):
+        assert rel_err(got.grad.float().cpu(), want.grad) < bwd_tol, name
+    # rows without in-edges aggregate to exactly zero
+    empty = torch.bincount(index[1], minlength=n) == 0
+    assert bool(empty.any()) and float(out.cpu()[empty].abs().max()) == 0.0
+
+
+def test_conv_core_long_rows_and_degree_skew():
+    """one hub row with thousands of in-edges next to empty rows (the 'pyg' batching quirk regime)"""
+    n, hidden, heads = 64, 256, 4
+    g = torch.Generator().manual_seed(3)
+    dst = torch.cat([torch.zeros(5000, dtype=torch.long), torch.randint(1, 8, (3000,), generator=g)])
+    src = torch.randint(0, n, (8000,), generator=g)
+    index = torch.stack([src, dst])
+    q, k, v = (torch.randn(n, hidden, generator=g) for _ in range(3))
+    ee = torch.randn(8000, hidden, generator=g)
+    ref = ref_conv_core(q.double(), k.double(), v.double(), ee.double(), index, heads)
+    plan = pkg.build_plan(index.to(DEV), n)
+    out = pkg.conv_core(q.to(DEV), k.to(DEV), v.to(DEV), ee.to(DEV), plan, heads)
+    assert rel_err(out.cpu(), ref) < 1e-5
+
+
+def test_conv_core_properties_at_config2_size():
+    """size-independent properties at BASELINE config 2 line-graph size (N=98304, L=1081344, H=256)."""
+    b = pkg.synthetic_batch(256, 32, 12, seed=0, lg_inc="pyg")
+    n, e, hidden, heads = b.edge_index.size(1), b.lg_edge_index.size(1), 256, 4
+    assert (n, e) == (98304, 1081344)
+    index = b.lg_edge_index.to(DEV)
+    plan = pkg.build_plan(index, n, validate=True)
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    q, k = (torch.randn(n, hidden, device=DEV, generator=gen).bfloat16() for _ in range(2))
+    ones = torch.ones(n, hidden, device=DEV, dtype=torch.bfloat16)
+    zeros_e = torch.zeros(e, hidden, device=DEV, dtype=torch.bfloat16)
+    # (1) attention weights of every non-empty row sum to one: v = 1, e = 0 -> agg in {0, 1}
+    agg = pkg.conv_core(q, k, ones, zeros_e, plan, heads)
+    deg = torch.bincount(index[1], minlength=n)
+    assert float((agg[deg > 0] - 1).abs().max()) < 1e-5 and float(agg[deg == 0].abs().max()) == 0.0
+    # (2) deterministic: bitwise identical on a second run
+    v = torch.randn(n, hidden, device=DEV, generator=gen).bfloat16()
+    ee = torch.randn(e, hidden, device=DEV, generator=gen).bfloat16()
+    a1 = pkg.conv_core(q, k, v, ee, plan, heads)
+    a2 = pkg.conv_core(q, k, v, ee, plan, heads)
+    assert torch.equal(a1, a2)
+    # (3) invariance to a permutation of the edge list (up to fp32 summation order)
+    perm = torch.randperm(e, device=DEV, generator=gen)
+    plan_p = pkg.build_plan(index[:, perm].contiguous(), n)
+    a3 = pkg.conv_core(q, k, v, ee[perm].contiguous(), plan_p, heads)
+    assert rel_err(a3, a1) < 1e-5
+    # (4) linear in (v, e) jointly for fixed logits is not separable (e enters the logits); but v alone is linear
+    a4 = pkg.conv_core(q, k, (2 * v.float()).bfloat16(), ee, plan, heads)
+    a5 = pkg.conv_core(q, k, torch.zeros_like(v), ee, plan, heads)
+    assert rel_err(a4 - a5, 2 * (a1 - a5)) < 1e-4
+
+
+def test_conv_core_dropout_statistics_and_backward_mask_consistency():
+    n, hidden, heads, e = 200, 64, 4, 20000
+    index = random_multigraph(n, e, 9, empty_tail=False)
+    plan = pkg.build_plan(index.to(DEV), n)
+    g = torch.Generator().manual_seed(2)
+    q = torch.zeros(n, hidden)                        # uniform attention: alpha = 1/deg
+    k = torch.randn(n, hidden, generator=g)
+    v = torch.ones(n, hidden)
+    ee = torch.zeros(e, hidden)
+    p = 0.25
+    args = [t.to(DEV).requires_grad_(True) for t in (q, k, v, ee)]
+    out = pkg.conv_core(*args, plan, heads, p_drop=p, seed=123, offset=7)
+    # E[agg] = 1 ; per head the kept fraction ~ 1-p
+    assert abs(float(out.mean()) - 1.0) < 0.02
+    out2 = pkg.conv_core(*args, plan, heads, p_drop=p, seed=123, offset=7)
+    assert torch.equal(out, out2)                     # same key -> same mask
+    out3 = pkg.conv_core(*args, plan, heads, p_drop=p, seed=124, offset=7)
+    assert not torch.equal(out, out3)
+    # backward regenerates the same mask: d(sum agg)/dv_j = sum_i a~_ij, and sum_j of that = sum(agg) when v = 1
+    out.sum().backward()
+    assert abs(float(args[2].grad.sum()) - float(out.sum())) / float(out.sum()) < 1e-4
+
+
+# ---- epilogue -----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("hidden", [256, 128, 64, 32, 8, 48, 96, 320])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gate_ln_forward_backward(hidden, dtype):
+    n = 333
+    g = torch.Generator().manual_seed(hidden)
+    agg = torch.randn(n, hidden, generator=g)
+    xr = torch.randn(n, hidden, generator=g).to(dtype).float()
+    x = torch.randn(n, hidden, generator=g)
+    wb = torch.randn(1, 3 * hidden, generator=g) * 0.2
+    gamma = torch.rand(hidden, generator=g) + 0.5
+    bias = torch.randn(hidden, generator=g) * 0.3
+    gout = torch.randn(n, hidden, generator=g)
+
+    ref_in = [t.double().requires_grad_(True) for t in (agg, xr, x, wb, gamma, bias)]
+    a, s, xx, w, gm, bs = ref_in
+    beta = torch.sigmoid(torch.cat([a, s, a - s], -1) @ w.t())
+    o = beta * s + (1 - beta) * a
+    ref = xx + torch.relu(torch.nn.functional.layer_norm(o, (hidden,), gm, bs, 1e-5))
+    ref.backward(gout.double())
+
+    dev_in = [agg.to(DEV), xr.to(DEV, dtype), x.to(DEV), wb.to(DEV), gamma.to(DEV), bias.to(DEV)]
+    dev_in = [t.requires_grad_(True) for t in dev_in]
+    y, y_lp = pkg.gate_ln_relu_residual(*dev_in, 1e-5, want_lp=True)
+    assert y_lp.dtype == dtype and rel_err(y_lp.float().cpu(), ref) < (1e-5 if dtype == torch.float32 else 1e-2)
+    y.backward(gout.to(DEV))
+    assert rel_err(y.cpu(), ref) < 1e-5
+    tol = 1e-4 if dtype == torch.float32 else 2e-2
+    for got, want, name in zip(dev_in, ref_in, ("agg", "xr", "x", "wbeta", "gamma", "bias")):
+        assert rel_err(got.grad.float().cpu(), want.grad) < tol, name
+
+
+def test_gate_ln_dropout_mask_shared_by_forward_and_backward():
+    n, hidden = 500, 256
+    g = torch.Generator().manual_seed(0)
+    agg, xr = torch.randn(n, hidden, generator=g), torch.randn(n, hidden, generator=g)
+    x = torch.zeros(n, hidden)
+    wb = torch.zeros(1, 3 * hidden)
+    gamma, bias = torch.ones(hidden), torch.full((hidden,), 5.0)      # relu always active
+    args = [t.to(DEV).requires_grad_(True) for t in (agg, xr, x, wb, gamma, bias)]
+    p = 0.4
+    y, _ = pkg.gate_ln_relu_residual(*args, 1e-5, p_drop=p, seed=5, offset=9)
+    kept = (y != 0)
+    assert abs(float(kept.float().mean()) - (1 - p)) < 0.01
+    y.sum().backward()
+    # d/dbias of sum(y) = sum over rows of keep/(1-p): zero exactly where the forward dropped
+    expect = kept.float().sum(0) / (1 - p)
+    assert rel_err(args[5].grad, expect) < 1e-5
+
+
+# ---- pooling ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("hidden", [256, 32, 48])
+def test_segment_mean(hidden):
+    counts = torch.tensor([3, 0, 5, 1, 7])
+    batch = torch.repeat_interleave(torch.arange(5), counts)
+    x = torch.randn(int(counts.sum()), hidden)
+    ref_x = x.double().requires_grad_(True)
+    ref = scatter(ref_x, batch, 0, dim_size=5, reduce="mean")
+    gout = torch.randn(5, hidden)
+    ref.backward(gout.double())
+    xd = x.to(DEV).requires_grad_(True)
+    plan = pkg.build_pool_plan(batch.to(DEV), 5)
+    out = pkg.segment_mean(xd, plan)
+    out.backward(gout.to(DEV))
+    assert rel_err(out.cpu(), ref) < 1e-6 and float(out[1].abs().max()) == 0.0
+    assert rel_err(xd.grad.cpu(), ref_x.grad) < 1e-6
+    # unsorted batch vector
+    perm = torch.randperm(batch.numel())
+    plan2 = pkg.build_pool_plan(batch[perm].to(DEV), 5)
+    assert rel_err(pkg.segment_mean(x[perm].to(DEV), plan2).cpu(), ref) < 1e-6
