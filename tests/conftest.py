@@ -44,6 +44,20 @@ class Bag:
 
 def rel_err(a, b):
     """max |a-b| / max(|b|_max, tiny): the relative error used for every tolerance in this suite."""
-    a, b = a.double(), b.double()
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
     denom = max(float(b.abs().max()), 1e-30)
     return float((a - b).abs().max()) / denom
+
+
+def grad_err(got, want, gmax):
+    """gradient error relative to max(|want|_max, 1e-3 * gmax), gmax = largest |gradient| over ALL parameters.
+
+    The floor matters for tensors whose true gradient is (near) zero by symmetry -- e.g. lin_key.bias: the
+    segment softmax is invariant to a shift of all keys of a row, so d/d b_k == 0 exactly and every
+    implementation (including the fp32 CPU oracle vs the fp64 oracle) only produces rounding noise there."""
+    got, want = got.detach().double().cpu(), want.detach().double().cpu()
+    return float((got - want).abs().max()) / max(float(want.abs().max()), 1e-3 * gmax, 1e-30)
+
+
+def grads_gmax(grads):
+    return max(float(v.detach().abs().max()) for v in grads.values())
