@@ -128,6 +128,24 @@ def conv_bytes(n_nodes, n_edges, hidden, heads, s, fwd=True):
             + 8 * heads * n_nodes + 4 * (4 * n_edges + 2 * n_nodes))
 
 
+def edgeattn_bytes(kind, n_nodes, n_edges, hidden, heads, s, accum=False):
+    """Algorithmic bytes of the streaming kernels: every operand row counted once."""
+    wide = s * heads * hidden * n_nodes                       # one [heads, Nn, H] tensor (qt, gt, abar, bbar)
+    if kind == "edgeattn_fwd":
+        return (s * hidden * (3 * n_nodes + n_edges) + wide           # q,k,v,f + qt
+                + wide + 4 * hidden * n_nodes + 12 * heads * n_nodes  # abar, aggv, stats
+                + 4 * (2 * n_edges + n_nodes + 1))
+    if kind == "edgeattn_bwd_dst":
+        return (s * hidden * (3 * n_nodes + n_edges) + 2 * wide + 8 * hidden * n_nodes   # q,k,v,f, qt,gt, dagg,agg
+                + (s * hidden * n_edges if accum else 0)                                  # running df
+                + s * hidden * n_nodes + wide + s * hidden * n_edges + 8 * heads * n_edges   # dq, bbar, df, coef
+                + 8 * heads * n_nodes + 4 * (2 * n_edges + n_nodes + 1))
+    if kind == "edgeattn_bwd_src":
+        return (4 * hidden * n_nodes + s * hidden * n_nodes + 8 * heads * n_edges        # dagg, q, coef
+                + 2 * s * hidden * n_nodes + 4 * (2 * n_edges + n_nodes + 1))             # dk, dv
+    raise ValueError(kind)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference's CPU path
 # ---------------------------------------------------------------------------------------------------------
@@ -277,18 +295,26 @@ def main_b200(args):
     peak, peak_src = load_peaks()
     s_bytes = 2 if cd == torch.bfloat16 else 4
     kern = {}
-    for name in ("conv_fwd", "conv_bwd"):
+    for name in ("conv_fwd", "conv_bwd", "edgeattn_fwd", "edgeattn_bwd_dst", "edgeattn_bwd_src"):
         recs = [(ms, meta) for ms, meta in durations.get(name, []) if meta and meta[1] == sizes["L"]]
         if recs:
             ms = statistics.mean(r[0] for r in recs)
-            nn_, ne_, h_, hd_, _ = recs[0][1]
-            b = conv_bytes(nn_, ne_, h_, hd_, s_bytes, fwd=(name == "conv_fwd"))
+            nn_, ne_, h_, hd_ = recs[0][1][:4]
+            if name.startswith("conv_"):
+                b = conv_bytes(nn_, ne_, h_, hd_, s_bytes, fwd=(name == "conv_fwd"))
+            elif name == "edgeattn_bwd_dst":
+                # accumulate-in-place launches move one more [L,H] read; average over the launches as timed
+                b = statistics.mean(edgeattn_bytes(name, nn_, ne_, h_, hd_, s_bytes, accum=bool(r[1][5])) for r in recs)
+            else:
+                b = edgeattn_bytes(name, nn_, ne_, h_, hd_, s_bytes)
             kern[name] = {"ms": ms, "bytes": b, "gbs": b / (ms * 1e-3) / 1e9, "launches_timed": len(recs)}
     totals = {name: sum(ms for ms, _ in v) / args.steps for name, v in durations.items()}
     roofline = None
     if kern:
         dom = max(kern, key=lambda n: kern[n]["ms"])
         roofline = {"kernel": f"alignn_{dom} (line-graph conv, Nn={sizes['E']}, Ne={sizes['L']})", "bound": "hbm",
+                    "note": "streaming kernels trade the per-edge GEMM for ~2.6k (fwd) / ~5.9k (bwd) fp32 MAC per edge: "
+                            "they are FMA/issue-limited before HBM-limited (DESIGN.md section 3)",
                     "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": kern[dom]["gbs"] / peak,
                     "peak_source": peak_src, "traffic": None, "algorithmic_bytes": kern[dom]["bytes"],
                     "avg_launch_ms": kern[dom]["ms"],
@@ -361,7 +387,8 @@ def main_b200(args):
                 "step": "plan(CSR/CSC sort) + fwd + Gaussian NLL + bwd" + (" + NCCL allreduce(flat grads)" if world > 1 else "")
                         + ("" if args.no_optimizer else " + global-norm clip 5.0 + AdamW(fused)"),
                 "l2": "per-step working set (>= 3 GB of edge projections) >> 126 MB L2; no explicit flush",
-                "projections": "cuBLAS via torch (bf16)" if cd == torch.bfloat16 else "cuBLAS via torch (fp32, TF32 off)",
+                "projections": "per-NODE projections only (the per-edge E x H x H GEMMs are eliminated algebraically); "
+                               + ("cuBLAS via torch (bf16)" if cd == torch.bfloat16 else "cuBLAS via torch (fp32, TF32 off)"),
             },
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "kernel_ms_per_step": {k2: round(v, 4) for k2, v in sorted(totals.items())},

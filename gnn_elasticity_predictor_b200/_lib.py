@@ -32,11 +32,27 @@ SIGNATURES = {
     "alignn_gate_ln_bwd_partial_rows": (c_int64, []),
     "alignn_gate_ln_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int,
                                    c_float, c_uint64, c_uint64, _P]),
+    "alignn_edgeattn_supported": (c_int, [c_int, c_int]),
+    "alignn_edgeattn_fwd": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                    c_int64, c_int64, c_int, c_int, c_int, c_float, c_uint64, c_uint64, _P]),
+    "alignn_edgeattn_bwd_dst": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P,
+                                        _P, _P, _P, _P, c_int64, _P, _P, _P, _P, c_int,
+                                        c_int64, c_int64, c_int, c_int, c_int, c_float, c_uint64, c_uint64, _P]),
+    "alignn_edgeattn_bwd_src": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64,
+                                        c_int, c_int, c_int, _P]),
+    "alignn_gate_ln_fwd2": (c_int, [_P, _P, _P, _P, c_int, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                    c_int64, c_int, c_int, c_float, c_float, c_uint64, c_uint64, _P]),
+    "alignn_gate_ln_bwd2": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P, _P,
+                                    c_int64, c_int, c_int, c_float, c_uint64, c_uint64, _P]),
+    "alignn_angle_supported": (c_int, [c_int, c_int]),
+    "alignn_angle_h1_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
+    "alignn_angle_partial_floats": (c_int64, [c_int]),
+    "alignn_angle_h1_bwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
     "alignn_segment_mean_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P]),
     "alignn_segment_mean_bwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P]),
 }
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 F32, BF16 = 0, 1
 
 

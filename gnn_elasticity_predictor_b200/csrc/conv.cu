@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(CONV_THREADS)
 conv_bwd_src_kernel(const float *__restrict__ dagg, const T *__restrict__ q, const float *__restrict__ coef,
                     const int32_t *__restrict__ rowptr_t, const int32_t *__restrict__ col_t,
                     const int32_t *__restrict__ eid_t, T *__restrict__ dk, T *__restrict__ dv,
-                    int64_t n_nodes, int hidden, int heads, int lph) {
+                    int64_t n_nodes, int hidden, int heads, int lph, int64_t ldq, int64_t ldd) {
     constexpr int RPW = 32 / LANES;
     const int lane = threadIdx.x & 31;
     const int sub = lane % LANES;
@@ -284,7 +284,7 @@ conv_bwd_src_kernel(const float *__restrict__ dagg, const T *__restrict__ q, con
         const int i0 = __ldg(col_t + p), i1 = __ldg(col_t + p + 1);
         const int id0 = __ldg(eid_t + p), id1 = __ldg(eid_t + p + 1);
         const F8 g0 = ld8(dagg + (int64_t)i0 * hidden + ch), g1 = ld8(dagg + (int64_t)i1 * hidden + ch);
-        const F8 q0 = ld8(q + (int64_t)i0 * hidden + ch), q1 = ld8(q + (int64_t)i1 * hidden + ch);
+        const F8 q0 = ld8(q + (int64_t)i0 * ldq + ch), q1 = ld8(q + (int64_t)i1 * ldq + ch);
         const float at0 = __ldg(coef + (int64_t)id0 * 2 * heads + head);
         const float ds0 = __ldg(coef + (int64_t)id0 * 2 * heads + heads + head);
         const float at1 = __ldg(coef + (int64_t)id1 * 2 * heads + head);
@@ -304,7 +304,7 @@ conv_bwd_src_kernel(const float *__restrict__ dagg, const T *__restrict__ q, con
         const int i0 = __ldg(col_t + p);
         const int id0 = __ldg(eid_t + p);
         const F8 g0 = ld8(dagg + (int64_t)i0 * hidden + ch);
-        const F8 q0 = ld8(q + (int64_t)i0 * hidden + ch);
+        const F8 q0 = ld8(q + (int64_t)i0 * ldq + ch);
         const float at0 = __ldg(coef + (int64_t)id0 * 2 * heads + head);
         const float ds0 = __ldg(coef + (int64_t)id0 * 2 * heads + heads + head);
 #pragma unroll
@@ -313,8 +313,8 @@ conv_bwd_src_kernel(const float *__restrict__ dagg, const T *__restrict__ q, con
             dkf.v[c] = fmaf(ds0, q0.v[c], dkf.v[c]);
         }
     }
-    st8(dk + row * hidden + ch, dkf);
-    st8(dv + row * hidden + ch, dvf);
+    st8(dk + row * ldd + ch, dkf);
+    st8(dv + row * ldd + ch, dvf);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -555,7 +555,7 @@ static void launch_bwd(const BwdArgs &a, int lph) {
         scale * LOG2E, a.p_drop, inv_keep, a.seed, a.offset);
     conv_bwd_src_kernel<T, LANES><<<grid, CONV_THREADS, 0, a.st>>>(
         a.dagg, (const T *)a.q, a.coef, a.rowptr_t, a.col_t, a.eid_t, (T *)a.dk, (T *)a.dv, a.n_nodes,
-        a.hidden, a.heads, lph);
+        a.hidden, a.heads, lph, (int64_t)a.hidden, (int64_t)a.hidden);
 }
 
 template <typename T>
@@ -644,4 +644,31 @@ extern "C" int alignn_conv_bwd(const float *dagg, const float *agg,
     if (dtype == ALIGNN_F32) return dispatch_bwd<float>(a);
     if (dtype == ALIGNN_BF16) return dispatch_bwd<__nv_bfloat16>(a);
     return ALIGNN_ERR_BAD_DTYPE;
+}
+
+// source-sorted pass on strided operands (q, dk, dv are column slices of [N, 4H] projection buffers)
+extern "C" int alignn_edgeattn_bwd_src(const float *dagg, const void *q, int64_t ldq, const float *coef,
+                                       const int32_t *rowptr_t, const int32_t *col_t, const int32_t *eid_t,
+                                       void *dk, void *dv, int64_t ldd, int64_t n_nodes, int64_t n_edges,
+                                       int hidden, int heads, int dtype, void *stream) {
+    int rc = check_shape(n_nodes, n_edges, hidden, heads, 0.f);
+    if (rc != ALIGNN_OK) return rc;
+    int lanes = 0, lph = 0;
+    if (!fast_shape(hidden, heads, &lanes, &lph) || lanes != 32) return ALIGNN_ERR_BAD_SHAPE;
+    if (n_nodes == 0) return ALIGNN_OK;
+    if (!dagg || !q || !rowptr_t || !dk || !dv || (n_edges > 0 && (!coef || !col_t || !eid_t))) return ALIGNN_ERR_BAD_ARG;
+    if (!aligned16(dagg) || !aligned16(q) || !aligned16(dk) || !aligned16(dv) || (ldq % 8) || (ldd % 8)) return ALIGNN_ERR_BAD_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const unsigned grid = fast_grid(n_nodes, 32);
+    if (dtype == ALIGNN_F32)
+        conv_bwd_src_kernel<float, 32><<<grid, CONV_THREADS, 0, st>>>(dagg, (const float *)q, coef, rowptr_t, col_t, eid_t,
+                                                                     (float *)dk, (float *)dv, n_nodes, hidden, heads, lph, ldq, ldd);
+    else if (dtype == ALIGNN_BF16)
+        conv_bwd_src_kernel<__nv_bfloat16, 32><<<grid, CONV_THREADS, 0, st>>>(
+            dagg, (const __nv_bfloat16 *)q, coef, rowptr_t, col_t, eid_t, (__nv_bfloat16 *)dk, (__nv_bfloat16 *)dv, n_nodes,
+            hidden, heads, lph, ldq, ldd);
+    else
+        return ALIGNN_ERR_BAD_DTYPE;
+    ALIGNN_LAUNCH_CHECK();
+    return ALIGNN_OK;
 }

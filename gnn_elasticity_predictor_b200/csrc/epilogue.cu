@@ -32,6 +32,17 @@ __device__ __forceinline__ void dropout8(uint64_t seed, uint64_t offset, uint64_
     }
 }
 
+// optional operands of the streaming (edge-GEMM-free) path; all-null / ld = hidden reproduces the plain op
+struct GateExtra {
+    const void *agge;      // [heads, rows, C] storage dtype: per-head Wc[t] abar_t (may be null)
+    const float *cvec;     // [hidden] f32: c = W_e b (may be null)
+    const float *stat_s;   // [rows, heads] f32: S = sum_j a~
+    float *agg_out;        // [rows, hidden] f32: full aggregate, saved for backward (may be null)
+    void *dagg_lp;         // backward: storage-dtype copy of dagg (may be null)
+    int heads;
+    int64_t ldxr, lddxr;   // row strides (elements) of xr and dxr
+};
+
 template <typename T, int LANES>
 __global__ void __launch_bounds__(EPI_THREADS)
 gate_ln_fwd_kernel(const float *__restrict__ agg, const T *__restrict__ xr, const float *__restrict__ x,
@@ -39,7 +50,7 @@ gate_ln_fwd_kernel(const float *__restrict__ agg, const T *__restrict__ xr, cons
                    const float *__restrict__ bias, float *__restrict__ y, T *__restrict__ y_lp,
                    float *__restrict__ beta_out, float *__restrict__ mean_out, float *__restrict__ rstd_out,
                    int64_t n_rows, int hidden, float eps, float p_drop, float inv_keep, uint64_t seed,
-                   uint64_t offset) {
+                   uint64_t offset, const GateExtra X) {
     constexpr int RPW = 32 / LANES;
     const int lane = threadIdx.x & 31;
     const int sub = lane % LANES;
@@ -52,8 +63,23 @@ gate_ln_fwd_kernel(const float *__restrict__ agg, const T *__restrict__ xr, cons
     for (int c = 0; c < 8; ++c) af.v[c] = sf.v[c] = xf.v[c] = 0.f;
     if (ok) {
         af = ld8(agg + row * hidden + ch);
-        sf = ld8(xr + row * hidden + ch);
+        sf = ld8(xr + row * X.ldxr + ch);
         xf = ld8(x + row * hidden + ch);
+        if (X.agge) {   // agg = aggv + (Wc[t] abar_t)  [HEADS, rows, C]  + c_t * S_t
+            const int C = hidden / X.heads, t = ch / C;
+            const F8 ef = ld8(reinterpret_cast<const T *>(X.agge) + ((int64_t)t * n_rows + row) * C + (ch - t * C));
+            float sv = 0.f;
+            F8 cf;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) cf.v[c] = 0.f;
+            if (X.cvec) {
+                cf = ld8(X.cvec + ch);
+                sv = __ldg(X.stat_s + row * X.heads + t);
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) af.v[c] += ef.v[c] + cf.v[c] * sv;
+        }
+        if (X.agg_out) st8(X.agg_out + row * hidden + ch, af);
     }
     const F8 w1 = ld8(wbeta + ch), w2 = ld8(wbeta + hidden + ch), w3 = ld8(wbeta + 2 * hidden + ch);
     float zp = 0.f;
@@ -106,7 +132,8 @@ gate_ln_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ agg, 
                    const float *__restrict__ bias, const float *__restrict__ beta_in,
                    const float *__restrict__ mean_in, const float *__restrict__ rstd_in,
                    float *__restrict__ dagg, T *__restrict__ dxr, float *__restrict__ partials,
-                   int64_t n_rows, int hidden, float p_drop, float inv_keep, uint64_t seed, uint64_t offset) {
+                   int64_t n_rows, int hidden, float p_drop, float inv_keep, uint64_t seed, uint64_t offset,
+                   const GateExtra X) {
     constexpr int RPW = 32 / LANES;
     __shared__ float red[EPI_WARPS][5][LANES * 8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -133,7 +160,7 @@ gate_ln_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ agg, 
         if (ok) {
             gf = ld8(dy + row * hidden + ch);
             af = ld8(agg + row * hidden + ch);
-            sf = ld8(xr + row * hidden + ch);
+            sf = ld8(xr + row * X.ldxr + ch);
             beta = __ldg(beta_in + row);
             mean = __ldg(mean_in + row);
             rstd = __ldg(rstd_in + row);
@@ -178,7 +205,8 @@ gate_ln_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ agg, 
                 a3.v[c] = fmaf(dz, af.v[c] - sf.v[c], a3.v[c]);
             }
             st8(dagg + row * hidden + ch, da);
-            st8(dxr + row * hidden + ch, ds);
+            if (X.dagg_lp) st8(reinterpret_cast<T *>(X.dagg_lp) + row * hidden + ch, da);
+            st8(dxr + row * X.lddxr + ch, ds);
         }
     }
     // fold the row groups of a warp (fixed butterfly order), then the warps of the block (fixed order)
@@ -354,22 +382,23 @@ template <typename T, int LANES>
 static void launch_epi_fwd(const float *agg, const void *xr, const float *x, const float *wbeta, const float *gamma,
                            const float *bias, float *y, void *y_lp, float *beta, float *mean, float *rstd,
                            int64_t n_rows, int hidden, float eps, float p_drop, uint64_t seed, uint64_t offset,
-                           cudaStream_t st) {
+                           const GateExtra &X, cudaStream_t st) {
     const int rows_per_block = EPI_WARPS * (32 / LANES);
     const unsigned grid = (unsigned)((n_rows + rows_per_block - 1) / rows_per_block);
     const float inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
     gate_ln_fwd_kernel<T, LANES><<<grid, EPI_THREADS, 0, st>>>(agg, (const T *)xr, x, wbeta, gamma, bias, y, (T *)y_lp,
                                                                beta, mean, rstd, n_rows, hidden, eps, p_drop, inv_keep,
-                                                               seed, offset);
+                                                               seed, offset, X);
 }
 
 template <typename T>
 static int dispatch_epi_fwd(const float *agg, const void *xr, const float *x, const float *wbeta, const float *gamma,
                             const float *bias, float *y, void *y_lp, float *beta, float *mean, float *rstd,
                             int64_t n_rows, int hidden, float eps, float p_drop, uint64_t seed, uint64_t offset,
-                            cudaStream_t st) {
+                            const GateExtra &X, bool extras, cudaStream_t st) {
     int lanes = 0;
-#define EPI_FWD(L) launch_epi_fwd<T, L>(agg, xr, x, wbeta, gamma, bias, y, y_lp, beta, mean, rstd, n_rows, hidden, eps, p_drop, seed, offset, st)
+#define EPI_FWD(L) launch_epi_fwd<T, L>(agg, xr, x, wbeta, gamma, bias, y, y_lp, beta, mean, rstd, n_rows, hidden, eps, p_drop, seed, offset, X, st)
+    if (extras && !epi_fast(hidden, &lanes)) return ALIGNN_ERR_BAD_SHAPE;
     if (epi_fast(hidden, &lanes)) {
         switch (lanes) {
             case 32: EPI_FWD(32); break;
@@ -395,20 +424,21 @@ template <typename T, int LANES>
 static void launch_epi_bwd(const float *dy, const float *agg, const void *xr, const float *wbeta, const float *gamma,
                            const float *bias, const float *beta, const float *mean, const float *rstd, float *dagg,
                            void *dxr, float *partials, int64_t n_rows, int hidden, float p_drop, uint64_t seed,
-                           uint64_t offset, cudaStream_t st) {
+                           uint64_t offset, const GateExtra &X, cudaStream_t st) {
     const float inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
     gate_ln_bwd_kernel<T, LANES><<<EPI_PARTIAL_BLOCKS, EPI_THREADS, 0, st>>>(
         dy, agg, (const T *)xr, wbeta, gamma, bias, beta, mean, rstd, dagg, (T *)dxr, partials, n_rows, hidden, p_drop,
-        inv_keep, seed, offset);
+        inv_keep, seed, offset, X);
 }
 
 template <typename T>
 static int dispatch_epi_bwd(const float *dy, const float *agg, const void *xr, const float *wbeta, const float *gamma,
                             const float *bias, const float *beta, const float *mean, const float *rstd, float *dagg,
                             void *dxr, float *partials, float *dparams, int64_t n_rows, int hidden, float p_drop,
-                            uint64_t seed, uint64_t offset, cudaStream_t st) {
+                            uint64_t seed, uint64_t offset, const GateExtra &X, bool extras, cudaStream_t st) {
     int lanes = 0;
-#define EPI_BWD(L) launch_epi_bwd<T, L>(dy, agg, xr, wbeta, gamma, bias, beta, mean, rstd, dagg, dxr, partials, n_rows, hidden, p_drop, seed, offset, st)
+#define EPI_BWD(L) launch_epi_bwd<T, L>(dy, agg, xr, wbeta, gamma, bias, beta, mean, rstd, dagg, dxr, partials, n_rows, hidden, p_drop, seed, offset, X, st)
+    if (extras && !epi_fast(hidden, &lanes)) return ALIGNN_ERR_BAD_SHAPE;
     if (epi_fast(hidden, &lanes)) {
         switch (lanes) {
             case 32: EPI_BWD(32); break;
@@ -444,25 +474,79 @@ using namespace alignn;
 
 extern "C" int64_t alignn_gate_ln_bwd_partial_rows(void) { return EPI_PARTIAL_BLOCKS; }
 
-extern "C" int alignn_gate_ln_fwd(const float *agg, const void *xr, const float *x,
-                                  const float *wbeta, const float *gamma, const float *bias,
-                                  float *y, void *y_lp, float *beta, float *mean, float *rstd,
-                                  int64_t n_rows, int hidden, int dtype, float eps,
-                                  float p_drop, uint64_t seed, uint64_t offset, void *stream) {
+static GateExtra plain_extra(int hidden) {
+    GateExtra X;
+    X.agge = nullptr; X.cvec = nullptr; X.stat_s = nullptr; X.agg_out = nullptr; X.dagg_lp = nullptr;
+    X.heads = 1; X.ldxr = hidden; X.lddxr = hidden;
+    return X;
+}
+
+static int gate_ln_fwd_impl(const float *agg, const void *xr, const float *x,
+                            const float *wbeta, const float *gamma, const float *bias,
+                            float *y, void *y_lp, float *beta, float *mean, float *rstd,
+                            int64_t n_rows, int hidden, int dtype, float eps,
+                            float p_drop, uint64_t seed, uint64_t offset, const GateExtra &X, bool extras, void *stream) {
     if (n_rows < 0 || hidden <= 0 || hidden > 2048) return ALIGNN_ERR_BAD_SHAPE;
     if (!(p_drop >= 0.f && p_drop < 1.f)) return ALIGNN_ERR_BAD_ARG;
     if (n_rows == 0) return ALIGNN_OK;
     if (!agg || !xr || !x || !wbeta || !gamma || !bias || !y || !beta || !mean || !rstd) return ALIGNN_ERR_BAD_ARG;
     if (!aligned16(agg) || !aligned16(xr) || !aligned16(x) || !aligned16(wbeta) || !aligned16(gamma) ||
-        !aligned16(bias) || !aligned16(y) || !aligned16(y_lp))
+        !aligned16(bias) || !aligned16(y) || !aligned16(y_lp) || !aligned16(X.agge) || !aligned16(X.cvec) ||
+        !aligned16(X.agg_out) || (X.ldxr % 8))
         return ALIGNN_ERR_BAD_ARG;
+    if (extras && (X.heads <= 0 || hidden % X.heads || (hidden / X.heads) % 8)) return ALIGNN_ERR_BAD_SHAPE;
+    if (X.cvec && !X.stat_s) return ALIGNN_ERR_BAD_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (dtype == ALIGNN_F32)
         return dispatch_epi_fwd<float>(agg, xr, x, wbeta, gamma, bias, y, y_lp, beta, mean, rstd, n_rows, hidden, eps,
-                                       p_drop, seed, offset, st);
+                                       p_drop, seed, offset, X, extras, st);
     if (dtype == ALIGNN_BF16)
         return dispatch_epi_fwd<__nv_bfloat16>(agg, xr, x, wbeta, gamma, bias, y, y_lp, beta, mean, rstd, n_rows,
-                                               hidden, eps, p_drop, seed, offset, st);
+                                               hidden, eps, p_drop, seed, offset, X, extras, st);
+    return ALIGNN_ERR_BAD_DTYPE;
+}
+
+extern "C" int alignn_gate_ln_fwd(const float *agg, const void *xr, const float *x,
+                                  const float *wbeta, const float *gamma, const float *bias,
+                                  float *y, void *y_lp, float *beta, float *mean, float *rstd,
+                                  int64_t n_rows, int hidden, int dtype, float eps,
+                                  float p_drop, uint64_t seed, uint64_t offset, void *stream) {
+    return gate_ln_fwd_impl(agg, xr, x, wbeta, gamma, bias, y, y_lp, beta, mean, rstd, n_rows, hidden, dtype, eps,
+                            p_drop, seed, offset, plain_extra(hidden), false, stream);
+}
+
+extern "C" int alignn_gate_ln_fwd2(const float *aggv, const void *agge, const float *cvec, const float *stat_s,
+                                   int heads, const void *xr, int64_t ldxr, const float *x,
+                                   const float *wbeta, const float *gamma, const float *bias,
+                                   float *agg_out, float *y, void *y_lp, float *beta, float *mean, float *rstd,
+                                   int64_t n_rows, int hidden, int dtype, float eps,
+                                   float p_drop, uint64_t seed, uint64_t offset, void *stream) {
+    GateExtra X = plain_extra(hidden);
+    X.agge = agge; X.cvec = cvec; X.stat_s = stat_s; X.agg_out = agg_out; X.heads = heads; X.ldxr = ldxr;
+    return gate_ln_fwd_impl(aggv, xr, x, wbeta, gamma, bias, y, y_lp, beta, mean, rstd, n_rows, hidden, dtype, eps,
+                            p_drop, seed, offset, X, true, stream);
+}
+
+static int gate_ln_bwd_impl(const float *dy, const float *agg, const void *xr,
+                            const float *wbeta, const float *gamma, const float *bias,
+                            const float *beta, const float *mean, const float *rstd,
+                            float *dagg, void *dxr, float *partials, float *dparams,
+                            int64_t n_rows, int hidden, int dtype,
+                            float p_drop, uint64_t seed, uint64_t offset, const GateExtra &X, bool extras, void *stream) {
+    if (n_rows < 0 || hidden <= 0 || hidden > 2048) return ALIGNN_ERR_BAD_SHAPE;
+    if (!(p_drop >= 0.f && p_drop < 1.f)) return ALIGNN_ERR_BAD_ARG;
+    if (!partials || !dparams || !wbeta || !gamma || !bias) return ALIGNN_ERR_BAD_ARG;
+    if (n_rows > 0 && (!dy || !agg || !xr || !beta || !mean || !rstd || !dagg || !dxr)) return ALIGNN_ERR_BAD_ARG;
+    if (!aligned16(dy) || !aligned16(agg) || !aligned16(xr) || !aligned16(wbeta) || !aligned16(gamma) ||
+        !aligned16(bias) || !aligned16(dagg) || !aligned16(dxr) || !aligned16(X.dagg_lp) || (X.ldxr % 8) || (X.lddxr % 8))
+        return ALIGNN_ERR_BAD_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == ALIGNN_F32)
+        return dispatch_epi_bwd<float>(dy, agg, xr, wbeta, gamma, bias, beta, mean, rstd, dagg, dxr, partials,
+                                       dparams, n_rows, hidden, p_drop, seed, offset, X, extras, st);
+    if (dtype == ALIGNN_BF16)
+        return dispatch_epi_bwd<__nv_bfloat16>(dy, agg, xr, wbeta, gamma, bias, beta, mean, rstd, dagg, dxr, partials,
+                                               dparams, n_rows, hidden, p_drop, seed, offset, X, extras, st);
     return ALIGNN_ERR_BAD_DTYPE;
 }
 
@@ -472,19 +556,18 @@ extern "C" int alignn_gate_ln_bwd(const float *dy, const float *agg, const void 
                                   float *dagg, void *dxr, float *partials, float *dparams,
                                   int64_t n_rows, int hidden, int dtype,
                                   float p_drop, uint64_t seed, uint64_t offset, void *stream) {
-    if (n_rows < 0 || hidden <= 0 || hidden > 2048) return ALIGNN_ERR_BAD_SHAPE;
-    if (!(p_drop >= 0.f && p_drop < 1.f)) return ALIGNN_ERR_BAD_ARG;
-    if (!partials || !dparams || !wbeta || !gamma || !bias) return ALIGNN_ERR_BAD_ARG;
-    if (n_rows > 0 && (!dy || !agg || !xr || !beta || !mean || !rstd || !dagg || !dxr)) return ALIGNN_ERR_BAD_ARG;
-    if (!aligned16(dy) || !aligned16(agg) || !aligned16(xr) || !aligned16(wbeta) || !aligned16(gamma) ||
-        !aligned16(bias) || !aligned16(dagg) || !aligned16(dxr))
-        return ALIGNN_ERR_BAD_ARG;
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (dtype == ALIGNN_F32)
-        return dispatch_epi_bwd<float>(dy, agg, xr, wbeta, gamma, bias, beta, mean, rstd, dagg, dxr, partials,
-                                       dparams, n_rows, hidden, p_drop, seed, offset, st);
-    if (dtype == ALIGNN_BF16)
-        return dispatch_epi_bwd<__nv_bfloat16>(dy, agg, xr, wbeta, gamma, bias, beta, mean, rstd, dagg, dxr, partials,
-                                               dparams, n_rows, hidden, p_drop, seed, offset, st);
-    return ALIGNN_ERR_BAD_DTYPE;
+    return gate_ln_bwd_impl(dy, agg, xr, wbeta, gamma, bias, beta, mean, rstd, dagg, dxr, partials, dparams, n_rows,
+                            hidden, dtype, p_drop, seed, offset, plain_extra(hidden), false, stream);
+}
+
+extern "C" int alignn_gate_ln_bwd2(const float *dy, const float *agg, const void *xr, int64_t ldxr,
+                                   const float *wbeta, const float *gamma, const float *bias,
+                                   const float *beta, const float *mean, const float *rstd,
+                                   float *dagg, void *dagg_lp, void *dxr, int64_t lddxr, float *partials, float *dparams,
+                                   int64_t n_rows, int hidden, int dtype,
+                                   float p_drop, uint64_t seed, uint64_t offset, void *stream) {
+    GateExtra X = plain_extra(hidden);
+    X.dagg_lp = dagg_lp; X.ldxr = ldxr; X.lddxr = lddxr;
+    return gate_ln_bwd_impl(dy, agg, xr, wbeta, gamma, bias, beta, mean, rstd, dagg, dxr, partials, dparams, n_rows,
+                            hidden, dtype, p_drop, seed, offset, X, true, stream);
 }

@@ -1,0 +1,189 @@
+"""Block-level autograd for the streaming path (hidden = 256): one ``torch.autograd.Function`` per conv block,
+hand-written backward, no per-edge dense projection anywhere.
+
+Algebra (see ``csrc/edgeattn.cu``): with per-edge features ``f`` and the folded edge projection
+``e = Wc f + c`` (line graph: ``f = h1 = relu(W1 a + b1)``, ``Wc = W_e W2``, ``c = W_e b2``, folding the second
+Linear of ``angle_encoder`` -- reference ``train.py:360-364`` -- into PyG's ``lin_edge``; atom graph: ``f`` = bond state,
+``Wc = W_e W_p``, ``c = W_e b_p``, folding ``edge_proj`` -- ``train.py:324,333``), every ``E x H x H`` contraction of the
+reference becomes an ``N x H x H`` one on the target nodes:
+
+    forward :  P = x [Wq;Wk;Wv;Ws]^T + b      QT_t = q_t Wc[t]        (per node)
+               (aggv, abar, stats) = edgeattn_fwd(q, k, v, QT, f)      (per edge, streams f once)
+               agg = aggv + abar_t Wc[t]^T + c_t S_t ;  y = x + drop(relu(LN(beta xr + (1-beta) agg)))
+    backward:  gate/LN backward -> dagg ;  GT_t = dagg_t Wc[t]
+               (dq_direct, bbar, coef, df) = edgeattn_bwd_dst(...) ;  (dk, dv) = edgeattn_bwd_src(coef, ...)
+               dq += bbar_t Wc[t]^T ;  dWc[t] = dagg_t^T abar_t + q_t^T bbar_t ;  dc_t = sum_i dagg_i,t S_i,t
+               dx = dy + dP [Wq;Wk;Wv;Ws] ;  dW4 = dP^T x ;  db4 = colsum(dP)
+
+The feature gradient ``df`` of the line-graph layers, which all share ``h1``, is accumulated in place across layers
+inside the backward kernels (:class:`FeatGradAccumulator`), ReLU-masked by the last one, and handed to
+:class:`_AngleH1` whose backward reduces it to ``dW1, db1`` -- no ``[L, H]`` gradient is ever summed by autograd.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from . import ops
+from .ops import GraphPlan
+
+
+class FeatGradAccumulator:
+    """Shared ``[L, H]`` buffer that the line-graph blocks' backward kernels accumulate ``df`` into.
+
+    Backward visits layers in reverse order: the first visitor (``order == 0``) writes, later ones
+    read-modify-write in place, the last one (``order == n - 1``) also applies the ReLU mask of ``h1``.
+    """
+
+    def __init__(self, n_blocks: int):
+        self.n_blocks = n_blocks
+        self.buf: Optional[Tensor] = None
+        self.visits = 0
+
+
+@dataclass
+class BlockCfg:
+    heads: int
+    eps: float
+    p_attn: float
+    p_out: float
+    seed_attn: int
+    off_attn: int
+    seed_out: int
+    off_out: int
+    cd: torch.dtype
+    want_lp: bool                      # also emit a compute-dtype copy of y
+    accum: Optional[FeatGradAccumulator] = None   # line-graph blocks sharing h1
+    is_last_visitor: bool = False      # this block's backward applies the ReLU mask and returns df to the anchor
+    anchor_dtype: Optional[torch.dtype] = None
+
+
+class _AngleH1(torch.autograd.Function):
+    """``h1 = relu(W1 a + b1)`` (first angle-encoder layer).  Its backward expects the ALREADY ReLU-masked gradient
+    (the last line-graph block's backward kernel applies the mask while accumulating)."""
+
+    @staticmethod
+    def forward(ctx, a: Tensor, w1: Tensor, b1: Tensor, cd: torch.dtype):
+        a = a.contiguous().float()
+        h1 = ops.raw_angle_h1_fwd(a, w1.detach().contiguous().float(), b1.detach().contiguous().float(), cd)
+        ctx.save_for_backward(a)
+        ctx.hidden = int(w1.size(0))
+        ctx.param_dtypes = (w1.dtype, b1.dtype)
+        return h1
+
+    @staticmethod
+    def backward(ctx, dpre: Tensor):
+        (a,) = ctx.saved_tensors
+        dw1, db1 = ops.raw_angle_h1_bwd(dpre.contiguous(), a, ctx.hidden)
+        return None, dw1.to(ctx.param_dtypes[0]), db1.to(ctx.param_dtypes[1]), None
+
+
+def angle_h1(a: Tensor, w1: Tensor, b1: Tensor, cd: torch.dtype) -> Tensor:
+    return _AngleH1.apply(a, w1, b1, cd)
+
+
+class _AttnBlock(torch.autograd.Function):
+    """One EdgeUpdateBlock / NodeUpdateBlock (reference ``train.py:303-336``) on the streaming kernels."""
+
+    @staticmethod
+    def forward(ctx, x32: Tensor, xb: Optional[Tensor], feat: Tensor, anchor: Optional[Tensor], w4: Tensor, b4: Tensor,
+                wc: Tensor, cvec: Optional[Tensor], wbeta: Tensor, gamma: Tensor, beta_ln: Tensor, plan: GraphPlan,
+                cfg: BlockCfg):
+        cd, h = cfg.cd, cfg.heads
+        n, hid = x32.shape
+        c = hid // h
+        x32 = x32.contiguous()
+        if xb is None or xb.dtype != cd:
+            xb = x32.to(cd)
+        feat = feat.contiguous()
+        if feat.dtype != cd:
+            feat = feat.to(cd)
+        w4c, b4c = w4.to(cd), b4.to(cd)
+        proj = torch.addmm(b4c, xb, w4c.t())                                  # [n, 4H]: q | k | v | skip
+        wc3 = wc.to(cd).view(h, c, hid)                                       # Wc[t] : [C, H]
+        q, k, v, xr = (proj[:, i * hid:(i + 1) * hid] for i in range(4))
+        q3 = q.unflatten(1, (h, c)).transpose(0, 1)                           # [h, n, C] view
+        qt = torch.bmm(q3, wc3)                                               # [h, n, H]
+        aggv, abar, m, z, s = ops.raw_edgeattn_fwd(q, k, v, qt, feat, plan, h, cfg.p_attn, cfg.seed_attn, cfg.off_attn)
+        agge = torch.bmm(abar, wc3.transpose(1, 2))                           # [h, n, C]
+        cv = cvec.detach().contiguous().float() if cvec is not None else None
+        wb = wbeta.detach().reshape(-1).contiguous().float()
+        gm, bl = gamma.detach().contiguous().float(), beta_ln.detach().contiguous().float()
+        y, y_lp, agg, beta, mean, rstd = ops.raw_gate_ln_fwd2(aggv, agge, cv, s if cv is not None else None, h, xr, x32,
+                                                              wb, gm, bl, cfg.eps, cfg.p_out, cfg.seed_out, cfg.off_out,
+                                                              cfg.want_lp and cd != torch.float32)
+        ctx.save_for_backward(xb, feat, proj, qt, abar, agg, m, z, s, beta, mean, rstd, w4c, wc3, cv, wb, gm, bl)
+        ctx.plan, ctx.cfg = plan, cfg
+        ctx.shapes = (wbeta.shape, wbeta.dtype, gamma.dtype, beta_ln.dtype, w4.dtype, b4.dtype, wc.dtype,
+                      None if cvec is None else cvec.dtype)
+        if y_lp is not None:
+            ctx.mark_non_differentiable(y_lp)
+        ctx.set_materialize_grads(False)
+        return y, y_lp                                                        # y_lp is None in the fp32 regime
+
+    @staticmethod
+    def backward(ctx, dy: Optional[Tensor], _dy_lp):
+        xb, feat, proj, qt, abar, agg, m, z, s, beta, mean, rstd, w4c, wc3, cv, wb, gm, bl = ctx.saved_tensors
+        plan, cfg = ctx.plan, ctx.cfg
+        cd, h = cfg.cd, cfg.heads
+        n, hid = agg.shape
+        c = hid // h
+        if dy is None:
+            dy = torch.zeros_like(agg)
+        dy = dy.contiguous().float()
+        q, k, v, xr = (proj[:, i * hid:(i + 1) * hid] for i in range(4))
+        dproj = torch.empty_like(proj)
+        dq, dk, dv, dxr = (dproj[:, i * hid:(i + 1) * hid] for i in range(4))
+
+        dagg, dagg_lp, dparams = ops.raw_gate_ln_bwd2(dy, agg, xr, wb, gm, bl, beta, mean, rstd, dxr,
+                                                      cd != torch.float32, cfg.p_out, cfg.seed_out, cfg.off_out)
+        if dagg_lp is None:
+            dagg_lp = dagg
+        g3 = dagg_lp.unflatten(1, (h, c)).transpose(0, 1)                     # [h, n, C]
+        gt = torch.bmm(g3, wc3)                                               # [h, n, H]
+
+        # feature gradient: shared accumulator (line graph) or a fresh buffer (atom graph / standalone)
+        acc = cfg.accum
+        relu_mask = False
+        if acc is not None:
+            first = acc.visits == 0
+            acc.visits += 1
+            if acc.buf is None:
+                acc.buf = torch.empty_like(feat)
+            df_in, df_out = (None if first else acc.buf), acc.buf
+            relu_mask = cfg.is_last_visitor
+        else:
+            df_in, df_out = None, torch.empty_like(feat)
+        bbar = ops.raw_edgeattn_bwd(dagg, agg, q, k, v, qt, gt, cv, feat, m, z, plan, h, dq, dk, dv, df_in, df_out,
+                                    relu_mask, cfg.p_attn, cfg.seed_attn, cfg.off_attn)
+
+        q3 = q.unflatten(1, (h, c)).transpose(0, 1)
+        dq.unflatten(1, (h, c)).add_(torch.bmm(bbar, wc3.transpose(1, 2)).transpose(0, 1))   # dq += bbar_t Wc[t]^T
+        dwc = (torch.bmm(g3.transpose(1, 2), abar) + torch.bmm(q3.transpose(1, 2), bbar)).reshape(hid, hid)
+        dcvec = None
+        if cv is not None:
+            dcvec = (dagg.view(n, h, c) * s.unsqueeze(-1)).sum(0).reshape(hid)
+
+        dxb = dproj @ w4c                                                     # [n, H]
+        dx32 = dy + dxb                                                       # promotes to fp32
+        dw4 = dproj.t() @ xb
+        db4 = dproj.sum(0, dtype=torch.float32)
+
+        wshape, wdt, gdt, bdt, w4dt, b4dt, wcdt, cdt = ctx.shapes
+        d_anchor = None
+        if ctx.needs_input_grad[3]:
+            if acc is None or cfg.is_last_visitor:
+                d_anchor = df_out if cfg.anchor_dtype in (None, df_out.dtype) else df_out.to(cfg.anchor_dtype)
+        return (dx32, None, None, d_anchor, dw4.to(w4dt), db4.to(b4dt), dwc.to(wcdt),
+                None if dcvec is None else dcvec.to(cdt), dparams[:3 * hid].reshape(wshape).to(wdt),
+                dparams[3 * hid:4 * hid].to(gdt), dparams[4 * hid:].to(bdt), None, None)
+
+
+def attn_block(x32: Tensor, xb: Optional[Tensor], feat: Tensor, anchor: Optional[Tensor], w4: Tensor, b4: Tensor,
+               wc: Tensor, cvec: Optional[Tensor], wbeta: Tensor, gamma: Tensor, beta_ln: Tensor, plan: GraphPlan,
+               cfg: BlockCfg):
+    """Returns ``(y fp32 [N, H], y in compute dtype)``; ``anchor`` is the tensor that receives ``df``."""
+    return _AttnBlock.apply(x32, xb, feat, anchor, w4, b4, wc, cvec, wbeta, gamma, beta_ln, plan, cfg)

@@ -29,7 +29,8 @@ import torch
 import torch.nn.functional as F
 from torch import Tensor, nn
 
-from . import ops
+from . import fused, ops
+from .fused import BlockCfg, FeatGradAccumulator
 from .ops import GraphPlan
 
 
@@ -129,6 +130,40 @@ def _fused_block_tail(conv: TransformerConv, norm: nn.LayerNorm, p_drop: float, 
     return y
 
 
+def _streaming_ok(conv: TransformerConv, x: Tensor, flag: Optional[bool]) -> bool:
+    """The streaming (edge-GEMM-free) kernels cover hidden = 256 with 1, 2 or 4 heads; ``flag`` forces on/off."""
+    if flag is False or not x.is_cuda:
+        return False
+    ok = conv.in_channels == conv.heads * conv.out_channels == conv.edge_dim and \
+        ops.edgeattn_supported(conv.in_channels, conv.heads)
+    if flag is True and not ok:
+        raise RuntimeError("streaming kernels need hidden == edge_dim == 256 and heads in {1, 2, 4}")
+    return ok
+
+
+def _stack4(conv: TransformerConv) -> Tuple[Tensor, Tensor]:
+    w4 = torch.cat([conv.lin_query.weight, conv.lin_key.weight, conv.lin_value.weight, conv.lin_skip.weight], dim=0)
+    b_skip = conv.lin_skip.bias if conv.lin_skip.bias is not None else torch.zeros_like(conv.lin_query.bias)
+    b4 = torch.cat([conv.lin_query.bias, conv.lin_key.bias, conv.lin_value.bias, b_skip], dim=0)
+    return w4, b4
+
+
+def _stream_block(conv: TransformerConv, norm: nn.LayerNorm, p_out: float, training: bool, x32: Tensor,
+                  xb: Optional[Tensor], feat: Tensor, anchor: Optional[Tensor], wc: Tensor, cvec: Optional[Tensor],
+                  plan: GraphPlan, cd: torch.dtype, accum: Optional[FeatGradAccumulator] = None,
+                  is_last_visitor: bool = False, want_lp: bool = True):
+    p_attn = conv.dropout if training else 0.0
+    p_o = p_out if training else 0.0
+    sa, oa = ops.next_dropout_key() if p_attn > 0.0 else (0, 0)
+    so, oo = ops.next_dropout_key() if p_o > 0.0 else (0, 0)
+    cfg = BlockCfg(heads=conv.heads, eps=norm.eps, p_attn=p_attn, p_out=p_o, seed_attn=sa, off_attn=oa, seed_out=so,
+                   off_out=oo, cd=cd, want_lp=want_lp, accum=accum, is_last_visitor=is_last_visitor,
+                   anchor_dtype=None if anchor is None else anchor.dtype)
+    w4, b4 = _stack4(conv)
+    return fused.attn_block(x32.float(), xb, feat, anchor, w4, b4, wc, cvec, conv.lin_beta.weight, norm.weight,
+                            norm.bias, plan, cfg)
+
+
 class EdgeUpdateBlock(nn.Module):
     """Line-graph conv block: bonds are nodes, bond angles are edges (reference ``train.py:303-317``)."""
 
@@ -147,6 +182,11 @@ class EdgeUpdateBlock(nn.Module):
         cd = _ambient_dtype(compute_dtype)
         if plan is None:
             plan = ops.build_plan(lg_edge_index, edge_state.size(0), validate=True)
+        if _streaming_ok(self.conv, edge_state, getattr(self, "streaming", None)):
+            with torch.autocast("cuda", enabled=False):
+                y, _ = _stream_block(self.conv, self.norm, self.dropout.p, self.training, edge_state, None, angle_emb,
+                                     angle_emb, self.conv.lin_edge.weight, None, plan, cd, want_lp=False)
+            return y
         agg, xr = self.conv.project_and_aggregate(edge_state, angle_emb, plan, cd)
         return _fused_block_tail(self.conv, self.norm, self.dropout.p, self.training, edge_state, agg, xr)
 
@@ -171,9 +211,20 @@ class NodeUpdateBlock(nn.Module):
         cd = _ambient_dtype(compute_dtype)
         if plan is None:
             plan = ops.build_plan(edge_index, node_state.size(0), validate=True)
+        if _streaming_ok(self.conv, node_state, getattr(self, "streaming", None)):
+            with torch.autocast("cuda", enabled=False):
+                wc, cvec = self.folded_edge_projection()
+                y, _ = _stream_block(self.conv, self.norm, self.dropout.p, self.training, node_state, None, edge_state,
+                                     edge_state, wc, cvec, plan, cd, want_lp=False)
+            return y
         edge_attr = _linear(edge_state, self.edge_proj, cd)
         agg, xr = self.conv.project_and_aggregate(node_state, edge_attr, plan, cd)
         return _fused_block_tail(self.conv, self.norm, self.dropout.p, self.training, node_state, agg, xr)
+
+    def folded_edge_projection(self) -> Tuple[Tensor, Tensor]:
+        """``lin_edge(edge_proj(s)) = (W_e W_p) s + W_e b_p``: one linear map of the bond state (fp32, autograd-tracked)."""
+        we = self.conv.lin_edge.weight.float()
+        return we @ self.edge_proj.weight.float(), we @ self.edge_proj.bias.float()
 
 
 class AlignnRegressor(nn.Module):
@@ -212,6 +263,8 @@ class AlignnRegressor(nn.Module):
         n_atoms, n_bonds = x.size(0), data.edge_index.size(1)
         n_angles = data.lg_edge_index.size(1)
         dev = x.device
+        if len(self.edge_blocks) > 0 and _streaming_ok(self.edge_blocks[0].conv, x, getattr(self, "streaming", None)):
+            return self._trunk_streaming(data, cd)
         with torch.autocast("cuda", enabled=False):
             node_state = _mlp2(self.node_encoder, x, cd).float()
             if data.edge_attr.numel() > 0:
@@ -243,6 +296,79 @@ class AlignnRegressor(nn.Module):
                               dim=1)
             shared = F.relu(_linear(self.dropout(feats), self.feat_proj[0], cd))
             return self.feat_proj[2](shared)
+
+    def _head_features(self, node_state: Tensor, data, pool_plan: GraphPlan) -> Tensor:
+        """pool -> concat globals -> feat_proj (reference ``train.py:562-573``).  B x 545 x 256: kept in fp32."""
+        pooled = ops.segment_mean(node_state, pool_plan)
+        n_graphs = pooled.size(0)
+        global_x = data.global_x
+        if global_x.dim() == 1:
+            global_x = global_x.unsqueeze(0)
+        sg = data.sg_one_hot
+        if sg.dim() == 1:
+            sg = sg.unsqueeze(0)
+        feats = torch.cat([pooled, global_x.reshape(n_graphs, -1).float(), sg.reshape(n_graphs, -1).float()], dim=1)
+        shared = F.relu(_linear(self.dropout(feats), self.feat_proj[0], torch.float32))
+        return self.feat_proj[2](shared)
+
+    def _trunk_streaming(self, data, cd: torch.dtype) -> Tensor:
+        """hidden = 256: no per-edge dense projection is ever materialised (see ``fused.py``)."""
+        dev = data.x.device
+        n_bonds, n_angles = data.edge_index.size(1), data.lg_edge_index.size(1)
+        with torch.autocast("cuda", enabled=False):
+            node32 = _mlp2(self.node_encoder, data.x, cd).float()
+            if data.edge_attr.numel() > 0:
+                edge32 = _mlp2(self.edge_encoder, data.edge_attr, cd).float()
+            else:
+                edge32 = torch.zeros(n_bonds, self.hidden, device=dev)
+            plans = getattr(data, "_alignn_plans", None)
+            if plans is None:
+                plans = self.build_plans(data)
+            lg_plan, g_plan, pool_plan = plans
+
+            run_lg = n_bonds > 0 and n_angles > 0        # EdgeUpdateBlock's empty-input guard (train.py:313-314)
+            run_atoms = n_bonds > 0                       # NodeUpdateBlock's guard (train.py:331-332)
+            n_layers = len(self.edge_blocks)
+            fold_angle = False
+            h1 = w2 = b2 = None
+            if run_lg:
+                enc = self.angle_encoder
+                if enc is not None and data.lg_edge_attr.numel() > 0 and \
+                        ops.angle_supported(enc[0].in_features, self.hidden):
+                    # h1 = relu(W1 a + b1); the second Linear is folded into every layer's edge projection
+                    h1 = fused.angle_h1(data.lg_edge_attr, enc[0].weight, enc[0].bias, cd)
+                    w2, b2 = enc[2].weight.float(), enc[2].bias.float()
+                    fold_angle = True
+                elif enc is not None and data.lg_edge_attr.numel() > 0:
+                    h1 = _mlp2(enc, data.lg_edge_attr, cd)          # unusual angle_dim: plain features
+                else:
+                    h1 = torch.zeros(n_angles, self.hidden, device=dev, dtype=cd)
+            accum = FeatGradAccumulator(n_layers) if run_lg else None
+
+            edge_b = node_b = None
+            for l, (eb, nb) in enumerate(zip(self.edge_blocks, self.node_blocks)):
+                if run_lg:
+                    we = eb.conv.lin_edge.weight.float()
+                    if fold_angle:
+                        wc, cvec = we @ w2, we @ b2
+                    else:
+                        wc, cvec = we, None
+                    shared_h1 = fold_angle or not h1.requires_grad
+                    if shared_h1:
+                        # layer 0 is visited last by backward: it masks the accumulated df and hands it to h1
+                        edge32, edge_b = _stream_block(eb.conv, eb.norm, eb.dropout.p, self.training, edge32, edge_b,
+                                                       h1.detach(), h1 if (l == 0 and fold_angle) else None, wc, cvec,
+                                                       lg_plan, cd, accum=accum if fold_angle else None,
+                                                       is_last_visitor=(l == 0))
+                    else:
+                        edge32, edge_b = _stream_block(eb.conv, eb.norm, eb.dropout.p, self.training, edge32, edge_b,
+                                                       h1, h1, wc, cvec, lg_plan, cd)
+                if run_atoms:
+                    wc, cvec = nb.folded_edge_projection()
+                    feat = edge_b if edge_b is not None else edge32
+                    node32, node_b = _stream_block(nb.conv, nb.norm, nb.dropout.p, self.training, node32, node_b, feat,
+                                                   edge32, wc, cvec, g_plan, cd)
+            return self._head_features(node32, data, pool_plan)
 
     def build_plans(self, data):
         """CSR/CSC plans of the line graph and the atom graph + pooling plan: once per batch, reused by all

@@ -327,3 +327,132 @@ def build_pool_plan(batch: Tensor, num_graphs: int) -> GraphPlan:
 def segment_mean(x: Tensor, pool_plan: GraphPlan) -> Tensor:
     """``global_mean_pool``: per-graph mean of node rows (fp32 ``[B, H]``)."""
     return _SegmentMean.apply(x, pool_plan)
+
+
+# --------------------------------------------------------------------------------------------------
+# streaming path (hidden = 256): raw wrappers, no autograd -- used by fused.py
+# --------------------------------------------------------------------------------------------------
+def edgeattn_supported(hidden: int, heads: int) -> bool:
+    return bool(_lib.load().alignn_edgeattn_supported(int(hidden), int(heads)))
+
+
+def angle_supported(in_dim: int, hidden: int) -> bool:
+    return bool(_lib.load().alignn_angle_supported(int(in_dim), int(hidden)))
+
+
+def _ld(t: Tensor) -> int:
+    """row stride (elements) of a 2-D tensor whose rows are contiguous"""
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise RuntimeError("expected a 2-D tensor with unit column stride")
+    return int(t.stride(0))
+
+
+def raw_edgeattn_fwd(q: Tensor, k: Tensor, v: Tensor, qt: Tensor, feat: Tensor, plan: GraphPlan, heads: int,
+                     p_drop: float, seed: int, offset: int):
+    lib = _lib.load()
+    n_nodes, hidden = q.shape
+    n_edges = plan.n_edges
+    dev = q.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    aggv = torch.empty(n_nodes, hidden, **f32)
+    abar = torch.empty(heads, n_nodes, hidden, dtype=q.dtype, device=dev)
+    m, z, s = (torch.empty(n_nodes, heads, **f32) for _ in range(3))
+    with torch.cuda.device(dev), _Launch("edgeattn_fwd", 1, (n_nodes, n_edges, hidden, heads, q.element_size())):
+        rc = lib.alignn_edgeattn_fwd(_p(q), _p(k), _p(v), _ld(q), _ld(k), _ld(v), _p(qt), _p(feat), _p(plan.rowptr),
+                                     _p(plan.col), _p(plan.eid), _p(aggv), _p(abar), _p(m), _p(z), _p(s), n_nodes,
+                                     n_edges, hidden, heads, _dtype_code(q), float(p_drop), seed, offset, _stream())
+    _lib.check(rc, "alignn_edgeattn_fwd")
+    return aggv, abar, m, z, s
+
+
+def raw_edgeattn_bwd(dagg: Tensor, agg: Tensor, q: Tensor, k: Tensor, v: Tensor, qt: Tensor, gt: Tensor,
+                     cvec: Optional[Tensor], feat: Tensor, m: Tensor, z: Tensor, plan: GraphPlan, heads: int,
+                     dq: Tensor, dk: Tensor, dv: Tensor, df_in: Optional[Tensor], df_out: Tensor, relu_mask: bool,
+                     p_drop: float, seed: int, offset: int) -> Tensor:
+    """Both backward passes; dq/dk/dv are (strided) outputs; returns bbar [heads, Nn, 256]."""
+    lib = _lib.load()
+    n_nodes, hidden = q.shape
+    n_edges = plan.n_edges
+    dev = q.device
+    bbar = torch.empty(heads, n_nodes, hidden, dtype=q.dtype, device=dev)
+    coef = torch.empty(max(n_edges, 1), 2 * heads, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        with _Launch("edgeattn_bwd_dst", 1, (n_nodes, n_edges, hidden, heads, q.element_size(), df_in is not None)):
+            rc = lib.alignn_edgeattn_bwd_dst(_p(dagg), _p(agg), _p(q), _p(k), _p(v), _ld(q), _ld(k), _ld(v), _p(qt),
+                                             _p(gt), _p(cvec), _p(feat), _p(m), _p(z), _p(plan.rowptr), _p(plan.col),
+                                             _p(plan.eid), _p(dq), _ld(dq), _p(bbar), _p(coef), _p(df_in), _p(df_out),
+                                             int(bool(relu_mask)), n_nodes, n_edges, hidden, heads, _dtype_code(q),
+                                             float(p_drop), seed, offset, _stream())
+        _lib.check(rc, "alignn_edgeattn_bwd_dst")
+        with _Launch("edgeattn_bwd_src", 1, (n_nodes, n_edges, hidden, heads, q.element_size())):
+            rc = lib.alignn_edgeattn_bwd_src(_p(dagg), _p(q), _ld(q), _p(coef), _p(plan.rowptr_t), _p(plan.col_t),
+                                             _p(plan.eid_t), _p(dk), _p(dv), _ld(dk), n_nodes, n_edges, hidden, heads,
+                                             _dtype_code(q), _stream())
+        _lib.check(rc, "alignn_edgeattn_bwd_src")
+    return bbar
+
+
+def raw_gate_ln_fwd2(aggv: Tensor, agge: Optional[Tensor], cvec: Optional[Tensor], stat_s: Optional[Tensor],
+                     heads: int, xr: Tensor, x: Tensor, wbeta: Tensor, gamma: Tensor, bias: Tensor, eps: float,
+                     p_drop: float, seed: int, offset: int, want_lp: bool):
+    lib = _lib.load()
+    n_rows, hidden = aggv.shape
+    dev = aggv.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    agg = torch.empty(n_rows, hidden, **f32)
+    y = torch.empty(n_rows, hidden, **f32)
+    y_lp = torch.empty(n_rows, hidden, dtype=xr.dtype, device=dev) if want_lp else None
+    beta, mean, rstd = (torch.empty(n_rows, **f32) for _ in range(3))
+    with torch.cuda.device(dev), _Launch("gate_ln_fwd", 1, (n_rows, hidden, xr.element_size())):
+        rc = lib.alignn_gate_ln_fwd2(_p(aggv), _p(agge), _p(cvec), _p(stat_s), heads, _p(xr), _ld(xr), _p(x), _p(wbeta),
+                                     _p(gamma), _p(bias), _p(agg), _p(y), _p(y_lp), _p(beta), _p(mean), _p(rstd),
+                                     n_rows, hidden, _dtype_code(xr), float(eps), float(p_drop), seed, offset,
+                                     _stream())
+    _lib.check(rc, "alignn_gate_ln_fwd2")
+    return y, y_lp, agg, beta, mean, rstd
+
+
+def raw_gate_ln_bwd2(dy: Tensor, agg: Tensor, xr: Tensor, wbeta: Tensor, gamma: Tensor, bias: Tensor, beta: Tensor,
+                     mean: Tensor, rstd: Tensor, dxr: Tensor, want_lp: bool, p_drop: float, seed: int, offset: int):
+    """Returns (dagg f32, dagg_lp or None, dparams f32 [5*hidden]); writes dxr (strided) in place."""
+    lib = _lib.load()
+    n_rows, hidden = agg.shape
+    dev = agg.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    dagg = torch.empty(n_rows, hidden, **f32)
+    dagg_lp = torch.empty(n_rows, hidden, dtype=xr.dtype, device=dev) if want_lp else None
+    partials = torch.empty(int(lib.alignn_gate_ln_bwd_partial_rows()) * 5 * hidden, **f32)
+    dparams = torch.empty(5 * hidden, **f32)
+    with torch.cuda.device(dev), _Launch("gate_ln_bwd", 2, (n_rows, hidden, xr.element_size())):
+        rc = lib.alignn_gate_ln_bwd2(_p(dy), _p(agg), _p(xr), _ld(xr), _p(wbeta), _p(gamma), _p(bias), _p(beta),
+                                     _p(mean), _p(rstd), _p(dagg), _p(dagg_lp), _p(dxr), _ld(dxr), _p(partials),
+                                     _p(dparams), n_rows, hidden, _dtype_code(xr), float(p_drop), seed, offset,
+                                     _stream())
+    _lib.check(rc, "alignn_gate_ln_bwd2")
+    return dagg, dagg_lp, dparams
+
+
+def raw_angle_h1_fwd(a: Tensor, w1: Tensor, b1: Tensor, dtype: torch.dtype) -> Tensor:
+    lib = _lib.load()
+    n_edges, in_dim = a.shape
+    hidden = int(w1.size(0))
+    h1 = torch.empty(n_edges, hidden, dtype=dtype, device=a.device)
+    with torch.cuda.device(a.device), _Launch("angle_h1_fwd", 1, (n_edges, in_dim, hidden)):
+        rc = lib.alignn_angle_h1_fwd(_p(a), _p(w1), _p(b1), _p(h1), n_edges, in_dim, hidden, _DT[dtype], _stream())
+    _lib.check(rc, "alignn_angle_h1_fwd")
+    return h1
+
+
+def raw_angle_h1_bwd(dpre: Tensor, a: Tensor, hidden: int):
+    """(dW1 [hidden, in_dim], db1 [hidden]) in fp32 from the ReLU-masked feature gradient."""
+    lib = _lib.load()
+    n_edges, in_dim = a.shape
+    f32 = dict(dtype=torch.float32, device=a.device)
+    partials = torch.empty(int(lib.alignn_angle_partial_floats(in_dim)), **f32)
+    out = torch.empty((in_dim + 1) * hidden, **f32)
+    with torch.cuda.device(a.device), _Launch("angle_h1_bwd", 2, (n_edges, in_dim, hidden)):
+        rc = lib.alignn_angle_h1_bwd(_p(dpre), _p(a), _p(partials), _p(out), n_edges, in_dim, hidden,
+                                     _dtype_code(dpre), _stream())
+    _lib.check(rc, "alignn_angle_h1_bwd")
+    dw1 = out[:in_dim * hidden].view(in_dim, hidden).t().contiguous()
+    return dw1, out[in_dim * hidden:].clone()

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define ALIGNN_ABI_VERSION 3
+#define ALIGNN_ABI_VERSION 4
 
 #define ALIGNN_F32 0
 #define ALIGNN_BF16 1
@@ -135,6 +135,64 @@ int alignn_segment_mean_fwd(const float *x, const int32_t *rowptr, const int32_t
                             int64_t n_graphs, int hidden, void *stream);
 int alignn_segment_mean_bwd(const float *dpooled, const int32_t *rowptr, const int32_t *eid, float *dx,
                             int64_t n_graphs, int hidden, void *stream);
+
+/* ==== streaming path: edge attention with LINEAR edge features (hidden = 256, heads in {1,2,4}) ============
+ * Same reference arithmetic as alignn_conv_fwd/bwd, plus the per-edge dense projections that feed it
+ * (`lin_edge` of PyG TransformerConv, reference scripts/train.py:308,326; the second Linear of `angle_encoder`,
+ * :360-364; `edge_proj`, :324,333).  With per-edge features f and e = Wc f + c the [E,H] tensor e is never
+ * materialised: logits use qt_i,t = Wc[t]^T q_i,t (a per-NODE projection), the aggregate is returned as
+ *   aggv_i,t = sum_j a~ v_j,t ,  abar_i,t = sum_j a~ f_ij  (then agg = aggv + Wc[t] abar_t + c_t S_t per node),
+ * and backward returns bbar_i,t = sum_j ds f_ij / sqrt(C) and the feature gradient
+ *   df_ij = sum_t ( ds_ij,t qt_i,t / sqrt(C) + a~_ij,t gt_i,t ),  gt_i,t = Wc[t]^T dagg_i,t,
+ * optionally accumulated onto df_in (sum over layers sharing f) and ReLU-masked by (f > 0).
+ * q,k,v are rows of strided buffers (ld* in elements, multiples of 8); qt, gt, abar, bbar are [heads, Nn, 256].
+ */
+int alignn_edgeattn_supported(int hidden, int heads);
+int alignn_edgeattn_fwd(const void *q, const void *k, const void *v, int64_t ldq, int64_t ldk, int64_t ldv,
+                        const void *qt, const void *feat,
+                        const int32_t *rowptr, const int32_t *col, const int32_t *eid,
+                        float *aggv, void *abar, float *stat_m, float *stat_z, float *stat_s,
+                        int64_t n_nodes, int64_t n_edges, int hidden, int heads, int dtype,
+                        float p_drop, uint64_t seed, uint64_t offset, void *stream);
+int alignn_edgeattn_bwd_dst(const float *dagg, const float *agg,
+                            const void *q, const void *k, const void *v, int64_t ldq, int64_t ldk, int64_t ldv,
+                            const void *qt, const void *gt, const float *cvec,
+                            const void *feat, const float *stat_m, const float *stat_z,
+                            const int32_t *rowptr, const int32_t *col, const int32_t *eid,
+                            void *dq, int64_t lddq, void *bbar, float *coef,
+                            const void *df_in, void *df_out, int relu_mask,
+                            int64_t n_nodes, int64_t n_edges, int hidden, int heads, int dtype,
+                            float p_drop, uint64_t seed, uint64_t offset, void *stream);
+int alignn_edgeattn_bwd_src(const float *dagg, const void *q, int64_t ldq, const float *coef,
+                            const int32_t *rowptr_t, const int32_t *col_t, const int32_t *eid_t,
+                            void *dk, void *dv, int64_t ldd, int64_t n_nodes, int64_t n_edges,
+                            int hidden, int heads, int dtype, void *stream);
+
+/* Epilogue variants for the streaming path: the aggregate arrives in parts (aggv f32 [rows,H]; agge storage dtype
+ * [heads, rows, C]; c_t * S_t), xr / dxr are strided column slices; agg_out receives the assembled aggregate (saved
+ * for backward), dagg_lp a storage-dtype copy of dagg for the gt projection. */
+int alignn_gate_ln_fwd2(const float *aggv, const void *agge, const float *cvec, const float *stat_s,
+                        int heads, const void *xr, int64_t ldxr, const float *x,
+                        const float *wbeta, const float *gamma, const float *bias,
+                        float *agg_out, float *y, void *y_lp, float *beta, float *mean, float *rstd,
+                        int64_t n_rows, int hidden, int dtype, float eps,
+                        float p_drop, uint64_t seed, uint64_t offset, void *stream);
+int alignn_gate_ln_bwd2(const float *dy, const float *agg, const void *xr, int64_t ldxr,
+                        const float *wbeta, const float *gamma, const float *bias,
+                        const float *beta, const float *mean, const float *rstd,
+                        float *dagg, void *dagg_lp, void *dxr, int64_t lddxr, float *partials, float *dparams,
+                        int64_t n_rows, int hidden, int dtype,
+                        float p_drop, uint64_t seed, uint64_t offset, void *stream);
+
+/* First angle-encoder layer: h1 = relu(W1 a + b1) (reference scripts/train.py:360-362 applied at :554) and its
+ * parameter gradients from the ReLU-masked feature gradient dpre: out[f*256 + c] = dW1[c,f] (f < in_dim),
+ * out[in_dim*256 + c] = db1[c].  in_dim <= 16, hidden = 256. */
+int alignn_angle_supported(int in_dim, int hidden);
+int alignn_angle_h1_fwd(const float *a, const float *w1, const float *b1, void *h1, int64_t n_edges,
+                        int in_dim, int hidden, int dtype, void *stream);
+int64_t alignn_angle_partial_floats(int in_dim);
+int alignn_angle_h1_bwd(const void *dpre, const float *a, float *partials, float *out, int64_t n_edges,
+                        int in_dim, int hidden, int dtype, void *stream);
 
 #ifdef __cplusplus
 }

@@ -189,3 +189,96 @@ def test_config2_size_bf16_step_is_finite_and_deterministic():
     assert torch.equal(loss1, loss2)
     for k in ("base.edge_blocks.0.conv.lin_edge.weight", "base.node_encoder.0.weight"):
         assert rel_err(g1[k], g2[k]) < 1e-5, k     # hand-written kernels are atomics-free (cuBLAS split-K may not be)
+
+
+# ---- streaming path (hidden = 256): blocks against the fp64 oracle, and against the materialised path ---------
+def _multigraph(n, e, seed, hub=0):
+    g = torch.Generator().manual_seed(seed)
+    dst = torch.randint(0, max(1, (3 * n) // 4), (e,), generator=g)      # last quarter of the rows stays empty
+    src = torch.randint(0, n, (e,), generator=g)
+    src[:3] = dst[:3]                                                     # self loops
+    src[3:6], dst[3:6] = src[0:3].clone(), dst[0:3].clone()              # duplicate edges
+    if hub:
+        dst[-hub:] = 1                                                    # one long row
+    return torch.stack([src, dst])
+
+
+@pytest.mark.parametrize("heads", [1, 2, 4])
+@pytest.mark.parametrize("kind", ["edge_block", "node_block"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_streaming_blocks_h256_vs_fp64_oracle(heads, kind, dtype):
+    hidden, n, e = 256, 97, 1500
+    torch.manual_seed(heads)
+    if kind == "edge_block":
+        ref = model_ref.EdgeUpdateBlock(hidden, heads, 0.0).double()
+        ours = pkg.EdgeUpdateBlock(hidden, heads, 0.0).to(DEV)
+    else:
+        ref = model_ref.NodeUpdateBlock(hidden, hidden, heads, 0.0).double()
+        ours = pkg.NodeUpdateBlock(hidden, hidden, heads, 0.0).to(DEV)
+    with torch.no_grad():
+        ref.norm.weight.uniform_(0.5, 1.5); ref.norm.bias.uniform_(-0.3, 0.3)
+    ours.load_state_dict({k: v.float() for k, v in ref.state_dict().items()}, strict=True)
+    ours.streaming = True
+    index = _multigraph(n, e, 7 + heads, hub=600)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(n, hidden, generator=g)
+    ea = torch.randn(e, hidden, generator=g)
+    gout = torch.randn(n, hidden, generator=g)
+    xr, er = x.double().requires_grad_(True), ea.double().requires_grad_(True)
+    yr = ref(xr, index, er)
+    yr.backward(gout.double())
+    xo, eo = x.to(DEV).requires_grad_(True), ea.to(DEV).requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(dtype == torch.bfloat16)):
+        yo = ours(xo, index.to(DEV), eo)
+    yo.backward(gout.to(DEV))
+    ftol, gtol = (1e-5, 1e-4) if dtype == torch.float32 else (2e-2, 2e-2)
+    assert rel_err(yo, yr) < ftol
+    assert rel_err(xo.grad, xr.grad) < gtol and rel_err(eo.grad, er.grad) < gtol
+    want = {k: p.grad for k, p in ref.named_parameters()}
+    gmax = grads_gmax(want)
+    for k, p in ours.named_parameters():
+        if dtype == torch.float32:
+            assert grad_err(p.grad, want[k], gmax) < gtol, k
+        else:
+            assert float((p.grad.double().cpu() - want[k]).abs().max()) < gtol * gmax, k
+
+
+def test_streaming_and_materialised_paths_agree_on_the_model():
+    torch.manual_seed(3)
+    a = pkg.HeteroAlignnRegressor(pkg.AlignnRegressor(206, 36, 11, 289, 2, 256, 2, 4, 0.0), 2).to(DEV)
+    batch = pkg.synthetic_batch(6, 10, 6, seed=4, lg_inc="bonds", dups=True).to(DEV)
+    outs = {}
+    for flag in (True, False):
+        a.base.streaming = flag
+        for blk in list(a.base.edge_blocks) + list(a.base.node_blocks):
+            blk.streaming = flag
+        _, _, loss, grads = _loss_and_grads(a, batch)
+        outs[flag] = (loss.detach().clone(), grads)
+    assert rel_err(outs[True][0], outs[False][0]) < 1e-5
+    gmax = grads_gmax(outs[False][1])
+    for k, w in outs[False][1].items():
+        assert grad_err(outs[True][1][k], w, gmax) < 1e-4, k
+
+
+def test_streaming_dropout_statistics():
+    """attention dropout inside the streaming kernels: unbiased in expectation, reproducible per key"""
+    torch.manual_seed(0)
+    blk = pkg.EdgeUpdateBlock(256, 4, 0.3).to(DEV)
+    blk.streaming = True
+    n, e = 64, 6000
+    index = _multigraph(n, e, 5).to(DEV)
+    x, ea = torch.randn(n, 256, device=DEV), torch.randn(e, 256, device=DEV)
+    blk.eval()
+    y_eval = blk(x, index, ea)
+    blk.train()
+    torch.manual_seed(1); y1 = blk(x, index, ea)
+    torch.manual_seed(1); y2 = blk(x, index, ea)
+    torch.manual_seed(2); y3 = blk(x, index, ea)
+    assert torch.equal(y1, y2) and not torch.equal(y1, y3) and not torch.equal(y1, y_eval)
+    ys = []
+    for s in range(24):
+        torch.manual_seed(100 + s)
+        ys.append(blk(x, index, ea))
+    # block output = x + dropout(relu(LN(.))): its mean over many masks stays close to the eval output scale
+    mean_train = torch.stack(ys).mean(0)
+    assert float((mean_train - x).mean()) == pytest.approx(float((y_eval - x).mean()), rel=0.2)
