@@ -264,6 +264,8 @@ def main_b200(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing -----------------------------------------------------------------------------
+    for i in range(args.members):                     # priming: every member once (allocator, cuBLAS heuristics)
+        step(i, dev_batch, target_z)
     for i in range(args.warmup):
         step(i, dev_batch, target_z)
     barrier()

@@ -157,7 +157,7 @@ class _AttnBlock(torch.autograd.Function):
             relu_mask = cfg.is_last_visitor
         else:
             df_in, df_out = None, torch.empty_like(feat)
-        bbar = ops.raw_edgeattn_bwd(dagg, agg, q, k, v, qt, gt, cv, feat, m, z, plan, h, dq, dk, dv, df_in, df_out,
+        bbar = ops.raw_edgeattn_bwd(dagg, dagg_lp, agg, q, k, v, qt, gt, cv, feat, m, z, plan, h, dq, dk, dv, df_in, df_out,
                                     relu_mask, cfg.p_attn, cfg.seed_attn, cfg.off_attn)
 
         q3 = q.unflatten(1, (h, c)).transpose(0, 1)

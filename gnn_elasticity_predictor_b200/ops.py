@@ -340,6 +340,14 @@ def angle_supported(in_dim: int, hidden: int) -> bool:
     return bool(_lib.load().alignn_angle_supported(int(in_dim), int(hidden)))
 
 
+USE_MMA = True   # tensor-core (mma.sync) variants of the streaming kernels where supported (H=256, 4 heads, bf16)
+
+
+def mma_enabled(hidden: int, heads: int, dtype: torch.dtype) -> bool:
+    return USE_MMA and dtype in _DT and bool(
+        _lib.load().alignn_edgeattn_mma_supported(int(hidden), int(heads), _DT[dtype]))
+
+
 def _ld(t: Tensor) -> int:
     """row stride (elements) of a 2-D tensor whose rows are contiguous"""
     if t.dim() != 2 or t.stride(1) != 1:
@@ -357,32 +365,44 @@ def raw_edgeattn_fwd(q: Tensor, k: Tensor, v: Tensor, qt: Tensor, feat: Tensor, 
     aggv = torch.empty(n_nodes, hidden, **f32)
     abar = torch.empty(heads, n_nodes, hidden, dtype=q.dtype, device=dev)
     m, z, s = (torch.empty(n_nodes, heads, **f32) for _ in range(3))
+    fn = lib.alignn_edgeattn_mma_fwd if mma_enabled(hidden, heads, q.dtype) else lib.alignn_edgeattn_fwd
     with torch.cuda.device(dev), _Launch("edgeattn_fwd", 1, (n_nodes, n_edges, hidden, heads, q.element_size())):
-        rc = lib.alignn_edgeattn_fwd(_p(q), _p(k), _p(v), _ld(q), _ld(k), _ld(v), _p(qt), _p(feat), _p(plan.rowptr),
-                                     _p(plan.col), _p(plan.eid), _p(aggv), _p(abar), _p(m), _p(z), _p(s), n_nodes,
-                                     n_edges, hidden, heads, _dtype_code(q), float(p_drop), seed, offset, _stream())
+        rc = fn(_p(q), _p(k), _p(v), _ld(q), _ld(k), _ld(v), _p(qt), _p(feat), _p(plan.rowptr),
+                _p(plan.col), _p(plan.eid), _p(aggv), _p(abar), _p(m), _p(z), _p(s), n_nodes,
+                n_edges, hidden, heads, _dtype_code(q), float(p_drop), seed, offset, _stream())
     _lib.check(rc, "alignn_edgeattn_fwd")
     return aggv, abar, m, z, s
 
 
-def raw_edgeattn_bwd(dagg: Tensor, agg: Tensor, q: Tensor, k: Tensor, v: Tensor, qt: Tensor, gt: Tensor,
-                     cvec: Optional[Tensor], feat: Tensor, m: Tensor, z: Tensor, plan: GraphPlan, heads: int,
-                     dq: Tensor, dk: Tensor, dv: Tensor, df_in: Optional[Tensor], df_out: Tensor, relu_mask: bool,
-                     p_drop: float, seed: int, offset: int) -> Tensor:
-    """Both backward passes; dq/dk/dv are (strided) outputs; returns bbar [heads, Nn, 256]."""
+def raw_edgeattn_bwd(dagg: Tensor, dagg_lp: Optional[Tensor], agg: Tensor, q: Tensor, k: Tensor, v: Tensor, qt: Tensor,
+                     gt: Tensor, cvec: Optional[Tensor], feat: Tensor, m: Tensor, z: Tensor, plan: GraphPlan, heads: int,
+                     dq: Tensor, dk: Tensor, dv: Tensor, df_in: Optional[Tensor], df_out: Optional[Tensor],
+                     relu_mask: bool, p_drop: float, seed: int, offset: int) -> Tensor:
+    """Both backward passes; dq/dk/dv are (strided) outputs; returns bbar [heads, Nn, 256].
+    ``dagg_lp``: storage-dtype copy of ``dagg`` (tensor-core path; made here when missing)."""
     lib = _lib.load()
     n_nodes, hidden = q.shape
     n_edges = plan.n_edges
     dev = q.device
     bbar = torch.empty(heads, n_nodes, hidden, dtype=q.dtype, device=dev)
     coef = torch.empty(max(n_edges, 1), 2 * heads, dtype=torch.float32, device=dev)
+    use_mma = mma_enabled(hidden, heads, q.dtype)
     with torch.cuda.device(dev):
         with _Launch("edgeattn_bwd_dst", 1, (n_nodes, n_edges, hidden, heads, q.element_size(), df_in is not None)):
-            rc = lib.alignn_edgeattn_bwd_dst(_p(dagg), _p(agg), _p(q), _p(k), _p(v), _ld(q), _ld(k), _ld(v), _p(qt),
-                                             _p(gt), _p(cvec), _p(feat), _p(m), _p(z), _p(plan.rowptr), _p(plan.col),
-                                             _p(plan.eid), _p(dq), _ld(dq), _p(bbar), _p(coef), _p(df_in), _p(df_out),
-                                             int(bool(relu_mask)), n_nodes, n_edges, hidden, heads, _dtype_code(q),
-                                             float(p_drop), seed, offset, _stream())
+            if use_mma:
+                if dagg_lp is None or dagg_lp.dtype != q.dtype:
+                    dagg_lp = dagg.to(q.dtype)
+                rc = lib.alignn_edgeattn_mma_bwd_dst(
+                    _p(dagg), _p(dagg_lp), _p(agg), _p(q), _p(k), _p(v), _ld(q), _ld(k), _ld(v), _p(qt), _p(gt),
+                    _p(cvec), _p(feat), _p(m), _p(z), _p(plan.rowptr), _p(plan.col), _p(plan.eid), _p(dq), _ld(dq),
+                    _p(bbar), _p(coef), _p(df_in), _p(df_out), int(bool(relu_mask)), n_nodes, n_edges, hidden, heads,
+                    _dtype_code(q), float(p_drop), seed, offset, _stream())
+            else:
+                rc = lib.alignn_edgeattn_bwd_dst(_p(dagg), _p(agg), _p(q), _p(k), _p(v), _ld(q), _ld(k), _ld(v), _p(qt),
+                                                 _p(gt), _p(cvec), _p(feat), _p(m), _p(z), _p(plan.rowptr), _p(plan.col),
+                                                 _p(plan.eid), _p(dq), _ld(dq), _p(bbar), _p(coef), _p(df_in), _p(df_out),
+                                                 int(bool(relu_mask)), n_nodes, n_edges, hidden, heads, _dtype_code(q),
+                                                 float(p_drop), seed, offset, _stream())
         _lib.check(rc, "alignn_edgeattn_bwd_dst")
         with _Launch("edgeattn_bwd_src", 1, (n_nodes, n_edges, hidden, heads, q.element_size())):
             rc = lib.alignn_edgeattn_bwd_src(_p(dagg), _p(q), _ld(q), _p(coef), _p(plan.rowptr_t), _p(plan.col_t),

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define ALIGNN_ABI_VERSION 4
+#define ALIGNN_ABI_VERSION 5
 
 #define ALIGNN_F32 0
 #define ALIGNN_BF16 1
@@ -167,6 +167,28 @@ int alignn_edgeattn_bwd_src(const float *dagg, const void *q, int64_t ldq, const
                             const int32_t *rowptr_t, const int32_t *col_t, const int32_t *eid_t,
                             void *dk, void *dv, int64_t ldd, int64_t n_nodes, int64_t n_edges,
                             int hidden, int heads, int dtype, void *stream);
+
+/* Tensor-core variants of the streaming kernels (hidden = 256, heads = 4, bf16 storage): identical contract to
+ * alignn_edgeattn_fwd / _bwd_dst, with the per-edge contractions on mma.sync (chunks of 16 in-edges of one target
+ * row) and attention dropout keyed by the edge's CSR position (so a forward/backward pair must use the same
+ * family of kernels). */
+int alignn_edgeattn_mma_supported(int hidden, int heads, int dtype);
+int alignn_edgeattn_mma_fwd(const void *q, const void *k, const void *v, int64_t ldq, int64_t ldk, int64_t ldv,
+                            const void *qt, const void *feat,
+                            const int32_t *rowptr, const int32_t *col, const int32_t *eid,
+                            float *aggv, void *abar, float *stat_m, float *stat_z, float *stat_s,
+                            int64_t n_nodes, int64_t n_edges, int hidden, int heads, int dtype,
+                            float p_drop, uint64_t seed, uint64_t offset, void *stream);
+
+int alignn_edgeattn_mma_bwd_dst(const float *dagg, const void *dagg_lp, const float *agg,
+                                const void *q, const void *k, const void *v, int64_t ldq, int64_t ldk, int64_t ldv,
+                                const void *qt, const void *gt, const float *cvec,
+                                const void *feat, const float *stat_m, const float *stat_z,
+                                const int32_t *rowptr, const int32_t *col, const int32_t *eid,
+                                void *dq, int64_t lddq, void *bbar, float *coef,
+                                const void *df_in, void *df_out, int relu_mask,
+                                int64_t n_nodes, int64_t n_edges, int hidden, int heads, int dtype,
+                                float p_drop, uint64_t seed, uint64_t offset, void *stream);
 
 /* Epilogue variants for the streaming path: the aggregate arrives in parts (aggv f32 [rows,H]; agge storage dtype
  * [heads, rows, C]; c_t * S_t), xr / dxr are strided column slices; agg_out receives the assembled aggregate (saved

@@ -33,7 +33,7 @@ for it in range(iters + 3):
     flush.zero_()
     aggv, abar, m, z, s = ops.raw_edgeattn_fwd(q, k, v, qt, feat, plan, h, 0.0, 0, 0)
     flush.zero_()
-    ops.raw_edgeattn_bwd(dagg, aggv, q, k, v, qt, gt, cvec, feat, m, z, plan, h, dq, dk, dv, df if it % 2 else None, df,
+    ops.raw_edgeattn_bwd(dagg, None, aggv, q, k, v, qt, gt, cvec, feat, m, z, plan, h, dq, dk, dv, df if it % 2 else None, df,
                          False, 0.0, 0, 0)
 torch.cuda.synchronize()
 d = ops.STATS.durations_ms()

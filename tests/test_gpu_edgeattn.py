@@ -1,0 +1,154 @@
+"""GPU parity of the streaming edge-attention kernels (CUDA-core and tensor-core families) through the C ABI against an
+fp64 torch restatement of the same arithmetic (PyG TransformerConv.message + softmax + 'add' aggregation at
+reference scripts/train.py:315,334 with the edge projection folded into per-node operands, see csrc/edgeattn.cu).
+
+The backward kernels are checked as the exact adjoint of the forward: with upstream gradients (dagg, gt, Gc) the scalar
+    L = sum_i <dagg_i, aggv_i> + sum_{i,t} <gt_{i,t}, abar_{i,t}> + sum_{i,t} Gc_{i,t} S_{i,t}
+has dL/dq = dq, dL/dqt = bbar, dL/dk = dk, dL/dv = dv, dL/df = df (autograd of the fp64 restatement)."""
+import math
+
+import pytest
+import torch
+
+from conftest import rel_err
+import gnn_elasticity_predictor_b200 as pkg
+from gnn_elasticity_predictor_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+H, HEADS, C = 256, 4, 64
+
+
+def skewed_graph(n, e, seed, hub):
+    """duplicates, self loops, rows without in-edges, one hub row with `hub` in-edges, degrees around 16"""
+    g = torch.Generator().manual_seed(seed)
+    src = torch.randint(0, n, (e,), generator=g)
+    dst = torch.randint(0, max(n - 5, 1), (e,), generator=g)     # last rows: no in-edges
+    dst[:hub] = 3
+    dst[hub:hub + 16] = 5                                          # exactly one full chunk
+    dst[hub + 16:hub + 33] = 6                                     # 17 edges: chunk + 1
+    src[-4:] = dst[-4:]
+    return torch.stack([src, dst])
+
+
+def reference(q, k, v, qt, f, index, dagg, gt, cvec):
+    """fp64 restatement; returns outputs and the adjoint gradients."""
+    q, k, v, qt, f = (t.detach().double().cpu().requires_grad_(True) for t in (q, k, v, qt, f))
+    dagg, gt = dagg.double().cpu(), gt.double().cpu()
+    n = q.size(0)
+    j, i = index[0], index[1]
+    s = ((q[i].view(-1, HEADS, C) * k[j].view(-1, HEADS, C)).sum(-1)
+         + torch.einsum("tec,ec->et", qt[:, i, :], f)) / math.sqrt(C)                       # [E, h]
+    m = torch.full((n, HEADS), -float("inf"), dtype=torch.float64).scatter_reduce(0, i[:, None].expand(-1, HEADS), s,
+                                                                                  "amax", include_self=True)
+    ex = torch.exp(s - m[i])
+    z = torch.zeros(n, HEADS, dtype=torch.float64).index_add_(0, i, ex)
+    a = ex / (z[i] + 1e-16)
+    aggv = torch.zeros(n, HEADS, C, dtype=torch.float64).index_add_(0, i, a[:, :, None] * v[j].view(-1, HEADS, C))
+    abar = torch.stack([torch.zeros(n, H, dtype=torch.float64).index_add_(0, i, a[:, t:t + 1] * f) for t in range(HEADS)])
+    S = torch.zeros(n, HEADS, dtype=torch.float64).index_add_(0, i, a)
+    out = dict(aggv=aggv.reshape(n, H), abar=abar, S=S)
+    gc = (dagg.view(n, HEADS, C) * cvec.double().cpu().view(HEADS, C)).sum(-1)
+    loss = (dagg * aggv.reshape(n, H)).sum() + (gt * abar).sum() + (gc * S).sum()
+    loss.backward()
+    out.update(dq=q.grad, dk=k.grad, dv=v.grad, bbar=qt.grad, df=f.grad)
+    return {kk: vv.detach() for kk, vv in out.items()}
+
+
+def make_case(n, e, seed, hub, dtype):
+    index = skewed_graph(n, e, seed, hub)
+    g = torch.Generator().manual_seed(seed + 1)
+    proj = (torch.randn(n, 4 * H, generator=g) * 0.7).to(dtype).to(DEV)
+    q, k, v = (proj[:, t * H:(t + 1) * H] for t in range(3))          # strided rows, like the fused projection
+    qt = (torch.randn(HEADS, n, H, generator=g) * 0.15).to(dtype).to(DEV)
+    f = torch.relu(torch.randn(e, H, generator=g)).to(dtype).to(DEV)
+    dagg = torch.randn(n, H, generator=g).to(DEV)
+    wc = torch.randn(HEADS, C, H, generator=g) * 0.06
+    cvec = (torch.randn(H, generator=g) * 0.3).to(DEV)
+    gt = torch.bmm(dagg.cpu().to(dtype).float().view(n, HEADS, C).transpose(0, 1), wc).to(dtype).to(DEV)   # [h, n, H]
+    return index, q, k, v, qt, f, dagg, gt, cvec, wc
+
+
+def run_kernels(index, q, k, v, qt, f, dagg, gt, cvec, wc, p=0.0, seed=0, df_in=None, relu_mask=False):
+    n = q.size(0)
+    plan = pkg.build_plan(index.to(DEV), n)
+    aggv, abar, m, z, s = ops.raw_edgeattn_fwd(q, k, v, qt, f, plan, HEADS, p, seed, 5)
+    # the assembled aggregate, as the block epilogue builds it: aggv + Wc[t] abar_t + c_t S_t
+    agge = torch.bmm(abar.float(), wc.to(DEV).transpose(1, 2)).transpose(0, 1).reshape(n, H)
+    agg = aggv + agge + (cvec.view(HEADS, C) * s.unsqueeze(-1)).reshape(n, H)
+    dproj = torch.zeros(n, 4 * H, dtype=q.dtype, device=DEV)
+    dq, dk, dv = (dproj[:, t * H:(t + 1) * H] for t in range(3))
+    df = torch.empty_like(f)
+    bbar = ops.raw_edgeattn_bwd(dagg, dagg.to(q.dtype), agg, q, k, v, qt, gt, cvec, f, m, z, plan, HEADS, dq, dk, dv,
+                                df_in, df, relu_mask, p, seed, 5)
+    torch.cuda.synchronize()
+    return dict(aggv=aggv, abar=abar, S=s, dq=dq, dk=dk, dv=dv, bbar=bbar, df=df, m=m, z=z)
+
+
+@pytest.mark.parametrize("mma", [False, True])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_edgeattn_forward_backward_vs_fp64(mma, dtype, monkeypatch):
+    if mma and dtype != torch.bfloat16:
+        pytest.skip("tensor-core family is bf16 only")
+    monkeypatch.setattr(ops, "USE_MMA", mma)
+    n, e = 211, 4000
+    case = make_case(n, e, 3, 700, dtype)
+    index, q, k, v, qt, f, dagg, gt, cvec, wc = case
+    want = reference(q, k, v, qt, f, index, dagg.to(dtype).float() if mma else dagg, gt, cvec)
+    got = run_kernels(*case)
+    # the same bf16-rounded operands go into both sides: only accumulation order / coefficient rounding differs
+    tol = 1e-5 if dtype == torch.float32 else (1.2e-2 if mma else 6e-3)
+    for key in ("aggv", "abar", "S"):
+        assert rel_err(got[key], want[key]) < tol, key
+    gtol = 1e-4 if dtype == torch.float32 else 2e-2
+    for key in ("dq", "dk", "dv", "bbar", "df"):
+        assert rel_err(got[key], want[key]) < gtol, key
+    # rows without in-edges
+    assert float(got["aggv"][-5:].abs().max()) == 0.0 and float(got["abar"][:, -5:].abs().max()) == 0.0
+
+
+def test_mma_family_matches_cuda_core_family():
+    case = make_case(300, 6000, 9, 100, torch.bfloat16)
+    ops.USE_MMA = False
+    try:
+        a = run_kernels(*case)
+    finally:
+        ops.USE_MMA = True
+    b = run_kernels(*case)
+    assert rel_err(b["m"], a["m"]) < 1e-5 and rel_err(b["z"], a["z"]) < 1e-4
+    for key in ("aggv", "abar", "S", "dq", "dk", "dv", "bbar", "df"):
+        assert rel_err(b[key], a[key]) < 1.5e-2, key
+
+
+@pytest.mark.parametrize("mma", [False, True])
+def test_edgeattn_accumulate_and_relu_mask(mma, monkeypatch):
+    monkeypatch.setattr(ops, "USE_MMA", mma)
+    case = make_case(120, 2500, 5, 64, torch.bfloat16)
+    f = case[5]
+    base = run_kernels(*case)["df"].float()
+    prev = (torch.randn_like(base) * 0.5).to(torch.bfloat16)
+    acc = run_kernels(*case, df_in=prev.clone(), relu_mask=True)["df"].float()
+    want = (base + prev.float()) * (f.float() > 0)
+    assert rel_err(acc, want) < 1e-2
+
+
+@pytest.mark.parametrize("mma", [False, True])
+def test_edgeattn_dropout_forward_backward_masks_agree(mma, monkeypatch):
+    """aggv is linear in v for a fixed mask, so <dagg, aggv(v)> = <dv, v> holds iff backward regenerates the
+    forward's dropout mask; also E[S] = 1 and a fraction ~p of the coefficients is dropped."""
+    monkeypatch.setattr(ops, "USE_MMA", mma)
+    case = list(make_case(256, 8000, 13, 300, torch.bfloat16))
+    index, q, k, v, qt, f, dagg, gt, cvec, wc = case
+    case[3] = qt * 0         # no feature term: S, aggv depend on (q, k, v) only
+    case[7] = gt * 0
+    case[8] = cvec * 0
+    got = run_kernels(*case, p=0.25, seed=1234)
+    lhs = float((dagg.double() * got["aggv"].double()).sum())
+    rhs = float((got["dv"].double() * v.double()).sum())
+    assert abs(lhs - rhs) < 2e-2 * max(abs(lhs), 1.0), (lhs, rhs)
+    s = got["S"][: 256 - 5]
+    assert abs(float(s.mean()) - 1.0) < 0.05
+    other = run_kernels(*case, p=0.25, seed=99)
+    assert rel_err(other["aggv"], got["aggv"]) > 1e-3          # a different seed gives a different mask
+    again = run_kernels(*case, p=0.25, seed=1234)
+    assert torch.equal(again["aggv"], got["aggv"]) and torch.equal(again["dq"], got["dq"])   # bit-reproducible

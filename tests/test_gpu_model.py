@@ -121,22 +121,35 @@ def test_config1_default_arch_fp32_vs_oracle(lg_inc):
 
 @pytest.mark.parametrize("seed", [1, 2])
 def test_config1_default_arch_bf16_autocast_vs_oracle(seed):
-    """bf16 autocast regime: rel 2e-2 on outputs and loss; gradients within 2e-2 of the gradient scale and
-    direction-preserving (cosine) per tensor."""
+    """bf16 autocast regime (reference ``train.py:632-636``).  Target = the oracle in fp64.  Tolerance: rel 2e-2 on
+    outputs and loss.  Gradients: |err| <= 2e-2 of the gradient scale, OR no worse than 1.5x the error the
+    reference's own bf16-autocast run (oracle on CPU under ``torch.autocast('cpu', bfloat16)``) makes on that
+    tensor against the same fp64 target -- at this size the reference's AMP itself misses 2e-2 on
+    ``feat_proj.0.weight`` (3.0e-2 / 3.8e-2 of the gradient scale for seeds 1 / 2); plus direction (cosine)."""
+    import copy
     ref, ours = _pair(256, 4, 4)
     batch = pkg.synthetic_batch(64, 16, 12, seed=seed, lg_inc="pyg")
-    ref = ref.double()
-    r_mean, r_logvar = ref(_as_double(batch))
-    r_loss = model_ref.gaussian_nll_loss(r_mean, r_logvar, pkg.zscore_targets(batch.y, 64).double())
+    tz = pkg.zscore_targets(batch.y, 64)
+    ref64 = copy.deepcopy(ref).double()
+    r_mean, r_logvar = ref64(_as_double(batch))
+    r_loss = model_ref.gaussian_nll_loss(r_mean, r_logvar, tz.double())
     r_loss.backward()
+    want = {k: p.grad for k, p in ref64.named_parameters() if p.grad is not None}
+    gmax = grads_gmax(want)
+    # the reference's own AMP error on the same batch (CPU bf16 autocast of the oracle)
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        a_mean, a_logvar = ref(batch)
+        a_loss = model_ref.gaussian_nll_loss(a_mean.float(), a_logvar.float(), tz)
+    a_loss.backward()
+    amp_err = {k: float((p.grad.double() - want[k]).abs().max()) for k, p in ref.named_parameters()
+               if p.grad is not None}
+
     mean, logvar, loss, grads = _loss_and_grads(ours, batch.to(DEV), autocast=True)
     assert rel_err(mean, r_mean) < 2e-2 and rel_err(logvar, r_logvar) < 2e-2
     assert rel_err(loss, r_loss) < 2e-2
-    want = {k: p.grad for k, p in ref.named_parameters() if p.grad is not None}
-    gmax = grads_gmax(want)
     for k, w in want.items():
         err = float((grads[k].double() - w.cpu()).abs().max())
-        assert err < 2e-2 * gmax, k
+        assert err < max(2e-2 * gmax, 1.5 * amp_err[k]), (k, err / gmax, amp_err[k] / gmax)
         if float(w.abs().max()) > 1e-3 * gmax:
             cos = float(torch.nn.functional.cosine_similarity(grads[k].double().flatten(), w.cpu().flatten(), dim=0))
             assert cos > 0.95, (k, cos)
@@ -231,16 +244,32 @@ def test_streaming_blocks_h256_vs_fp64_oracle(heads, kind, dtype):
     with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(dtype == torch.bfloat16)):
         yo = ours(xo, index.to(DEV), eo)
     yo.backward(gout.to(DEV))
-    ftol, gtol = (1e-5, 1e-4) if dtype == torch.float32 else (2e-2, 2e-2)
-    assert rel_err(yo, yr) < ftol
-    assert rel_err(xo.grad, xr.grad) < gtol and rel_err(eo.grad, er.grad) < gtol
     want = {k: p.grad for k, p in ref.named_parameters()}
     gmax = grads_gmax(want)
+    if dtype == torch.float32:
+        assert rel_err(yo, yr) < 1e-5
+        assert rel_err(xo.grad, xr.grad) < 1e-4 and rel_err(eo.grad, er.grad) < 1e-4
+        for k, p in ours.named_parameters():
+            assert grad_err(p.grad, want[k], gmax) < 1e-4, k
+        return
+    # bf16: rel 2e-2, or no worse than 1.5x the error of the reference's OWN bf16-autocast run (oracle block on
+    # CPU under torch.autocast('cpu', bfloat16)) against the same fp64 target
+    import copy
+    amp = copy.deepcopy(ref).float()
+    amp.zero_grad()
+    xa, ea_a = x.clone().requires_grad_(True), ea.clone().requires_grad_(True)
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        ya = amp(xa, index, ea_a)
+    ya.backward(gout)
+    tol = lambda got, w: max(2e-2, 1.5 * rel_err(got, w))   # noqa: E731
+    assert rel_err(yo, yr) < tol(ya, yr)
+    assert rel_err(xo.grad, xr.grad) < tol(xa.grad, xr.grad), (rel_err(xo.grad, xr.grad), rel_err(xa.grad, xr.grad))
+    assert rel_err(eo.grad, er.grad) < tol(ea_a.grad, er.grad), (rel_err(eo.grad, er.grad), rel_err(ea_a.grad, er.grad))
+    amp_grads = {k: p.grad for k, p in amp.named_parameters()}
     for k, p in ours.named_parameters():
-        if dtype == torch.float32:
-            assert grad_err(p.grad, want[k], gmax) < gtol, k
-        else:
-            assert float((p.grad.double().cpu() - want[k]).abs().max()) < gtol * gmax, k
+        err = float((p.grad.double().cpu() - want[k]).abs().max())
+        amp_err = float((amp_grads[k].double() - want[k]).abs().max())
+        assert err < max(2e-2 * gmax, 1.5 * amp_err), (k, err / gmax, amp_err / gmax)
 
 
 def test_streaming_and_materialised_paths_agree_on_the_model():
