@@ -46,6 +46,27 @@ SIGNATURES = {
     "alignn_edgeattn_mma_bwd_dst": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P,
                                             _P, _P, _P, _P, c_int64, _P, _P, _P, _P, c_int,
                                             c_int64, c_int64, c_int, c_int, c_int, c_float, c_uint64, c_uint64, _P]),
+    "alignn_edgeattn_mma_fwd_s": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, _P, c_int64, c_int64, _P, _P, _P, _P,
+                                          _P, _P, c_int64, c_int64, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int,
+                                          c_float, c_uint64, c_uint64, _P, _P]),
+    "alignn_edgeattn_mma_bwd_dst_s": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, _P, c_int64, c_int64,
+                                              _P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P, c_int64,
+                                              c_int64, _P, _P, _P, c_int, c_int64, c_int64, c_int, c_int, c_int,
+                                              c_float, c_uint64, c_uint64, _P, _P]),
+    "alignn_lgattn_supported": (c_int, [c_int, c_int, c_int, c_int]),
+    "alignn_lg_pack_angles": (c_int, [_P, _P, _P, c_int64, c_int, _P]),
+    "alignn_lgattn_fwd": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, _P, c_int64, c_int64, _P, _P, _P, c_int,
+                                  _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P,
+                                  c_int64, c_int64, c_int, c_int, c_int, c_float, c_uint64, c_uint64, _P, _P]),
+    "alignn_lgattn_bwd_dst": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, _P, c_int64, c_int64, _P, c_int64,
+                                      c_int64, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, c_int64, _P, c_int64, c_int64,
+                                      _P, c_int64, c_int64, c_int, c_int, c_int, c_float, c_uint64, c_uint64, _P, _P]),
+    "alignn_lg_angle_grad_partial_floats": (c_int64, [c_int64, c_int64]),
+    "alignn_lg_angle_grad": (c_int, [_P, _P, _P, c_int, _P, c_int, _P, _P, _P, c_int64, c_int64, c_int64, c_int64,
+                                     _P, _P, c_int64, c_int64, _P]),
+    "alignn_adamw_partial_floats": (c_int64, []),
+    "alignn_clip_adamw_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64,
+                                       c_float, c_float, c_float, c_float, c_float, c_float, _P]),
     "alignn_gate_ln_fwd2": (c_int, [_P, _P, _P, _P, c_int, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                     c_int64, c_int, c_int, c_float, c_float, c_uint64, c_uint64, _P]),
     "alignn_gate_ln_bwd2": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P, _P,
@@ -58,7 +79,7 @@ SIGNATURES = {
     "alignn_segment_mean_bwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P]),
 }
 
-ABI_VERSION = 5
+ABI_VERSION = 7
 F32, BF16 = 0, 1
 
 

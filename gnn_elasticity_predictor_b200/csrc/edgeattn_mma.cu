@@ -12,8 +12,9 @@
 //   phase 2   acc[256 ch x 8] += F^T[256 x 16] . P[16 x 8 | cols 0..3]  +  V^T[256 x 16] . P[16 x 8 | cols 4..7]
 //             -> columns 0..3 = abar_i,t (all channels), columns 4..7 = sum_j a~ v_j (own-head channels used)  (32 MMAs)
 //
-// F, K, V rows are gathered by per-row TMA bulk copies into a warp-private double-buffered ring (rows padded to
-// 528 B so ldmatrix is conflict-free); B operands of phase 1 come straight from global memory in a channel
+// F, K, V rows are gathered with cp.async (16 bytes per lane, one warp instruction per row; per-row TMA bulk copies
+// cap at ~45 cycles per copy per SM, measured: profiles/r01_v3_notes.txt) into a warp-private double-buffered ring
+// (rows padded to 528 B so ldmatrix is conflict-free); B operands of phase 1 come straight from global memory in a channel
 // permutation shared by both operands (one 16-byte load feeds two MMAs); P goes from accumulator to B-fragment
 // layout with two movmatrix.  No atomics; every row's result is independent of the launch geometry.
 #include <math.h>
@@ -40,8 +41,10 @@ struct MmFwdParams {
     float *stat_m, *stat_z, *stat_s;  // [Nn, 4]
     int64_t n_nodes, n_edges;
     int64_t ldq, ldk, ldv;
+    int64_t ldqt, hsqt, ldab, hsab;   // qt[row * ldqt + t * hsqt + ch], abar likewise
     float scale_log2, p_drop, inv_keep;
     uint64_t seed, offset;
+    const uint64_t *rng_step;         // optional device counter added to `offset`
 };
 
 struct FwdRowFrags {
@@ -51,7 +54,7 @@ struct FwdRowFrags {
 
 __device__ __forceinline__ void load_fwd_row(FwdRowFrags &rf, const MmFwdParams &P, int64_t row, int g, int q) {
     const int t = g & 3;
-    const uint4 *pt = reinterpret_cast<const uint4 *>(P.qt + ((int64_t)t * P.n_nodes + row) * MM_HID) + q;
+    const uint4 *pt = reinterpret_cast<const uint4 *>(P.qt + row * P.ldqt + (int64_t)t * P.hsqt) + q;
 #pragma unroll
     for (int c = 0; c < 8; ++c) rf.qt[c] = __ldg(pt + 4 * c);
     const uint4 *pq = reinterpret_cast<const uint4 *>(P.q + row * P.ldq + 64 * t) + q;
@@ -66,7 +69,6 @@ edgeattn_mma_fwd_kernel(const MmFwdParams P) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, q = lane & 3;
     unsigned char *base = smem_raw + (size_t)warp * PER_WARP;
-    uint64_t *full = reinterpret_cast<uint64_t *>(base + 2 * 3 * MM_TILE);
     const uint32_t base_u32 = smem_u32(base);
 
     const int64_t W = (int64_t)gridDim.x * MM_WARPS, w = (int64_t)blockIdx.x * MM_WARPS + warp;
@@ -78,12 +80,6 @@ edgeattn_mma_fwd_kernel(const MmFwdParams P) {
 
     // padding rows of a chunk are multiplied by exact zeros in phase 2: they must hold finite values
     for (int off = lane * 16; off < 2 * 3 * MM_TILE; off += 32 * 16) sts128(base_u32 + off, make_uint4(0, 0, 0, 0));
-    if (lane == 0) {
-        mbar_init(full + 0, 1);
-        mbar_init(full + 1, 1);
-        mbar_fence_init();
-    }
-    fence_proxy_async();
     __syncwarp();
 
     StageCursor<MM_E> prod, cons;
@@ -94,29 +90,30 @@ edgeattn_mma_fwd_kernel(const MmFwdParams P) {
     wcol.init(P.col, wbase, e_end, lane);
     weid.init(P.eid, wbase, e_end, lane);
 
+    // gather one chunk: every lane copies 16 bytes of every row (cp.async, L1 bypass); one commit group per stage
     auto issue = [&](int s) {
-        if (prod.done()) return;
-        const int n = prod.count();
-        const int u = lane & 15;
-        const int o = prod.pos + min(u, n - 1) - wbase;
-        const int j = wcol.get(o), id = weid.get(o);
-        if (lane == 0) mbar_expect_tx(full + s, (uint32_t)(n * 3 * 512));
-        __syncwarp();
-        if (u < n) {
-            unsigned char *st = base + (size_t)s * 3 * MM_TILE + (size_t)u * MM_ROWB;
-            if (lane < 16) {
-                bulk_g2s(st, P.k + (int64_t)j * P.ldk, 512, full + s);
-                bulk_g2s(st + 2 * MM_TILE, P.feat + (int64_t)id * MM_HID, 512, full + s);
-            } else {
-                bulk_g2s(st + MM_TILE, P.v + (int64_t)j * P.ldv, 512, full + s);
+        if (!prod.done()) {
+            const int n = prod.count();
+            const int o = prod.pos + min(lane & 15, n - 1) - wbase;
+            const int j = wcol.get(o), id = weid.get(o);
+            const uint32_t dst = base_u32 + (uint32_t)s * 3 * MM_TILE + lane * 16;
+#pragma unroll
+            for (int u = 0; u < MM_E; ++u) {
+                if (u < n) {   // warp-uniform
+                    const int ju = __shfl_sync(FULL, j, u), idu = __shfl_sync(FULL, id, u);
+                    cp_async16(dst + u * MM_ROWB, P.k + (int64_t)ju * P.ldk + lane * 8);
+                    cp_async16(dst + MM_TILE + u * MM_ROWB, P.v + (int64_t)ju * P.ldv + lane * 8);
+                    cp_async16(dst + 2 * MM_TILE + u * MM_ROWB, P.feat + (int64_t)idu * MM_HID + lane * 8);
+                }
+            }
+            prod.advance(P.rowptr);
+            if (prod.pos - wbase >= 32 && !prod.done()) {
+                wbase += 32;
+                wcol.shift(P.col, wbase, e_end, lane);
+                weid.shift(P.eid, wbase, e_end, lane);
             }
         }
-        prod.advance(P.rowptr);
-        if (prod.pos - wbase >= 32 && !prod.done()) {
-            wbase += 32;
-            wcol.shift(P.col, wbase, e_end, lane);
-            weid.shift(P.eid, wbase, e_end, lane);
-        }
+        cp_async_commit();   // always: keeps the group count uniform
     };
 
     auto zero_rows = [&](int64_t lo, int64_t hi) {   // rows without in-edges: all outputs are zero
@@ -126,7 +123,7 @@ edgeattn_mma_fwd_kernel(const MmFwdParams P) {
         for (int64_t r = lo; r < hi; ++r) {
             st8(P.aggv + r * MM_HID + lane * 8, zf);
 #pragma unroll
-            for (int t = 0; t < MM_HEADS; ++t) st8(P.abar + ((int64_t)t * P.n_nodes + r) * MM_HID + lane * 8, zf);
+            for (int t = 0; t < MM_HEADS; ++t) st8(P.abar + r * P.ldab + (int64_t)t * P.hsab + lane * 8, zf);
             if (lane < MM_HEADS) {
                 P.stat_m[r * MM_HEADS + lane] = 0.f;
                 P.stat_z[r * MM_HEADS + lane] = 0.f;
@@ -161,7 +158,8 @@ edgeattn_mma_fwd_kernel(const MmFwdParams P) {
             m0 = m1 = -INFINITY;
             z0 = z1 = zd0 = zd1 = 0.f;
         }
-        mbar_wait(full + s, (uint32_t)((it >> 1) & 1));
+        cp_async_wait<1>();   // everything but the group just committed (the next chunk) has landed
+        __syncwarp();
         const uint32_t ktile = base_u32 + (uint32_t)s * 3 * MM_TILE, vtile = ktile + MM_TILE, ftile = ktile + 2 * MM_TILE;
 
         // ---- phase 1: logits ------------------------------------------------------------------------------
@@ -197,8 +195,9 @@ edgeattn_mma_fwd_kernel(const MmFwdParams P) {
         z1 = z1 * corr1 + (p01 + p11);
         if (P.p_drop > 0.f) {
             float d0[4], d1[4];
-            dropout_scale4(P.seed, P.offset, (uint64_t)(pos + g), P.p_drop, P.inv_keep, d0);
-            dropout_scale4(P.seed, P.offset, (uint64_t)(pos + g + 8), P.p_drop, P.inv_keep, d1);
+            const uint64_t roff = P.offset + (P.rng_step ? *P.rng_step : 0ull);
+            dropout_scale4(P.seed, roff, (uint64_t)(pos + g), P.p_drop, P.inv_keep, d0);
+            dropout_scale4(P.seed, roff, (uint64_t)(pos + g + 8), P.p_drop, P.inv_keep, d1);
             p00 *= hsel ? d0[2] : d0[0];
             p01 *= hsel ? d0[3] : d0[1];
             p10 *= hsel ? d1[2] : d1[0];
@@ -266,7 +265,7 @@ edgeattn_mma_fwd_kernel(const MmFwdParams P) {
                     uint2 o;
                     o.x = pack_bf16(x.x, x.y);
                     o.y = pack_bf16(x.z, x.w);
-                    *reinterpret_cast<uint2 *>(P.abar + ((int64_t)t * P.n_nodes + row) * MM_HID + ch) = o;
+                    *reinterpret_cast<uint2 *>(P.abar + row * P.ldab + (int64_t)t * P.hsab + ch) = o;
                 }
                 const int head = ch >> 6;
                 const float4 y = lds128f(ktile + (uint32_t)((4 + head) * MM_STG + ch) * 4);
@@ -274,8 +273,7 @@ edgeattn_mma_fwd_kernel(const MmFwdParams P) {
             }
             next_unwritten = row + 1;
         }
-        __syncwarp();          // every lane is done with stage s ...
-        fence_proxy_async();   // ... before the async proxy refills it
+        __syncwarp();          // every lane is done with stage s before it is refilled
         cons = nxt;
     }
     zero_rows(next_unwritten, r1);
@@ -307,8 +305,10 @@ struct MmBwdParams {
     __nv_bfloat16 *df_out;                   // [Ne, 256] or null (feature gradient not wanted)
     int64_t n_nodes, n_edges;
     int64_t ldq, ldk, ldv, lddq;
+    int64_t ldqt, hsqt, ldgt, hsgt, ldbb, hsbb;
     float scale, scale_log2, p_drop, inv_keep;
     uint64_t seed, offset;
+    const uint64_t *rng_step;
     int relu_mask;
 };
 
@@ -319,8 +319,8 @@ struct BwdRowFrags {
 
 __device__ __forceinline__ void load_bwd_row(BwdRowFrags &rf, const MmBwdParams &P, int64_t row, int g, int q) {
     const int t = g & 3;
-    const __nv_bfloat16 *wide = g < 4 ? P.qt : P.gt;
-    const uint4 *pt = reinterpret_cast<const uint4 *>(wide + ((int64_t)t * P.n_nodes + row) * MM_HID) + q;
+    const __nv_bfloat16 *wide = g < 4 ? P.qt + row * P.ldqt + (int64_t)t * P.hsqt : P.gt + row * P.ldgt + (int64_t)t * P.hsgt;
+    const uint4 *pt = reinterpret_cast<const uint4 *>(wide) + q;
 #pragma unroll
     for (int c = 0; c < 8; ++c) rf.x[c] = __ldg(pt + 4 * c);
     const __nv_bfloat16 *nar = g < 4 ? P.q + row * P.ldq : P.dagg_lp + row * MM_HID;
@@ -337,7 +337,6 @@ edgeattn_mma_bwd_kernel(const MmBwdParams P) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, q = lane & 3;
     unsigned char *base = smem_raw + (size_t)warp * PER_WARP;
-    uint64_t *full = reinterpret_cast<uint64_t *>(base + 2 * 3 * MM_TILE);
     int *eid_stash = reinterpret_cast<int *>(base + 2 * 3 * MM_TILE + 64);   // [2][16]
     const uint32_t base_u32 = smem_u32(base);
 
@@ -349,12 +348,6 @@ edgeattn_mma_bwd_kernel(const MmBwdParams P) {
     const int e_end = __ldg(P.rowptr + r1);
 
     for (int off = lane * 16; off < 2 * 3 * MM_TILE; off += 32 * 16) sts128(base_u32 + off, make_uint4(0, 0, 0, 0));
-    if (lane == 0) {
-        mbar_init(full + 0, 1);
-        mbar_init(full + 1, 1);
-        mbar_fence_init();
-    }
-    fence_proxy_async();
     __syncwarp();
 
     StageCursor<MM_E> prod, cons;
@@ -366,29 +359,29 @@ edgeattn_mma_bwd_kernel(const MmBwdParams P) {
     weid.init(P.eid, wbase, e_end, lane);
 
     auto issue = [&](int s) {
-        if (prod.done()) return;
-        const int n = prod.count();
-        const int u = lane & 15;
-        const int o = prod.pos + min(u, n - 1) - wbase;
-        const int j = wcol.get(o), id = weid.get(o);
-        if (lane == 0) mbar_expect_tx(full + s, (uint32_t)(n * 3 * 512));
-        __syncwarp();
-        if (u < n) {
-            unsigned char *st = base + (size_t)s * 3 * MM_TILE + (size_t)u * MM_ROWB;
-            if (lane < 16) {
-                bulk_g2s(st, P.k + (int64_t)j * P.ldk, 512, full + s);
-                bulk_g2s(st + 2 * MM_TILE, P.feat + (int64_t)id * MM_HID, 512, full + s);
-                eid_stash[s * 16 + u] = id;
-            } else {
-                bulk_g2s(st + MM_TILE, P.v + (int64_t)j * P.ldv, 512, full + s);
+        if (!prod.done()) {
+            const int n = prod.count();
+            const int o = prod.pos + min(lane & 15, n - 1) - wbase;
+            const int j = wcol.get(o), id = weid.get(o);
+            if (lane < 16) eid_stash[s * 16 + lane] = id;
+            const uint32_t dst = base_u32 + (uint32_t)s * 3 * MM_TILE + lane * 16;
+#pragma unroll
+            for (int u = 0; u < MM_E; ++u) {
+                if (u < n) {   // warp-uniform
+                    const int ju = __shfl_sync(FULL, j, u), idu = __shfl_sync(FULL, id, u);
+                    cp_async16(dst + u * MM_ROWB, P.k + (int64_t)ju * P.ldk + lane * 8);
+                    cp_async16(dst + MM_TILE + u * MM_ROWB, P.v + (int64_t)ju * P.ldv + lane * 8);
+                    cp_async16(dst + 2 * MM_TILE + u * MM_ROWB, P.feat + (int64_t)idu * MM_HID + lane * 8);
+                }
+            }
+            prod.advance(P.rowptr);
+            if (prod.pos - wbase >= 32 && !prod.done()) {
+                wbase += 32;
+                wcol.shift(P.col, wbase, e_end, lane);
+                weid.shift(P.eid, wbase, e_end, lane);
             }
         }
-        prod.advance(P.rowptr);
-        if (prod.pos - wbase >= 32 && !prod.done()) {
-            wbase += 32;
-            wcol.shift(P.col, wbase, e_end, lane);
-            weid.shift(P.eid, wbase, e_end, lane);
-        }
+        cp_async_commit();
     };
 
     auto zero_rows = [&](int64_t lo, int64_t hi) {
@@ -398,7 +391,7 @@ edgeattn_mma_bwd_kernel(const MmBwdParams P) {
         for (int64_t r = lo; r < hi; ++r) {
             st8(P.dq + r * P.lddq + lane * 8, zf);
 #pragma unroll
-            for (int t = 0; t < MM_HEADS; ++t) st8(P.bbar + ((int64_t)t * P.n_nodes + r) * MM_HID + lane * 8, zf);
+            for (int t = 0; t < MM_HEADS; ++t) st8(P.bbar + r * P.ldbb + (int64_t)t * P.hsbb + lane * 8, zf);
         }
     };
 
@@ -445,7 +438,8 @@ edgeattn_mma_bwd_kernel(const MmBwdParams P) {
             iz0 = 1.0f / (__ldg(P.stat_z + row * MM_HEADS + hsel) + 1e-16f);
             iz1 = 1.0f / (__ldg(P.stat_z + row * MM_HEADS + hsel + 1) + 1e-16f);
         }
-        mbar_wait(full + s, (uint32_t)((it >> 1) & 1));
+        cp_async_wait<1>();   // everything but the group just committed (the next chunk) has landed
+        __syncwarp();
         const uint32_t ktile = base_u32 + (uint32_t)s * 3 * MM_TILE, vtile = ktile + MM_TILE, ftile = ktile + 2 * MM_TILE;
 
         // ---- phase 1: logits (cols 0..3) and d a~ (cols 4..7) --------------------------------------------------
@@ -488,8 +482,9 @@ edgeattn_mma_bwd_kernel(const MmBwdParams P) {
         float dr00 = 1.f, dr01 = 1.f, dr10 = 1.f, dr11 = 1.f;
         if (P.p_drop > 0.f) {
             float e0[4], e1[4];
-            dropout_scale4(P.seed, P.offset, (uint64_t)(pos + g), P.p_drop, P.inv_keep, e0);
-            dropout_scale4(P.seed, P.offset, (uint64_t)(pos + g + 8), P.p_drop, P.inv_keep, e1);
+            const uint64_t roff = P.offset + (P.rng_step ? *P.rng_step : 0ull);
+            dropout_scale4(P.seed, roff, (uint64_t)(pos + g), P.p_drop, P.inv_keep, e0);
+            dropout_scale4(P.seed, roff, (uint64_t)(pos + g + 8), P.p_drop, P.inv_keep, e1);
             dr00 = hsel ? e0[2] : e0[0];
             dr01 = hsel ? e0[3] : e0[1];
             dr10 = hsel ? e1[2] : e1[0];
@@ -501,8 +496,11 @@ edgeattn_mma_bwd_kernel(const MmBwdParams P) {
         const float a10 = v1 ? fast_exp2(sl10 * P.scale_log2 - mh0) * iz0 : 0.f;
         const float a11 = v1 ? fast_exp2(sl11 * P.scale_log2 - mh1) * iz1 : 0.f;
         const float at00 = a00 * dr00, at01 = a01 * dr01, at10 = a10 * dr10, at11 = a11 * dr11;
-        const float ds00 = a00 * ((d00 + G0) * dr00 - D0) * P.scale, ds01 = a01 * ((d01 + G1) * dr01 - D1) * P.scale;
-        const float ds10 = a10 * ((d10 + G0) * dr10 - D0) * P.scale, ds11 = a11 * ((d11 + G1) * dr11 - D1) * P.scale;
+        // padding rows may hold arbitrary bit patterns (the staging buffer aliases a tile): select, never multiply
+        const float ds00 = v0 ? a00 * ((d00 + G0) * dr00 - D0) * P.scale : 0.f;
+        const float ds01 = v0 ? a01 * ((d01 + G1) * dr01 - D1) * P.scale : 0.f;
+        const float ds10 = v1 ? a10 * ((d10 + G0) * dr10 - D0) * P.scale : 0.f;
+        const float ds11 = v1 ? a11 * ((d11 + G1) * dr11 - D1) * P.scale : 0.f;
         const int id0 = eid_stash[s * 16 + min(g, n - 1)], id1 = eid_stash[s * 16 + min(g + 8, n - 1)];
         {   // coef row = (a~_0..3, ds_0..3): lanes q < 2 store a~, lanes q >= 2 store ds
             const float2 w0 = lo_half ? make_float2(at00, at01) : make_float2(ds00, ds01);
@@ -597,7 +595,7 @@ edgeattn_mma_bwd_kernel(const MmBwdParams P) {
                     uint2 ov;
                     ov.x = pack_bf16(x.x, x.y);
                     ov.y = pack_bf16(x.z, x.w);
-                    *reinterpret_cast<uint2 *>(P.bbar + ((int64_t)t * P.n_nodes + row) * MM_HID + ch) = ov;
+                    *reinterpret_cast<uint2 *>(P.bbar + row * P.ldbb + (int64_t)t * P.hsbb + ch) = ov;
                 }
                 const int head = ch >> 6;
                 const float4 y = lds128f(vtile + (uint32_t)((4 + head) * MM_STG + ch) * 4);
@@ -609,7 +607,6 @@ edgeattn_mma_bwd_kernel(const MmBwdParams P) {
             next_unwritten = row + 1;
         }
         __syncwarp();
-        fence_proxy_async();
         cons = nxt;
     }
     zero_rows(next_unwritten, r1);
@@ -632,12 +629,14 @@ extern "C" int alignn_edgeattn_mma_supported(int hidden, int heads, int dtype) {
     return hidden == MM_HID && heads == MM_HEADS && dtype == ALIGNN_BF16;
 }
 
-extern "C" int alignn_edgeattn_mma_fwd(const void *q, const void *k, const void *v, int64_t ldq, int64_t ldk,
-                                       int64_t ldv, const void *qt, const void *feat,
-                                       const int32_t *rowptr, const int32_t *col, const int32_t *eid,
-                                       float *aggv, void *abar, float *stat_m, float *stat_z, float *stat_s,
-                                       int64_t n_nodes, int64_t n_edges, int hidden, int heads, int dtype,
-                                       float p_drop, uint64_t seed, uint64_t offset, void *stream) {
+extern "C" int alignn_edgeattn_mma_fwd_s(const void *q, const void *k, const void *v, int64_t ldq, int64_t ldk,
+                                         int64_t ldv, const void *qt, int64_t ldqt, int64_t hsqt, const void *feat,
+                                         const int32_t *rowptr, const int32_t *col, const int32_t *eid,
+                                         float *aggv, void *abar, int64_t ldab, int64_t hsab,
+                                         float *stat_m, float *stat_z, float *stat_s,
+                                         int64_t n_nodes, int64_t n_edges, int hidden, int heads, int dtype,
+                                         float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step,
+                                         void *stream) {
     if (!alignn_edgeattn_mma_supported(hidden, heads, dtype)) return ALIGNN_ERR_BAD_SHAPE;
     if (n_nodes < 0 || n_edges < 0 || !(p_drop >= 0.f && p_drop < 1.f)) return ALIGNN_ERR_BAD_ARG;
     if (n_nodes >= ((int64_t)1 << 31) - 1 || n_edges >= ((int64_t)1 << 31) - 64) return ALIGNN_ERR_BAD_SHAPE;
@@ -645,7 +644,7 @@ extern "C" int alignn_edgeattn_mma_fwd(const void *q, const void *k, const void 
     if (!q || !k || !v || !qt || !rowptr || !aggv || !abar || !stat_m || !stat_z || !stat_s) return ALIGNN_ERR_BAD_ARG;
     if (n_edges > 0 && (!feat || !col || !eid)) return ALIGNN_ERR_BAD_ARG;
     if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(qt) || !aligned16(feat) || !aligned16(aggv) ||
-        !aligned16(abar) || (ldq % 8) || (ldk % 8) || (ldv % 8))
+        !aligned16(abar) || (ldq % 8) || (ldk % 8) || (ldv % 8) || (ldqt % 8) || (hsqt % 8) || (ldab % 8) || (hsab % 8))
         return ALIGNN_ERR_BAD_ARG;
     MmFwdParams p;
     p.q = (const __nv_bfloat16 *)q; p.k = (const __nv_bfloat16 *)k; p.v = (const __nv_bfloat16 *)v;
@@ -653,6 +652,7 @@ extern "C" int alignn_edgeattn_mma_fwd(const void *q, const void *k, const void 
     p.rowptr = rowptr; p.col = col; p.eid = eid;
     p.aggv = aggv; p.abar = (__nv_bfloat16 *)abar; p.stat_m = stat_m; p.stat_z = stat_z; p.stat_s = stat_s;
     p.n_nodes = n_nodes; p.n_edges = n_edges; p.ldq = ldq; p.ldk = ldk; p.ldv = ldv;
+    p.ldqt = ldqt; p.hsqt = hsqt; p.ldab = ldab; p.hsab = hsab; p.rng_step = rng_step;
     p.scale_log2 = LOG2E / sqrtf((float)(hidden / heads));
     p.p_drop = p_drop; p.inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
     p.seed = seed; p.offset = offset;
@@ -664,15 +664,17 @@ extern "C" int alignn_edgeattn_mma_fwd(const void *q, const void *k, const void 
     return ALIGNN_OK;
 }
 
-extern "C" int alignn_edgeattn_mma_bwd_dst(const float *dagg, const void *dagg_lp, const float *agg,
-                                           const void *q, const void *k, const void *v, int64_t ldq, int64_t ldk,
-                                           int64_t ldv, const void *qt, const void *gt, const float *cvec,
-                                           const void *feat, const float *stat_m, const float *stat_z,
-                                           const int32_t *rowptr, const int32_t *col, const int32_t *eid,
-                                           void *dq, int64_t lddq, void *bbar, float *coef,
-                                           const void *df_in, void *df_out, int relu_mask,
-                                           int64_t n_nodes, int64_t n_edges, int hidden, int heads, int dtype,
-                                           float p_drop, uint64_t seed, uint64_t offset, void *stream) {
+extern "C" int alignn_edgeattn_mma_bwd_dst_s(const float *dagg, const void *dagg_lp, const float *agg,
+                                             const void *q, const void *k, const void *v, int64_t ldq, int64_t ldk,
+                                             int64_t ldv, const void *qt, int64_t ldqt, int64_t hsqt,
+                                             const void *gt, int64_t ldgt, int64_t hsgt, const float *cvec,
+                                             const void *feat, const float *stat_m, const float *stat_z,
+                                             const int32_t *rowptr, const int32_t *col, const int32_t *eid,
+                                             void *dq, int64_t lddq, void *bbar, int64_t ldbb, int64_t hsbb, float *coef,
+                                             const void *df_in, void *df_out, int relu_mask,
+                                             int64_t n_nodes, int64_t n_edges, int hidden, int heads, int dtype,
+                                             float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step,
+                                             void *stream) {
     if (!alignn_edgeattn_mma_supported(hidden, heads, dtype)) return ALIGNN_ERR_BAD_SHAPE;
     if (n_nodes < 0 || n_edges < 0 || !(p_drop >= 0.f && p_drop < 1.f)) return ALIGNN_ERR_BAD_ARG;
     if (n_nodes >= ((int64_t)1 << 31) - 1 || n_edges >= ((int64_t)1 << 31) - 64) return ALIGNN_ERR_BAD_SHAPE;
@@ -683,7 +685,8 @@ extern "C" int alignn_edgeattn_mma_bwd_dst(const float *dagg, const void *dagg_l
     if (df_in && !df_out) return ALIGNN_ERR_BAD_ARG;
     if (!aligned16(dagg) || !aligned16(dagg_lp) || !aligned16(agg) || !aligned16(q) || !aligned16(k) || !aligned16(v) ||
         !aligned16(qt) || !aligned16(gt) || !aligned16(cvec) || !aligned16(feat) || !aligned16(dq) || !aligned16(bbar) ||
-        !aligned16(coef) || !aligned16(df_in) || !aligned16(df_out) || (ldq % 8) || (ldk % 8) || (ldv % 8) || (lddq % 8))
+        !aligned16(coef) || !aligned16(df_in) || !aligned16(df_out) || (ldq % 8) || (ldk % 8) || (ldv % 8) || (lddq % 8) ||
+        (ldqt % 8) || (hsqt % 8) || (ldgt % 8) || (hsgt % 8) || (ldbb % 8) || (hsbb % 8))
         return ALIGNN_ERR_BAD_ARG;
     MmBwdParams p;
     p.dagg = dagg; p.agg = agg; p.dagg_lp = (const __nv_bfloat16 *)dagg_lp;
@@ -694,6 +697,7 @@ extern "C" int alignn_edgeattn_mma_bwd_dst(const float *dagg, const void *dagg_l
     p.dq = (__nv_bfloat16 *)dq; p.bbar = (__nv_bfloat16 *)bbar; p.coef = coef;
     p.df_in = (const __nv_bfloat16 *)df_in; p.df_out = (__nv_bfloat16 *)df_out;
     p.n_nodes = n_nodes; p.n_edges = n_edges; p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.lddq = lddq;
+    p.ldqt = ldqt; p.hsqt = hsqt; p.ldgt = ldgt; p.hsgt = hsgt; p.ldbb = ldbb; p.hsbb = hsbb; p.rng_step = rng_step;
     p.scale = 1.0f / sqrtf((float)(hidden / heads));
     p.scale_log2 = p.scale * LOG2E;
     p.p_drop = p_drop; p.inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
@@ -710,4 +714,31 @@ extern "C" int alignn_edgeattn_mma_bwd_dst(const float *dagg, const void *dagg_l
     }
     ALIGNN_LAUNCH_CHECK();
     return ALIGNN_OK;
+}
+
+// contiguous [heads, Nn, 256] layouts of qt / gt / abar / bbar
+extern "C" int alignn_edgeattn_mma_fwd(const void *q, const void *k, const void *v, int64_t ldq, int64_t ldk,
+                                       int64_t ldv, const void *qt, const void *feat,
+                                       const int32_t *rowptr, const int32_t *col, const int32_t *eid,
+                                       float *aggv, void *abar, float *stat_m, float *stat_z, float *stat_s,
+                                       int64_t n_nodes, int64_t n_edges, int hidden, int heads, int dtype,
+                                       float p_drop, uint64_t seed, uint64_t offset, void *stream) {
+    return alignn_edgeattn_mma_fwd_s(q, k, v, ldq, ldk, ldv, qt, MM_HID, n_nodes * MM_HID, feat, rowptr, col, eid, aggv,
+                                     abar, MM_HID, n_nodes * MM_HID, stat_m, stat_z, stat_s, n_nodes, n_edges, hidden,
+                                     heads, dtype, p_drop, seed, offset, nullptr, stream);
+}
+
+extern "C" int alignn_edgeattn_mma_bwd_dst(const float *dagg, const void *dagg_lp, const float *agg,
+                                           const void *q, const void *k, const void *v, int64_t ldq, int64_t ldk,
+                                           int64_t ldv, const void *qt, const void *gt, const float *cvec,
+                                           const void *feat, const float *stat_m, const float *stat_z,
+                                           const int32_t *rowptr, const int32_t *col, const int32_t *eid,
+                                           void *dq, int64_t lddq, void *bbar, float *coef,
+                                           const void *df_in, void *df_out, int relu_mask,
+                                           int64_t n_nodes, int64_t n_edges, int hidden, int heads, int dtype,
+                                           float p_drop, uint64_t seed, uint64_t offset, void *stream) {
+    return alignn_edgeattn_mma_bwd_dst_s(dagg, dagg_lp, agg, q, k, v, ldq, ldk, ldv, qt, MM_HID, n_nodes * MM_HID, gt,
+                                         MM_HID, n_nodes * MM_HID, cvec, feat, stat_m, stat_z, rowptr, col, eid, dq, lddq,
+                                         bbar, MM_HID, n_nodes * MM_HID, coef, df_in, df_out, relu_mask, n_nodes, n_edges,
+                                         hidden, heads, dtype, p_drop, seed, offset, nullptr, stream);
 }

@@ -374,6 +374,103 @@ def raw_edgeattn_fwd(q: Tensor, k: Tensor, v: Tensor, qt: Tensor, feat: Tensor, 
     return aggv, abar, m, z, s
 
 
+def pack_angles(a: Tensor, plan: GraphPlan) -> Tensor:
+    """``[L, 16]`` bf16 angle features in the plan's target-sorted order, bias column set to 1 (``csrc/lgattn.cu``)."""
+    lib = _lib.load()
+    a = a.contiguous().float()
+    n_edges, in_dim = a.shape
+    out = torch.empty(max(n_edges, 1), 16, dtype=torch.bfloat16, device=a.device)
+    with torch.cuda.device(a.device), _Launch("lg_pack_angles", 1, (n_edges, in_dim)):
+        rc = lib.alignn_lg_pack_angles(_p(a), _p(plan.eid), _p(out), n_edges, in_dim, _stream())
+    _lib.check(rc, "alignn_lg_pack_angles")
+    return out[:n_edges]
+
+
+def raw_lgattn_fwd(q: Tensor, k: Tensor, v: Tensor, qt: Tensor, a_csr: Tensor, w1: Tensor, b1: Tensor, plan: GraphPlan,
+                   heads: int, p_drop: float, seed: int, offset: int, rng_step: Optional[Tensor] = None):
+    """``qt``: [heads, n, 256] view (any row / head strides, unit channel stride).  Returns (aggv, abar, m, z, s)."""
+    lib = _lib.load()
+    n_nodes, hidden = q.shape
+    n_edges = plan.n_edges
+    dev = q.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    aggv = torch.empty(n_nodes, hidden, **f32)
+    abar = torch.empty(heads, n_nodes, hidden, dtype=q.dtype, device=dev)
+    m, z, s = (torch.empty(n_nodes, heads, **f32) for _ in range(3))
+    with torch.cuda.device(dev), _Launch("lgattn_fwd", 1, (n_nodes, n_edges, hidden, heads, q.element_size())):
+        rc = lib.alignn_lgattn_fwd(_p(q), _p(k), _p(v), _ld(q), _ld(k), _ld(v), _p(qt), int(qt.stride(1)),
+                                   int(qt.stride(0)), _p(a_csr), _p(w1), _p(b1), int(w1.size(1)), _p(plan.rowptr),
+                                   _p(plan.col), _p(aggv), _p(abar), int(abar.stride(1)), int(abar.stride(0)),
+                                   _p(m), _p(z), _p(s), n_nodes, n_edges, hidden, heads, _dtype_code(q), float(p_drop),
+                                   seed, offset, _p(rng_step), _stream())
+    _lib.check(rc, "alignn_lgattn_fwd")
+    return aggv, abar, m, z, s
+
+
+def csc_positions(plan: GraphPlan) -> Tensor:
+    """int32 [Ne]: CSR (target-sorted) position of the p-th edge of the CSC (source-sorted) order; cached on the plan."""
+    pos_t = getattr(plan, "_pos_t", None)
+    if pos_t is None:
+        inv = torch.empty(max(plan.n_edges, 1), dtype=torch.int32, device=plan.eid.device)
+        inv[plan.eid.long()] = torch.arange(plan.n_edges, dtype=torch.int32, device=plan.eid.device)
+        pos_t = inv[plan.eid_t.long()].contiguous()
+        plan._pos_t = pos_t
+    return pos_t
+
+
+def raw_lgattn_bwd(dagg: Tensor, dagg_lp: Tensor, agg: Tensor, q: Tensor, k: Tensor, v: Tensor, qt: Tensor, gt: Tensor,
+                   cvec: Optional[Tensor], a_csr: Tensor, w1: Tensor, b1: Tensor, m: Tensor, z: Tensor, plan: GraphPlan,
+                   heads: int, dq: Tensor, dk: Tensor, dv: Tensor, bbar: Tensor, p_drop: float, seed: int, offset: int,
+                   rng_step: Optional[Tensor] = None) -> Tensor:
+    """Both backward passes of the in-kernel-feature line-graph conv.  qt / gt / bbar: [heads, n, 256] views (any row /
+    head strides).  Returns coef [Ne, 8] (CSR order) for :func:`raw_lg_angle_grad`."""
+    lib = _lib.load()
+    n_nodes, hidden = q.shape
+    n_edges = plan.n_edges
+    dev = q.device
+    coef = torch.empty(max(n_edges, 1), 2 * heads, dtype=torch.float32, device=dev)
+    pos_t = csc_positions(plan)
+    with torch.cuda.device(dev):
+        with _Launch("lgattn_bwd_dst", 1, (n_nodes, n_edges, hidden, heads, q.element_size())):
+            rc = lib.alignn_lgattn_bwd_dst(
+                _p(dagg), _p(dagg_lp), _p(agg), _p(q), _p(k), _p(v), _ld(q), _ld(k), _ld(v),
+                _p(qt), int(qt.stride(1)), int(qt.stride(0)), _p(gt), int(gt.stride(1)), int(gt.stride(0)),
+                _p(cvec), _p(a_csr), _p(w1), _p(b1), int(w1.size(1)), _p(m), _p(z), _p(plan.rowptr), _p(plan.col),
+                _p(dq), _ld(dq), _p(bbar), int(bbar.stride(1)), int(bbar.stride(0)), _p(coef), n_nodes, n_edges, hidden,
+                heads, _dtype_code(q), float(p_drop), seed, offset, _p(rng_step), _stream())
+        _lib.check(rc, "alignn_lgattn_bwd_dst")
+        with _Launch("edgeattn_bwd_src", 1, (n_nodes, n_edges, hidden, heads, q.element_size())):
+            rc = lib.alignn_edgeattn_bwd_src(_p(dagg), _p(q), _ld(q), _p(coef), _p(plan.rowptr_t), _p(plan.col_t),
+                                             _p(pos_t), _p(dk), _p(dv), _ld(dk), n_nodes, n_edges, hidden, heads,
+                                             _dtype_code(q), _stream())
+        _lib.check(rc, "alignn_edgeattn_bwd_src")
+    return coef
+
+
+def raw_lg_angle_grad(a_csr: Tensor, w1: Tensor, b1: Tensor, plan: GraphPlan, coefs, qts, gts):
+    """(dW1 [256, in_dim], db1 [256]) in fp32 from the coefficient tensors of all line-graph layers."""
+    lib = _lib.load()
+    in_dim = int(w1.size(1))
+    dev = w1.device
+    n_nodes, n_edges = plan.n_nodes, plan.n_edges
+    f32 = dict(dtype=torch.float32, device=dev)
+    total = torch.zeros((in_dim + 1) * 256, **f32)
+    partials = torch.empty(int(lib.alignn_lg_angle_grad_partial_floats(n_nodes, n_edges)), **f32)
+    for lo in range(0, len(coefs), 4):
+        c, qq, gg = coefs[lo:lo + 4], qts[lo:lo + 4], gts[lo:lo + 4]
+        n = len(c)
+        out = torch.empty((in_dim + 1) * 256, **f32)
+        arr = lambda ts: (ctypes.c_void_p * n)(*[t.data_ptr() for t in ts])   # noqa: E731
+        with torch.cuda.device(dev), _Launch("lg_angle_grad", 2, (n_nodes, n_edges, n)):
+            rc = lib.alignn_lg_angle_grad(_p(a_csr), _p(w1), _p(b1), in_dim, _p(plan.rowptr), n, arr(c), arr(qq), arr(gg),
+                                          int(qq[0].stride(1)), int(qq[0].stride(0)), int(gg[0].stride(1)),
+                                          int(gg[0].stride(0)), _p(partials), _p(out), n_nodes, n_edges, _stream())
+        _lib.check(rc, "alignn_lg_angle_grad")
+        total = out if lo == 0 and len(coefs) <= 4 else total + out
+    dw1 = total[:in_dim * 256].view(in_dim, 256).t().contiguous()
+    return dw1, total[in_dim * 256:].clone()
+
+
 def raw_edgeattn_bwd(dagg: Tensor, dagg_lp: Optional[Tensor], agg: Tensor, q: Tensor, k: Tensor, v: Tensor, qt: Tensor,
                      gt: Tensor, cvec: Optional[Tensor], feat: Tensor, m: Tensor, z: Tensor, plan: GraphPlan, heads: int,
                      dq: Tensor, dk: Tensor, dv: Tensor, df_in: Optional[Tensor], df_out: Optional[Tensor],

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define ALIGNN_ABI_VERSION 5
+#define ALIGNN_ABI_VERSION 7
 
 #define ALIGNN_F32 0
 #define ALIGNN_BF16 1
@@ -189,6 +189,77 @@ int alignn_edgeattn_mma_bwd_dst(const float *dagg, const void *dagg_lp, const fl
                                 const void *df_in, void *df_out, int relu_mask,
                                 int64_t n_nodes, int64_t n_edges, int hidden, int heads, int dtype,
                                 float p_drop, uint64_t seed, uint64_t offset, void *stream);
+
+/* Strided variants: qt / gt / abar / bbar addressed as base[row * ld + head * hs + channel] (e.g. column blocks of a
+ * fused projection), optional device dropout counter `rng_step` added to `offset`. */
+int alignn_edgeattn_mma_fwd_s(const void *q, const void *k, const void *v, int64_t ldq, int64_t ldk, int64_t ldv,
+                              const void *qt, int64_t ldqt, int64_t hsqt, const void *feat,
+                              const int32_t *rowptr, const int32_t *col, const int32_t *eid,
+                              float *aggv, void *abar, int64_t ldab, int64_t hsab,
+                              float *stat_m, float *stat_z, float *stat_s,
+                              int64_t n_nodes, int64_t n_edges, int hidden, int heads, int dtype,
+                              float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step, void *stream);
+int alignn_edgeattn_mma_bwd_dst_s(const float *dagg, const void *dagg_lp, const float *agg,
+                                  const void *q, const void *k, const void *v, int64_t ldq, int64_t ldk, int64_t ldv,
+                                  const void *qt, int64_t ldqt, int64_t hsqt, const void *gt, int64_t ldgt, int64_t hsgt,
+                                  const float *cvec, const void *feat, const float *stat_m, const float *stat_z,
+                                  const int32_t *rowptr, const int32_t *col, const int32_t *eid,
+                                  void *dq, int64_t lddq, void *bbar, int64_t ldbb, int64_t hsbb, float *coef,
+                                  const void *df_in, void *df_out, int relu_mask,
+                                  int64_t n_nodes, int64_t n_edges, int hidden, int heads, int dtype,
+                                  float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step, void *stream);
+
+/* ---- line-graph attention with the angle embedding recomputed in-kernel (hidden 256, 4 heads, bf16) ---------------
+ * Replaces `angle_encoder(lg_edge_attr)` (reference scripts/train.py:360-364, 554) + the line-graph TransformerConv
+ * of EdgeUpdateBlock (train.py:308, 315): f_ij = h1 = relu(W1 a_ij + b1) is rebuilt from the packed angle features
+ * inside the kernel instead of being read as a [L, 256] tensor (see csrc/lgattn.cu).  Same outputs as
+ * alignn_edgeattn_fwd; qt / abar are addressed as base[row * ld + head * hs + channel]; `rng_step` (optional device
+ * counter) is added to `offset` so that a captured CUDA graph draws fresh dropout masks on every replay.
+ *   alignn_lg_pack_angles : a_csr[p] = (bf16(a[eid[p], :]), 1, 0...)  -- [L, 16] bf16 in target-sorted order. */
+int alignn_lgattn_supported(int hidden, int heads, int in_dim, int dtype);
+int alignn_lg_pack_angles(const float *a, const int32_t *eid, void *a_csr, int64_t n_edges, int in_dim, void *stream);
+int alignn_lgattn_fwd(const void *q, const void *k, const void *v, int64_t ldq, int64_t ldk, int64_t ldv,
+                      const void *qt, int64_t ldqt, int64_t hsqt,
+                      const void *a_csr, const float *w1, const float *b1, int in_dim,
+                      const int32_t *rowptr, const int32_t *col,
+                      float *aggv, void *abar, int64_t ldab, int64_t hsab,
+                      float *stat_m, float *stat_z, float *stat_s,
+                      int64_t n_nodes, int64_t n_edges, int hidden, int heads, int dtype,
+                      float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step, void *stream);
+
+/* Backward of alignn_lgattn_fwd w.r.t. q (dq), qt (bbar) and -- through coef, consumed by alignn_edgeattn_bwd_src with
+ * the plan's CSC->CSR position map in place of eid_t -- k, v.  coef: f32 [L, 8] in target-sorted order, (a~_0..3,
+ * ds_0..3) per angle.  No [L, 256] feature gradient is produced: */
+int alignn_lgattn_bwd_dst(const float *dagg, const void *dagg_lp, const float *agg,
+                          const void *q, const void *k, const void *v, int64_t ldq, int64_t ldk, int64_t ldv,
+                          const void *qt, int64_t ldqt, int64_t hsqt, const void *gt, int64_t ldgt, int64_t hsgt,
+                          const float *cvec, const void *a_csr, const float *w1, const float *b1, int in_dim,
+                          const float *stat_m, const float *stat_z, const int32_t *rowptr, const int32_t *col,
+                          void *dq, int64_t lddq, void *bbar, int64_t ldbb, int64_t hsbb, float *coef,
+                          int64_t n_nodes, int64_t n_edges, int hidden, int heads, int dtype,
+                          float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step, void *stream);
+/* ... the gradient of the first angle-encoder Linear (reference scripts/train.py:360) is formed once per step from the
+ * coefficients of all (<= 4 per call) line-graph layers: out[r*256 + c] = dW1[c, r] (r < in_dim), out[in_dim*256 + c] =
+ * db1[c].  coef / qt / gt are HOST arrays of n_layers device pointers; partials: f32
+ * [alignn_lg_angle_grad_partial_floats()] scratch.  Deterministic (fixed-order reductions). */
+int64_t alignn_lg_angle_grad_partial_floats(int64_t n_nodes, int64_t n_edges);
+int alignn_lg_angle_grad(const void *a_csr, const float *w1, const float *b1, int in_dim,
+                         const int32_t *rowptr, int n_layers, const float *const *coef,
+                         const void *const *qt, const void *const *gt,
+                         int64_t ldqt, int64_t hsqt, int64_t ldgt, int64_t hsgt,
+                         float *partials, float *out, int64_t n_nodes, int64_t n_edges, void *stream);
+
+/* ---- fused global-norm clip + AdamW over one flat parameter bucket (reference scripts/train.py:690-699, 1516-1540) --
+ * params/grads/exp_avg/exp_avg_sq: f32 [n]; shadow_bf16: optional bf16 copy of the updated parameters; partials:
+ * f32 [alignn_adamw_partial_floats()]; step: f32[1] device step count (advanced here); lr2: f32[2] device learning
+ * rates of [0, split) and [split, n); norm_out: optional f32[1] total gradient norm; grad_scale multiplies the raw
+ * gradient (loss-scale / world-size factors).  max_norm <= 0 disables clipping. */
+int64_t alignn_adamw_partial_floats(void);
+int alignn_clip_adamw_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq,
+                           void *shadow_bf16, float *partials, float *step, const float *lr2,
+                           float *norm_out, int64_t n, int64_t split,
+                           float beta1, float beta2, float eps, float weight_decay, float max_norm,
+                           float grad_scale, void *stream);
 
 /* Epilogue variants for the streaming path: the aggregate arrives in parts (aggv f32 [rows,H]; agge storage dtype
  * [heads, rows, C]; c_t * S_t), xr / dxr are strided column slices; agg_out receives the assembled aggregate (saved

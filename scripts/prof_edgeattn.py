@@ -25,6 +25,10 @@ feat = torch.relu(torch.randn(e, H, device=dev, generator=g)).to(dt)
 dagg = torch.randn(n, H, device=dev, generator=g)
 cvec = torch.randn(H, device=dev, generator=g) * 0.1
 df = torch.empty_like(feat)
+a = torch.rand(e, 11, device=dev, generator=g)
+w1 = torch.randn(H, 11, device=dev, generator=g) * 0.5
+b1 = torch.randn(H, device=dev, generator=g) * 0.2
+a_csr = ops.pack_angles(a, plan) if dt == torch.bfloat16 else None
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 ops.STATS.events = True
 for it in range(iters + 3):
@@ -32,12 +36,20 @@ for it in range(iters + 3):
         torch.cuda.synchronize(); ops.STATS.reset()
     flush.zero_()
     aggv, abar, m, z, s = ops.raw_edgeattn_fwd(q, k, v, qt, feat, plan, h, 0.0, 0, 0)
+    if a_csr is not None:
+        flush.zero_()
+        ops.raw_lgattn_fwd(q, k, v, qt, a_csr, w1, b1, plan, h, 0.0, 0, 0)
     flush.zero_()
     ops.raw_edgeattn_bwd(dagg, None, aggv, q, k, v, qt, gt, cvec, feat, m, z, plan, h, dq, dk, dv, df if it % 2 else None, df,
                          False, 0.0, 0, 0)
 torch.cuda.synchronize()
 d = ops.STATS.durations_ms()
 sb = 2 if dt == torch.bfloat16 else 4
+if "lgattn_fwd" in d:
+    ms = statistics.median(x[0] for x in d["lgattn_fwd"])
+    by = edgeattn_bytes("edgeattn_fwd", n, e, H, h, sb)
+    print(f"{mode} {dt} lgattn_fwd (h1 recomputed in-kernel): {ms*1e3:.1f} us  {by/ms/1e6:.0f} GB/s of stored-feature "
+          f"algorithmic bytes ({by/ms/1e6/6452.8:.3f} of measured peak)  bytes={by}")
 for name in ("edgeattn_fwd", "edgeattn_bwd_dst", "edgeattn_bwd_src"):
     for accum in ((False, True) if name == "edgeattn_bwd_dst" else (False,)):
         xs = [x[0] for x in d[name] if name != "edgeattn_bwd_dst" or bool(x[1][5]) == accum]

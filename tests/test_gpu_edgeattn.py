@@ -139,7 +139,7 @@ def test_edgeattn_dropout_forward_backward_masks_agree(mma, monkeypatch):
     monkeypatch.setattr(ops, "USE_MMA", mma)
     case = list(make_case(256, 8000, 13, 300, torch.bfloat16))
     index, q, k, v, qt, f, dagg, gt, cvec, wc = case
-    case[3] = qt * 0         # no feature term: S, aggv depend on (q, k, v) only
+    case[4] = qt * 0         # no feature term: S, aggv depend on (q, k, v) only
     case[7] = gt * 0
     case[8] = cvec * 0
     got = run_kernels(*case, p=0.25, seed=1234)
@@ -152,3 +152,93 @@ def test_edgeattn_dropout_forward_backward_masks_agree(mma, monkeypatch):
     assert rel_err(other["aggv"], got["aggv"]) > 1e-3          # a different seed gives a different mask
     again = run_kernels(*case, p=0.25, seed=1234)
     assert torch.equal(again["aggv"], got["aggv"]) and torch.equal(again["dq"], got["dq"])   # bit-reproducible
+
+
+# ---- line-graph kernels with the angle embedding recomputed in-kernel (csrc/lgattn.cu) ---------------------------------
+def lg_case(n, e, seed, hub, in_dim=11):
+    index, q, k, v, qt, f, dagg, gt, cvec, wc = make_case(n, e, seed, hub, torch.bfloat16)
+    g = torch.Generator().manual_seed(seed + 7)
+    a = torch.rand(e, in_dim, generator=g).to(DEV)
+    w1 = (torch.randn(H, in_dim, generator=g) * 0.5).to(DEV)
+    b1 = (torch.randn(H, generator=g) * 0.2).to(DEV)
+    # what the reference computes under bf16 autocast: Linear(bf16 a, bf16 W1, bf16 b1) -> bf16 -> relu
+    pre = a.to(torch.bfloat16).float() @ w1.to(torch.bfloat16).float().t() + b1.to(torch.bfloat16).float()
+    feat = torch.relu(pre).to(torch.bfloat16)
+    return index, q, k, v, qt, feat, dagg, gt, cvec, wc, a, w1, b1
+
+
+@pytest.mark.parametrize("p", [0.0, 0.2])
+def test_lgattn_forward_matches_stored_feature_kernel(p):
+    n, e = 301, 7000
+    index, q, k, v, qt, feat, dagg, gt, cvec, wc, a, w1, b1 = lg_case(n, e, 21, 500)
+    plan = pkg.build_plan(index.to(DEV), n)
+    a_csr = ops.pack_angles(a, plan)
+    assert a_csr.shape == (e, 16) and float(a_csr[:, 11].min()) == 1.0 and float(a_csr[:, 12:].abs().max()) == 0.0
+    assert torch.equal(a_csr[:, :11], a[plan.eid.long()].to(torch.bfloat16))
+    got = ops.raw_lgattn_fwd(q, k, v, qt, a_csr, w1, b1, plan, HEADS, 0.0, 7, 3)
+    want = ops.raw_edgeattn_fwd(q, k, v, qt, feat, plan, HEADS, 0.0, 7, 3)
+    for name, x, y in zip(("aggv", "abar", "m", "z", "s"), got, want):
+        assert rel_err(x, y) < (1e-2 if name != "m" else 1e-3), name
+    if p > 0:   # row-interleaved qt/abar strides + dropout statistics
+        qt_i = qt.permute(1, 0, 2).contiguous().permute(1, 0, 2)           # [h, n, 256] view of an [n, h, 256] buffer
+        d1 = ops.raw_lgattn_fwd(q, k, v, qt_i, a_csr, w1, b1, plan, HEADS, p, 7, 3)
+        d2 = ops.raw_lgattn_fwd(q, k, v, qt, a_csr, w1, b1, plan, HEADS, p, 7, 3)
+        assert torch.equal(d1[0], d2[0]) and torch.equal(d1[1], d2[1])
+        step = torch.tensor([5], dtype=torch.int64, device=DEV)
+        d3 = ops.raw_lgattn_fwd(q, k, v, qt, a_csr, w1, b1, plan, HEADS, p, 7, 3, rng_step=step)
+        d4 = ops.raw_lgattn_fwd(q, k, v, qt, a_csr, w1, b1, plan, HEADS, p, 7, 8)
+        assert torch.equal(d3[0], d4[0]) and not torch.equal(d3[0], d2[0])   # device counter == host offset
+        s = d2[4][: n - 5]
+        assert abs(float(s.mean()) - 1.0) < 0.05
+
+
+def test_lgattn_backward_and_angle_gradient_match_stored_feature_kernels():
+    """dq / bbar / dk / dv of the in-kernel-feature backward == the stored-feature tensor-core backward fed with the
+    same h1; the fused angle-encoder gradient == (sum_l df_l * [h1 > 0])^T a from the stored-feature kernels' df."""
+    n, e, layers = 257, 6000, 3
+    index, q, k, v, qt, feat, dagg, gt, cvec, wc, a, w1, b1 = lg_case(n, e, 31, 300)
+    plan = pkg.build_plan(index.to(DEV), n)
+    a_csr = ops.pack_angles(a, plan)
+    g = torch.Generator().manual_seed(5)
+    coefs, qts, gts = [], [], []
+    df_total = torch.zeros(e, H, device=DEV)
+    for l in range(layers):
+        qt_l = (qt.float() * (1.0 + 0.3 * l)).to(torch.bfloat16)
+        gt_l = (gt.float() * (1.0 - 0.2 * l)).to(torch.bfloat16)
+        dagg_l = dagg * (1.0 + 0.1 * l)
+        p_drop, seed = (0.0, 0) if l != 1 else (0.1, 77)
+        aggv, abar, m, z, s = ops.raw_lgattn_fwd(q, k, v, qt_l, a_csr, w1, b1, plan, HEADS, p_drop, seed, 3)
+        agge = torch.bmm(abar.float(), wc.to(DEV).transpose(1, 2)).transpose(0, 1).reshape(n, H)
+        agg = aggv + agge + (cvec.view(HEADS, C) * s.unsqueeze(-1)).reshape(n, H)
+        dlp = dagg_l.to(torch.bfloat16)
+        outs = []
+        for jit in (True, False):
+            dproj = torch.zeros(n, 4 * H, dtype=torch.bfloat16, device=DEV)
+            dq, dk, dv = (dproj[:, t * H:(t + 1) * H] for t in range(3))
+            if jit:
+                bbar = torch.empty(HEADS, n, H, dtype=torch.bfloat16, device=DEV)
+                coef = ops.raw_lgattn_bwd(dagg_l, dlp, agg, q, k, v, qt_l, gt_l, cvec, a_csr, w1, b1, m, z, plan, HEADS,
+                                          dq, dk, dv, bbar, p_drop, seed, 3)
+                coefs.append(coef); qts.append(qt_l); gts.append(gt_l)
+                outs.append((dq.clone(), dk.clone(), dv.clone(), bbar))
+            elif p_drop == 0.0:    # (dropout streams differ between the families: eid- vs position-keyed)
+                df = torch.empty_like(feat)
+                bbar = ops.raw_edgeattn_bwd(dagg_l, dlp, agg, q, k, v, qt_l, gt_l, cvec, feat, m, z, plan, HEADS, dq, dk,
+                                            dv, None, df, False, 0.0, 0, 3)
+                outs.append((dq.clone(), dk.clone(), dv.clone(), bbar))
+                df_total += df.float()
+        if len(outs) == 2:
+            for name, x, y in zip(("dq", "dk", "dv", "bbar"), outs[0], outs[1]):
+                assert rel_err(x, y) < 1.5e-2, (l, name)
+    # angle gradient over the dropout-free layers, against the stored-feature df
+    keep = [0, 2]
+    dw1, db1 = ops.raw_lg_angle_grad(a_csr, w1, b1, plan, [coefs[i] for i in keep], [qts[i] for i in keep],
+                                     [gts[i] for i in keep])
+    masked = df_total * (feat.float() > 0)
+    want_w = masked.t() @ a.to(torch.bfloat16).float()
+    want_b = masked.sum(0)
+    assert rel_err(dw1, want_w) < 2e-2 and rel_err(db1, want_b) < 2e-2
+    # determinism + all three layers (incl. the dropout one) run
+    d1 = ops.raw_lg_angle_grad(a_csr, w1, b1, plan, coefs, qts, gts)
+    d2 = ops.raw_lg_angle_grad(a_csr, w1, b1, plan, coefs, qts, gts)
+    assert torch.equal(d1[0], d2[0]) and torch.equal(d1[1], d2[1]) and bool(torch.isfinite(d1[0]).all())
