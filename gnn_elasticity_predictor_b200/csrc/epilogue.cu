@@ -41,6 +41,7 @@ struct GateExtra {
     void *dagg_lp;         // backward: storage-dtype copy of dagg (may be null)
     int heads;
     int64_t ldxr, lddxr;   // row strides (elements) of xr and dxr
+    const uint64_t *rng_step;   // optional device counter added to the dropout offset (CUDA-graph replays)
 };
 
 template <typename T, int LANES>
@@ -109,7 +110,8 @@ gate_ln_fwd_kernel(const float *__restrict__ agg, const T *__restrict__ xr, cons
     float keep[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) keep[c] = 1.f;
-    if (p_drop > 0.f) dropout8(seed, offset, (uint64_t)row * hidden + ch, p_drop, inv_keep, keep);
+    if (p_drop > 0.f)
+        dropout8(seed, offset + (X.rng_step ? *X.rng_step : 0ull), (uint64_t)row * hidden + ch, p_drop, inv_keep, keep);
     F8 out;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -168,7 +170,8 @@ gate_ln_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ agg, 
         float keep[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) keep[c] = 1.f;
-        if (p_drop > 0.f && ok) dropout8(seed, offset, (uint64_t)row * hidden + ch, p_drop, inv_keep, keep);
+        if (p_drop > 0.f && ok)
+            dropout8(seed, offset + (X.rng_step ? *X.rng_step : 0ull), (uint64_t)row * hidden + ch, p_drop, inv_keep, keep);
         F8 xh, dxh;
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -477,7 +480,7 @@ extern "C" int64_t alignn_gate_ln_bwd_partial_rows(void) { return EPI_PARTIAL_BL
 static GateExtra plain_extra(int hidden) {
     GateExtra X;
     X.agge = nullptr; X.cvec = nullptr; X.stat_s = nullptr; X.agg_out = nullptr; X.dagg_lp = nullptr;
-    X.heads = 1; X.ldxr = hidden; X.lddxr = hidden;
+    X.heads = 1; X.ldxr = hidden; X.lddxr = hidden; X.rng_step = nullptr;
     return X;
 }
 
@@ -520,9 +523,11 @@ extern "C" int alignn_gate_ln_fwd2(const float *aggv, const void *agge, const fl
                                    const float *wbeta, const float *gamma, const float *bias,
                                    float *agg_out, float *y, void *y_lp, float *beta, float *mean, float *rstd,
                                    int64_t n_rows, int hidden, int dtype, float eps,
-                                   float p_drop, uint64_t seed, uint64_t offset, void *stream) {
+                                   float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step, void *stream) {
     GateExtra X = plain_extra(hidden);
     X.agge = agge; X.cvec = cvec; X.stat_s = stat_s; X.agg_out = agg_out; X.heads = heads; X.ldxr = ldxr;
+    X.rng_step = rng_step;
+    if (rng_step && (hidden % 8 || hidden > 256 || (256 % hidden))) return ALIGNN_ERR_BAD_SHAPE;   // fast mapping only
     return gate_ln_fwd_impl(aggv, xr, x, wbeta, gamma, bias, y, y_lp, beta, mean, rstd, n_rows, hidden, dtype, eps,
                             p_drop, seed, offset, X, true, stream);
 }
@@ -565,9 +570,10 @@ extern "C" int alignn_gate_ln_bwd2(const float *dy, const float *agg, const void
                                    const float *beta, const float *mean, const float *rstd,
                                    float *dagg, void *dagg_lp, void *dxr, int64_t lddxr, float *partials, float *dparams,
                                    int64_t n_rows, int hidden, int dtype,
-                                   float p_drop, uint64_t seed, uint64_t offset, void *stream) {
+                                   float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step, void *stream) {
     GateExtra X = plain_extra(hidden);
-    X.dagg_lp = dagg_lp; X.ldxr = ldxr; X.lddxr = lddxr;
+    X.dagg_lp = dagg_lp; X.ldxr = ldxr; X.lddxr = lddxr; X.rng_step = rng_step;
+    if (rng_step && (hidden % 8 || hidden > 256 || (256 % hidden))) return ALIGNN_ERR_BAD_SHAPE;
     return gate_ln_bwd_impl(dy, agg, xr, wbeta, gamma, bias, beta, mean, rstd, dagg, dxr, partials, dparams, n_rows,
                             hidden, dtype, p_drop, seed, offset, X, true, stream);
 }

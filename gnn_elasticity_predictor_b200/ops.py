@@ -374,6 +374,53 @@ def raw_edgeattn_fwd(q: Tensor, k: Tensor, v: Tensor, qt: Tensor, feat: Tensor, 
     return aggv, abar, m, z, s
 
 
+def raw_attn_fwd_s(q: Tensor, k: Tensor, v: Tensor, qt: Tensor, feat: Tensor, plan: GraphPlan, heads: int,
+                   p_drop: float, seed: int, offset: int, rng_step: Optional[Tensor] = None):
+    """Stored-feature tensor-core forward; ``qt`` is a [heads, n, 256] view with arbitrary row / head strides."""
+    lib = _lib.load()
+    n_nodes, hidden = q.shape
+    n_edges = plan.n_edges
+    dev = q.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    aggv = torch.empty(n_nodes, hidden, **f32)
+    abar = torch.empty(heads, n_nodes, hidden, dtype=q.dtype, device=dev)
+    m, z, s = (torch.empty(n_nodes, heads, **f32) for _ in range(3))
+    with torch.cuda.device(dev), _Launch("edgeattn_fwd", 1, (n_nodes, n_edges, hidden, heads, q.element_size())):
+        rc = lib.alignn_edgeattn_mma_fwd_s(_p(q), _p(k), _p(v), _ld(q), _ld(k), _ld(v), _p(qt), int(qt.stride(1)),
+                                           int(qt.stride(0)), _p(feat), _p(plan.rowptr), _p(plan.col), _p(plan.eid),
+                                           _p(aggv), _p(abar), int(abar.stride(1)), int(abar.stride(0)), _p(m), _p(z),
+                                           _p(s), n_nodes, n_edges, hidden, heads, _dtype_code(q), float(p_drop), seed,
+                                           offset, _p(rng_step), _stream())
+    _lib.check(rc, "alignn_edgeattn_mma_fwd_s")
+    return aggv, abar, m, z, s
+
+
+def raw_attn_bwd_s(dagg: Tensor, dagg_lp: Tensor, agg: Tensor, q: Tensor, k: Tensor, v: Tensor, qt: Tensor, gt: Tensor,
+                   cvec: Optional[Tensor], feat: Tensor, m: Tensor, z: Tensor, plan: GraphPlan, heads: int, dq: Tensor,
+                   dk: Tensor, dv: Tensor, bbar: Tensor, df_out: Optional[Tensor], p_drop: float, seed: int, offset: int,
+                   rng_step: Optional[Tensor] = None) -> None:
+    """Stored-feature tensor-core backward (both passes); qt / gt / bbar are [heads, n, 256] views."""
+    lib = _lib.load()
+    n_nodes, hidden = q.shape
+    n_edges = plan.n_edges
+    dev = q.device
+    coef = torch.empty(max(n_edges, 1), 2 * heads, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        with _Launch("edgeattn_bwd_dst", 1, (n_nodes, n_edges, hidden, heads, q.element_size(), False)):
+            rc = lib.alignn_edgeattn_mma_bwd_dst_s(
+                _p(dagg), _p(dagg_lp), _p(agg), _p(q), _p(k), _p(v), _ld(q), _ld(k), _ld(v), _p(qt), int(qt.stride(1)),
+                int(qt.stride(0)), _p(gt), int(gt.stride(1)), int(gt.stride(0)), _p(cvec), _p(feat), _p(m), _p(z),
+                _p(plan.rowptr), _p(plan.col), _p(plan.eid), _p(dq), _ld(dq), _p(bbar), int(bbar.stride(1)),
+                int(bbar.stride(0)), _p(coef), None, _p(df_out), 0, n_nodes, n_edges, hidden, heads, _dtype_code(q),
+                float(p_drop), seed, offset, _p(rng_step), _stream())
+        _lib.check(rc, "alignn_edgeattn_mma_bwd_dst_s")
+        with _Launch("edgeattn_bwd_src", 1, (n_nodes, n_edges, hidden, heads, q.element_size())):
+            rc = lib.alignn_edgeattn_bwd_src(_p(dagg), _p(q), _ld(q), _p(coef), _p(plan.rowptr_t), _p(plan.col_t),
+                                             _p(plan.eid_t), _p(dk), _p(dv), _ld(dk), n_nodes, n_edges, hidden, heads,
+                                             _dtype_code(q), _stream())
+        _lib.check(rc, "alignn_edgeattn_bwd_src")
+
+
 def pack_angles(a: Tensor, plan: GraphPlan) -> Tensor:
     """``[L, 16]`` bf16 angle features in the plan's target-sorted order, bias column set to 1 (``csrc/lgattn.cu``)."""
     lib = _lib.load()
@@ -511,7 +558,7 @@ def raw_edgeattn_bwd(dagg: Tensor, dagg_lp: Optional[Tensor], agg: Tensor, q: Te
 
 def raw_gate_ln_fwd2(aggv: Tensor, agge: Optional[Tensor], cvec: Optional[Tensor], stat_s: Optional[Tensor],
                      heads: int, xr: Tensor, x: Tensor, wbeta: Tensor, gamma: Tensor, bias: Tensor, eps: float,
-                     p_drop: float, seed: int, offset: int, want_lp: bool):
+                     p_drop: float, seed: int, offset: int, want_lp: bool, rng_step: Optional[Tensor] = None):
     lib = _lib.load()
     n_rows, hidden = aggv.shape
     dev = aggv.device
@@ -524,13 +571,14 @@ def raw_gate_ln_fwd2(aggv: Tensor, agge: Optional[Tensor], cvec: Optional[Tensor
         rc = lib.alignn_gate_ln_fwd2(_p(aggv), _p(agge), _p(cvec), _p(stat_s), heads, _p(xr), _ld(xr), _p(x), _p(wbeta),
                                      _p(gamma), _p(bias), _p(agg), _p(y), _p(y_lp), _p(beta), _p(mean), _p(rstd),
                                      n_rows, hidden, _dtype_code(xr), float(eps), float(p_drop), seed, offset,
-                                     _stream())
+                                     _p(rng_step), _stream())
     _lib.check(rc, "alignn_gate_ln_fwd2")
     return y, y_lp, agg, beta, mean, rstd
 
 
 def raw_gate_ln_bwd2(dy: Tensor, agg: Tensor, xr: Tensor, wbeta: Tensor, gamma: Tensor, bias: Tensor, beta: Tensor,
-                     mean: Tensor, rstd: Tensor, dxr: Tensor, want_lp: bool, p_drop: float, seed: int, offset: int):
+                     mean: Tensor, rstd: Tensor, dxr: Tensor, want_lp: bool, p_drop: float, seed: int, offset: int,
+                     rng_step: Optional[Tensor] = None):
     """Returns (dagg f32, dagg_lp or None, dparams f32 [5*hidden]); writes dxr (strided) in place."""
     lib = _lib.load()
     n_rows, hidden = agg.shape
@@ -544,7 +592,7 @@ def raw_gate_ln_bwd2(dy: Tensor, agg: Tensor, xr: Tensor, wbeta: Tensor, gamma: 
         rc = lib.alignn_gate_ln_bwd2(_p(dy), _p(agg), _p(xr), _ld(xr), _p(wbeta), _p(gamma), _p(bias), _p(beta),
                                      _p(mean), _p(rstd), _p(dagg), _p(dagg_lp), _p(dxr), _ld(dxr), _p(partials),
                                      _p(dparams), n_rows, hidden, _dtype_code(xr), float(p_drop), seed, offset,
-                                     _stream())
+                                     _p(rng_step), _stream())
     _lib.check(rc, "alignn_gate_ln_bwd2")
     return dagg, dagg_lp, dparams
 

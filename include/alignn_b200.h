@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define ALIGNN_ABI_VERSION 7
+#define ALIGNN_ABI_VERSION 8
 
 #define ALIGNN_F32 0
 #define ALIGNN_BF16 1
@@ -263,19 +263,20 @@ int alignn_clip_adamw_step(float *params, const float *grads, float *exp_avg, fl
 
 /* Epilogue variants for the streaming path: the aggregate arrives in parts (aggv f32 [rows,H]; agge storage dtype
  * [heads, rows, C]; c_t * S_t), xr / dxr are strided column slices; agg_out receives the assembled aggregate (saved
- * for backward), dagg_lp a storage-dtype copy of dagg for the gt projection. */
+ * for backward), dagg_lp a storage-dtype copy of dagg for the gt projection; rng_step: optional device counter added
+ * to the dropout offset (hidden in {8..256} dividing 256 only). */
 int alignn_gate_ln_fwd2(const float *aggv, const void *agge, const float *cvec, const float *stat_s,
                         int heads, const void *xr, int64_t ldxr, const float *x,
                         const float *wbeta, const float *gamma, const float *bias,
                         float *agg_out, float *y, void *y_lp, float *beta, float *mean, float *rstd,
                         int64_t n_rows, int hidden, int dtype, float eps,
-                        float p_drop, uint64_t seed, uint64_t offset, void *stream);
+                        float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step, void *stream);
 int alignn_gate_ln_bwd2(const float *dy, const float *agg, const void *xr, int64_t ldxr,
                         const float *wbeta, const float *gamma, const float *bias,
                         const float *beta, const float *mean, const float *rstd,
                         float *dagg, void *dagg_lp, void *dxr, int64_t lddxr, float *partials, float *dparams,
                         int64_t n_rows, int hidden, int dtype,
-                        float p_drop, uint64_t seed, uint64_t offset, void *stream);
+                        float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step, void *stream);
 
 /* First angle-encoder layer: h1 = relu(W1 a + b1) (reference scripts/train.py:360-362 applied at :554) and its
  * parameter gradients from the ReLU-masked feature gradient dpre: out[f*256 + c] = dW1[c,f] (f < in_dim),
