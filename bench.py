@@ -29,6 +29,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
+NCU_TRAFFIC = {"lgattn_fwd": 706576128}
 METRIC = "ALIGNN train graphs/sec (fwd+bwd)"
 UNIT = "graphs/s"
 ARCH = dict(node_dim=206, edge_dim=36, angle_dim=11, global_dim=289, target_dim=2, hidden=256, layers=4, heads=4)
@@ -55,6 +57,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-optimizer", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="run every step eagerly (no CUDA-graph replay)")
     return ap.parse_args()
 
 
@@ -146,6 +149,23 @@ def edgeattn_bytes(kind, n_nodes, n_edges, hidden, heads, s, accum=False):
     raise ValueError(kind)
 
 
+def lgattn_bytes(kind, n_nodes, n_edges, hidden, heads, s):
+    """Algorithmic bytes of the in-kernel-feature line-graph kernels (csrc/lgattn.cu): per angle
+    only the packed 32-byte feature row + the 4-byte source id (+ the 32-byte coefficient row in backward); every
+    per-bond operand row counted once."""
+    wide = s * heads * hidden * n_nodes                       # one [heads, Nn, H] tensor (qt, gt, abar, bbar)
+    node = s * hidden * n_nodes                               # one [Nn, H] storage-dtype tensor
+    if kind == "lgattn_fwd":
+        return (3 * node + wide + 36 * n_edges                        # q,k,v, qt, a_csr + col
+                + wide + 4 * hidden * n_nodes + 12 * heads * n_nodes  # abar, aggv, stats
+                + 4 * (n_nodes + 1))
+    if kind == "lgattn_bwd_dst":
+        return (3 * node + 2 * wide + 36 * n_edges + 8 * hidden * n_nodes + node   # q,k,v, qt,gt, a_csr+col, dagg,agg, dagg_lp
+                + node + wide + 8 * heads * n_edges                                 # dq, bbar, coef
+                + 8 * heads * n_nodes + 4 * (n_nodes + 1))
+    raise ValueError(kind)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference's CPU path
 # ---------------------------------------------------------------------------------------------------------
@@ -225,38 +245,31 @@ def main_b200(args):
     n_graphs, atoms, k = WORKLOADS[args.workload]
     cd = torch.bfloat16 if args.dtype == "bf16" else torch.float32
 
+    from gnn_elasticity_predictor_b200 import engine
+
     # members (reference: --ensemble-size 5, seeds seed + 1007*i, train.py:2053)
-    members, buckets, optims = [], [], []
+    members, steppers = [], []
     for m in range(args.members):
         torch.manual_seed(42 + 1007 * m)
         model = pkg.HeteroAlignnRegressor(pkg.AlignnRegressor(dropout=args.dropout, **ARCH), ARCH["target_dim"]).to(dev)
         model.base.compute_dtype = cd
         model.train()
         members.append(model)
-        buckets.append(dp.FlatGradBucket(model.parameters()))
-        optims.append(torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True))
+        steppers.append(engine.TrainStep(model, lr=1e-3, weight_decay=1e-4, max_norm=5.0, loss_scale=1.0 / world,
+                                         graph=not args.no_graph, optimizer=not args.no_optimizer))
 
     host_batches = [pkg.synthetic_batch(n_graphs, atoms, k, seed=1000 * rank + i, lg_inc=args.lg_inc).pin_memory()
                     for i in range(2)]
     sizes = host_batches[0].sizes
     dev_batch = host_batches[0].to(dev)
     target_z = pkg.zscore_targets(dev_batch.y, dev_batch.num_graphs)
-    loss_scale = 1.0 / world
+    LG_KERNELS = ("lgattn_fwd", "lgattn_bwd_dst", "edgeattn_fwd", "edgeattn_bwd_dst", "edgeattn_bwd_src", "conv_fwd",
+                  "conv_bwd")
+    ops.STATS.graph_events = True           # event-record nodes around the line-graph kernels inside the captured graphs
+    ops.STATS.graph_filter = set(LG_KERNELS)
 
     def step(i, batch, tz):
-        m = i % args.members
-        model, bucket = members[m], buckets[m]
-        bucket.zero()
-        model.base.build_plans(batch)                 # CSR/CSC sort of this batch: part of every step
-        mean, logvar = model(batch)
-        loss = pkg.gaussian_nll_loss(mean.float(), logvar.float(), tz)
-        (loss * loss_scale).backward()
-        if world > 1:
-            bucket.all_reduce()
-        if not args.no_optimizer:
-            dp.global_grad_clip(bucket, 5.0)
-            optims[m].step()
-        return loss, mean, logvar
+        return steppers[i % args.members].step(batch, tz)
 
     def barrier():
         if world > 1:
@@ -264,7 +277,7 @@ def main_b200(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing -----------------------------------------------------------------------------
-    for i in range(args.members):                     # priming: every member once (allocator, cuBLAS heuristics)
+    for i in range(3 * args.members):                 # priming: allocator, cuBLAS heuristics, graph capture per member
         step(i, dev_batch, target_z)
     for i in range(args.warmup):
         step(i, dev_batch, target_z)
@@ -285,7 +298,9 @@ def main_b200(args):
     ops.STATS.events = False
     elapsed_ms = t0.elapsed_time(t1)
     launches = ops.STATS.kernels
-    durations = ops.STATS.durations_ms()
+    graphed = sum(s_.replays for s_ in steppers) > 0
+    # graph mode: durations of the event nodes inside the replayed graphs (last replay of every member's graph)
+    durations = ops.STATS.graph_durations_ms() if graphed else ops.STATS.durations_ms()
     t = torch.tensor([elapsed_ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -297,12 +312,14 @@ def main_b200(args):
     peak, peak_src = load_peaks()
     s_bytes = 2 if cd == torch.bfloat16 else 4
     kern = {}
-    for name in ("conv_fwd", "conv_bwd", "edgeattn_fwd", "edgeattn_bwd_dst", "edgeattn_bwd_src"):
+    for name in LG_KERNELS:
         recs = [(ms, meta) for ms, meta in durations.get(name, []) if meta and meta[1] == sizes["L"]]
         if recs:
             ms = statistics.mean(r[0] for r in recs)
             nn_, ne_, h_, hd_ = recs[0][1][:4]
-            if name.startswith("conv_"):
+            if name.startswith("lgattn_"):
+                b = lgattn_bytes(name, nn_, ne_, h_, hd_, s_bytes)
+            elif name.startswith("conv_"):
                 b = conv_bytes(nn_, ne_, h_, hd_, s_bytes, fwd=(name == "conv_fwd"))
             elif name == "edgeattn_bwd_dst":
                 # accumulate-in-place launches move one more [L,H] read; average over the launches as timed
@@ -310,16 +327,18 @@ def main_b200(args):
             else:
                 b = edgeattn_bytes(name, nn_, ne_, h_, hd_, s_bytes)
             kern[name] = {"ms": ms, "bytes": b, "gbs": b / (ms * 1e-3) / 1e9, "launches_timed": len(recs)}
-    totals = {name: sum(ms for ms, _ in v) / args.steps for name, v in durations.items()}
+    totals = {name: sum(ms for ms, _ in v) / (args.members if graphed else args.steps) for name, v in durations.items()}
     roofline = None
     if kern:
         dom = max(kern, key=lambda n: kern[n]["ms"])
         roofline = {"kernel": f"alignn_{dom} (line-graph conv, Nn={sizes['E']}, Ne={sizes['L']})", "bound": "hbm",
-                    "note": "streaming kernels trade the per-edge GEMM for ~2.6k (fwd) / ~5.9k (bwd) fp32 MAC per edge: "
-                            "they are FMA/issue-limited before HBM-limited (DESIGN.md section 3)",
+                    "note": "per-angle work is rebuilt on the tensor pipe (mma.sync) from 36 B/angle; the kernel is "
+                            "issue/latency-limited before it is HBM-limited (DESIGN.md section 3, profiles/)",
+                    "timed": ("CUDA external-event nodes inside the replayed step graphs, last replay of each member's "
+                              "graph" if graphed else "CUDA events around every C-ABI call in the timed region"),
                     "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": kern[dom]["gbs"] / peak,
-                    "peak_source": peak_src, "traffic": None, "algorithmic_bytes": kern[dom]["bytes"],
-                    "avg_launch_ms": kern[dom]["ms"],
+                    "peak_source": peak_src, "traffic": NCU_TRAFFIC.get(dom), "algorithmic_bytes": kern[dom]["bytes"],
+                    "avg_launch_ms": kern[dom]["ms"], "launches_timed": kern[dom]["launches_timed"],
                     "others": {n: {"GB/s": round(v["gbs"], 1), "frac": round(v["gbs"] / peak, 4), "ms": round(v["ms"], 4)}
                                for n, v in kern.items() if n != dom}}
 
@@ -369,6 +388,21 @@ def main_b200(args):
                "how": "pinned host batch -> H2D (copy stream, next batch overlapped) -> plan + fwd + loss + bwd"
                       + ("" if args.no_optimizer else " + clip + AdamW") + " -> D2H loss/mean/logvar + sync, every step"}
 
+    # ---- per-kernel breakdown of one step per member: eager pass with CUDA events, OUTSIDE the timed regions ---------
+    if graphed:
+        for s_ in steppers:
+            s_.use_graph = False
+        barrier()
+        ops.STATS.reset()
+        ops.STATS.events = True
+        for i in range(args.members):
+            step(i, dev_batch, target_z)
+        barrier()
+        ops.STATS.events = False
+        totals = {name: sum(ms for ms, _ in v) / args.members for name, v in ops.STATS.durations_ms().items()}
+        for s_ in steppers:
+            s_.use_graph = True
+
     # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -387,13 +421,16 @@ def main_b200(args):
                 "arch": ARCH, "dropout": args.dropout, "lg_inc": args.lg_inc, "global_batch": n_graphs * world,
                 "parallelism": f"dp{world}" if world > 1 else "single",
                 "step": "plan(CSR/CSC sort) + fwd + Gaussian NLL + bwd" + (" + NCCL allreduce(flat grads)" if world > 1 else "")
-                        + ("" if args.no_optimizer else " + global-norm clip 5.0 + AdamW(fused)"),
+                        + ("" if args.no_optimizer else " + global-norm clip 5.0 + AdamW (one fused kernel pair)")
+                        + ("; whole step replayed as one CUDA graph per member" if graphed else "; eager launches"),
                 "l2": "per-step working set (>= 3 GB of edge projections) >> 126 MB L2; no explicit flush",
                 "projections": "per-NODE projections only (the per-edge E x H x H GEMMs are eliminated algebraically); "
                                + ("cuBLAS via torch (bf16)" if cd == torch.bfloat16 else "cuBLAS via torch (fp32, TF32 off)"),
             },
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "kernel_ms_per_step": {k2: round(v, 4) for k2, v in sorted(totals.items())},
+            "kernel_ms_per_step_how": ("eager pass with CUDA events after the timed regions (hand-written kernels only)"
+                                       if graphed else "CUDA events in the timed region (hand-written kernels only)"),
         }
         print(json.dumps(line), flush=True)
     if world > 1:

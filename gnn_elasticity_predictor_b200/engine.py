@@ -1,0 +1,204 @@
+"""One-call training step over the hot path: plan + forward + Gaussian NLL + backward (+ gradient all-reduce) + global-norm
+clip + AdamW, optionally captured into a CUDA graph per batch signature.
+
+What it replaces in the reference is the body of ``train_epoch_hetero``'s batch loop (``scripts/train.py:639-699``):
+``model(batch)`` -> NLL + log-sigma L2 (``:655-681``) -> ``backward()`` (``:691/697``) -> ``clip_grad_norm_(5.0)`` (``:693,698``)
+-> ``AdamW.step()`` with the two learning-rate groups built at ``:1516-1540`` (base + mean heads | log-variance heads).
+
+B200 specifics:
+
+* all parameters live in ONE flat fp32 buffer (``model.parameters()`` order, log-variance heads last), their gradients in a
+  second flat buffer with identical offsets (:class:`dp.FlatGradBucket`), Adam moments in two more: the optimizer is ONE
+  fused kernel pair (``csrc/optim.cu``: deterministic norm -> clip -> decoupled-weight-decay Adam), the DP exchange ONE
+  NCCL all-reduce;
+* nothing in the step synchronises with the host, so the whole step is captured once per batch signature
+  ``(B, N, E, L)`` into a CUDA graph and replayed: ~1 200 kernel launches collapse into one ``cudaGraphLaunch``.  Dropout
+  masks stay fresh across replays through a device-side step counter added to every Philox offset (``ops.RNG_STEP``);
+  the learning rates and the Adam step count also live on the device;
+* batches whose signature has not been captured (ragged datasets) run the same code eagerly.
+
+The step leaves ``param.grad`` populated (views of the flat bucket), so callers can still inspect gradients.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+from . import _lib, ops
+from .dp import FlatGradBucket
+from .modules import HeteroAlignnRegressor, gaussian_nll_loss
+from .synthetic import GraphBatch
+
+_P = ops._p
+
+
+class FusedAdamW:
+    """Clip + AdamW over the flat parameter bucket (``alignn_clip_adamw_step``); two LR groups split at ``split``."""
+
+    def __init__(self, bucket: FlatGradBucket, split: int, lr: float, lr_sigma: Optional[float], weight_decay: float,
+                 betas=(0.9, 0.999), eps: float = 1e-8, max_norm: float = 5.0, n_active: Optional[int] = None):
+        self.bucket, self.split = bucket, int(split)
+        dev = bucket.flat.device
+        n = bucket.flat.numel()
+        # parameters past n_active never receive a gradient (torch's AdamW skips such parameters entirely: no decay)
+        self.n_active = n if n_active is None else int(n_active)
+        self.flat_params = torch.empty(n, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            self.flat_params.zero_()
+            for p, off in zip(bucket.params, bucket.offsets):
+                self.flat_params[off:off + p.numel()].copy_(p.detach().reshape(-1))
+                p.data = self.flat_params[off:off + p.numel()].view_as(p)
+        self.exp_avg = torch.zeros_like(self.flat_params)
+        self.exp_avg_sq = torch.zeros_like(self.flat_params)
+        lib = _lib.load()
+        self.partials = torch.zeros(int(lib.alignn_adamw_partial_floats()), dtype=torch.float32, device=dev)
+        self.step_count = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.lr = torch.tensor([lr, lr if lr_sigma is None else lr_sigma], dtype=torch.float32, device=dev)
+        self.norm = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.betas, self.eps, self.weight_decay, self.max_norm = betas, float(eps), float(weight_decay), float(max_norm)
+
+    def set_lr(self, lr: float, lr_sigma: Optional[float] = None) -> None:
+        """Scheduler hook (reference ``_cosine_schedule``, ``train.py:1215``): device-side, seen by captured graphs."""
+        self.lr.copy_(torch.tensor([lr, lr if lr_sigma is None else lr_sigma], dtype=torch.float32), non_blocking=True)
+
+    def step(self, grad_scale: float = 1.0) -> None:
+        lib = _lib.load()
+        n = self.n_active
+        with torch.cuda.device(self.flat_params.device), ops._Launch("clip_adamw", 2, (n,)):
+            rc = lib.alignn_clip_adamw_step(_P(self.flat_params), _P(self.bucket.flat), _P(self.exp_avg),
+                                            _P(self.exp_avg_sq), None, _P(self.partials), _P(self.step_count),
+                                            _P(self.lr), _P(self.norm), n, self.split, self.betas[0], self.betas[1],
+                                            self.eps, self.weight_decay, self.max_norm, float(grad_scale), ops._stream())
+        _lib.check(rc, "alignn_clip_adamw_step")
+
+    def state(self):
+        return [self.flat_params, self.exp_avg, self.exp_avg_sq, self.step_count]
+
+
+class _Captured:
+    __slots__ = ("graph", "graph_opt", "batch", "tz", "loss", "mean", "logvar", "kernels")
+
+
+class TrainStep:
+    """``step(batch, target_z) -> (loss, mean, logvar)`` -- device tensors, valid until the next call.
+
+    ``graph=True`` captures one CUDA graph per batch signature after ``graph_warmup`` eager steps on that signature (the
+    warm-up steps are real training steps).  ``loss_scale`` is the DP weight ``B_local / B_global``."""
+
+    def __init__(self, model: HeteroAlignnRegressor, lr: float = 1e-3, lr_sigma: Optional[float] = None,
+                 weight_decay: float = 1e-4, max_norm: float = 5.0, log_sigma_l2: float = 0.1,
+                 min_logvar_floor: float = -2.9, loss_scale: float = 1.0, graph: bool = True, graph_warmup: int = 2,
+                 optimizer: bool = True, group=None):
+        self.model = model
+        params = [p for p in model.parameters() if p.requires_grad]
+        if not params or not params[0].is_cuda:
+            raise RuntimeError("TrainStep needs a model on a CUDA device (there is no CPU path)")
+        self.dev = params[0].device
+        # bucket order: [base (used) + mean heads | log-variance heads | base.output_heads]: the hetero forward never
+        # touches base.output_heads (train.py:579-586), so they get no gradient and the reference's optimizer skips them
+        sigma = {id(p) for p in model.logvar_heads.parameters()}
+        unused = {id(p) for p in model.base.output_heads.parameters()}
+        ordered = ([p for p in params if id(p) not in sigma and id(p) not in unused]
+                   + [p for p in params if id(p) in sigma] + [p for p in params if id(p) in unused])
+        self.bucket = FlatGradBucket(ordered)
+        split = n_active = self.bucket.flat.numel()
+        for p, off in zip(self.bucket.params, self.bucket.offsets):
+            if id(p) in sigma:
+                split = min(split, off)
+            if id(p) in unused:
+                n_active = min(n_active, off)
+        split = min(split, n_active)
+        self.opt = FusedAdamW(self.bucket, split, lr, lr_sigma, weight_decay, max_norm=max_norm,
+                              n_active=n_active) if optimizer else None
+        self.log_sigma_l2, self.floor, self.loss_scale = float(log_sigma_l2), float(min_logvar_floor), float(loss_scale)
+        self.use_graph, self.graph_warmup, self.group = bool(graph), int(graph_warmup), group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rng_step = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self._captured: Dict[Tuple, _Captured] = {}
+        self._seen: Dict[Tuple, int] = {}
+        self.replays = 0
+        self.eager_steps = 0
+
+    # -- the step itself (eager; also what gets captured) ------------------------------------------------------
+    def _fwd_bwd(self, batch, tz: Tensor):
+        self.bucket.zero()
+        self.model.base.build_plans(batch)                 # CSR/CSC sorts of this batch: part of every step
+        mean, logvar = self.model(batch)
+        loss = gaussian_nll_loss(mean.float(), logvar.float(), tz, self.log_sigma_l2, self.floor)
+        (loss * self.loss_scale).backward()
+        return loss.detach(), mean.detach(), logvar.detach()
+
+    def _finish(self):
+        if self.opt is not None:
+            self.opt.step()
+        self.rng_step.add_(1)
+
+    def _eager(self, batch, tz):
+        prev, ops.RNG_STEP = ops.RNG_STEP, self.rng_step
+        try:
+            out = self._fwd_bwd(batch, tz)
+            if self.world > 1:
+                self.bucket.all_reduce(self.group)
+            self._finish()
+        finally:
+            ops.RNG_STEP = prev
+        self.eager_steps += 1
+        return out
+
+    # -- capture ---------------------------------------------------------------------------------------------------
+    @staticmethod
+    def signature(batch) -> Tuple:
+        return tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(batch.tensors().items())) + (batch.num_graphs,)
+
+    def _capture(self, batch: GraphBatch, tz: Tensor) -> _Captured:
+        cap = _Captured()
+        cap.batch = GraphBatch.__new__(GraphBatch)
+        cap.batch.num_graphs, cap.batch.lg_inc = batch.num_graphs, batch.lg_inc
+        for k in GraphBatch._TENSORS:
+            v = getattr(batch, k)
+            setattr(cap.batch, k, v.clone() if isinstance(v, Tensor) else v)
+        cap.tz = tz.clone()
+        prev, ops.RNG_STEP = ops.RNG_STEP, self.rng_step
+        torch.cuda.synchronize(self.dev)
+        k0 = ops.STATS.kernels
+        try:
+            cap.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cap.graph):
+                cap.loss, cap.mean, cap.logvar = self._fwd_bwd(cap.batch, cap.tz)
+                if self.world == 1:
+                    self._finish()
+            cap.graph_opt = None
+            if self.world > 1:                      # the collective stays outside the graphs
+                cap.graph_opt = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(cap.graph_opt, pool=cap.graph.pool()):
+                    self._finish()
+        finally:
+            ops.RNG_STEP = prev
+        cap.kernels = ops.STATS.kernels - k0       # hand-written kernels inside the graph(s): relaunched by every replay
+        ops.STATS.kernels = k0
+        return cap
+
+    def step(self, batch, target_z: Tensor):
+        if not self.use_graph or not isinstance(batch, GraphBatch):
+            return self._eager(batch, target_z)
+        sig = self.signature(batch)
+        cap = self._captured.get(sig)
+        if cap is None:
+            seen = self._seen.get(sig, 0)
+            self._seen[sig] = seen + 1
+            if seen < self.graph_warmup:
+                return self._eager(batch, target_z)
+            cap = self._captured[sig] = self._capture(batch, target_z)
+        for k, v in cap.batch.tensors().items():
+            v.copy_(getattr(batch, k), non_blocking=True)
+        cap.tz.copy_(target_z, non_blocking=True)
+        cap.graph.replay()
+        if cap.graph_opt is not None:
+            self.bucket.all_reduce(self.group)
+            cap.graph_opt.replay()
+        self.replays += 1
+        ops.STATS.kernels += cap.kernels
+        return cap.loss, cap.mean, cap.logvar

@@ -44,6 +44,16 @@ class FeatGradAccumulator:
         self.visits = 0
 
 
+class LgShared:
+    """Per-forward state of the in-kernel-feature line-graph family (``csrc/lgattn.cu``): the packed angle rows, the first
+    angle-encoder layer, and -- filled during backward -- every layer's (coef, qt, gt), from which the LAST visited
+    block (layer 0) forms ``dW1, db1`` in one fused pass (no ``[L, H]`` gradient ever exists)."""
+
+    def __init__(self, a_csr: Tensor, w1: Tensor, b1: Tensor, n_blocks: int):
+        self.a_csr, self.w1, self.b1, self.n_blocks = a_csr, w1, b1, n_blocks
+        self.coefs, self.qts, self.gts = [], [], []
+
+
 @dataclass
 class BlockCfg:
     heads: int
@@ -59,6 +69,8 @@ class BlockCfg:
     accum: Optional[FeatGradAccumulator] = None   # line-graph blocks sharing h1
     is_last_visitor: bool = False      # this block's backward applies the ReLU mask and returns df to the anchor
     anchor_dtype: Optional[torch.dtype] = None
+    lg: Optional[LgShared] = None      # in-kernel-feature line-graph family (bf16, hidden 256, 4 heads)
+    strided: bool = False              # stored-feature tensor-core family with strided operands + device RNG counter
 
 
 class _AngleH1(torch.autograd.Function):
@@ -86,39 +98,56 @@ def angle_h1(a: Tensor, w1: Tensor, b1: Tensor, cd: torch.dtype) -> Tensor:
 
 
 class _AttnBlock(torch.autograd.Function):
-    """One EdgeUpdateBlock / NodeUpdateBlock (reference ``train.py:303-336``) on the streaming kernels."""
+    """One EdgeUpdateBlock / NodeUpdateBlock (reference ``train.py:303-336``) on the streaming kernels.
+
+    Kernel family per block: ``cfg.lg`` -> in-kernel angle features (``feat`` unused, ``w1 / b1`` differentiable at the
+    block that backward visits last); ``cfg.strided`` -> stored-feature tensor-core kernels; else the generic
+    stored-feature kernels (fp32 / shared-h1 accumulation)."""
 
     @staticmethod
-    def forward(ctx, x32: Tensor, xb: Optional[Tensor], feat: Tensor, anchor: Optional[Tensor], w4: Tensor, b4: Tensor,
-                wc: Tensor, cvec: Optional[Tensor], wbeta: Tensor, gamma: Tensor, beta_ln: Tensor, plan: GraphPlan,
-                cfg: BlockCfg):
+    def forward(ctx, x32: Tensor, xb: Optional[Tensor], feat: Optional[Tensor], anchor: Optional[Tensor], w4: Tensor,
+                b4: Tensor, wc: Tensor, cvec: Optional[Tensor], wbeta: Tensor, gamma: Tensor, beta_ln: Tensor,
+                w1: Optional[Tensor], b1: Optional[Tensor], plan: GraphPlan, cfg: BlockCfg):
         cd, h = cfg.cd, cfg.heads
         n, hid = x32.shape
         c = hid // h
+        rs = ops.RNG_STEP
         x32 = x32.contiguous()
         if xb is None or xb.dtype != cd:
             xb = x32.to(cd)
-        feat = feat.contiguous()
-        if feat.dtype != cd:
-            feat = feat.to(cd)
+        if cfg.lg is None:
+            feat = feat.contiguous()
+            if feat.dtype != cd:
+                feat = feat.to(cd)
+        else:
+            feat = None
         w4c, b4c = w4.to(cd), b4.to(cd)
         proj = torch.addmm(b4c, xb, w4c.t())                                  # [n, 4H]: q | k | v | skip
         wc3 = wc.to(cd).view(h, c, hid)                                       # Wc[t] : [C, H]
         q, k, v, xr = (proj[:, i * hid:(i + 1) * hid] for i in range(4))
         q3 = q.unflatten(1, (h, c)).transpose(0, 1)                           # [h, n, C] view
         qt = torch.bmm(q3, wc3)                                               # [h, n, H]
-        aggv, abar, m, z, s = ops.raw_edgeattn_fwd(q, k, v, qt, feat, plan, h, cfg.p_attn, cfg.seed_attn, cfg.off_attn)
+        if cfg.lg is not None:
+            lg = cfg.lg
+            aggv, abar, m, z, s = ops.raw_lgattn_fwd(q, k, v, qt, lg.a_csr, lg.w1, lg.b1, plan, h, cfg.p_attn,
+                                                     cfg.seed_attn, cfg.off_attn, rs)
+        elif cfg.strided:
+            aggv, abar, m, z, s = ops.raw_attn_fwd_s(q, k, v, qt, feat, plan, h, cfg.p_attn, cfg.seed_attn,
+                                                     cfg.off_attn, rs)
+        else:
+            aggv, abar, m, z, s = ops.raw_edgeattn_fwd(q, k, v, qt, feat, plan, h, cfg.p_attn, cfg.seed_attn,
+                                                       cfg.off_attn)
         agge = torch.bmm(abar, wc3.transpose(1, 2))                           # [h, n, C]
         cv = cvec.detach().contiguous().float() if cvec is not None else None
         wb = wbeta.detach().reshape(-1).contiguous().float()
         gm, bl = gamma.detach().contiguous().float(), beta_ln.detach().contiguous().float()
         y, y_lp, agg, beta, mean, rstd = ops.raw_gate_ln_fwd2(aggv, agge, cv, s if cv is not None else None, h, xr, x32,
                                                               wb, gm, bl, cfg.eps, cfg.p_out, cfg.seed_out, cfg.off_out,
-                                                              cfg.want_lp and cd != torch.float32)
+                                                              cfg.want_lp and cd != torch.float32, rs)
         ctx.save_for_backward(xb, feat, proj, qt, abar, agg, m, z, s, beta, mean, rstd, w4c, wc3, cv, wb, gm, bl)
-        ctx.plan, ctx.cfg = plan, cfg
+        ctx.plan, ctx.cfg, ctx.rs = plan, cfg, rs
         ctx.shapes = (wbeta.shape, wbeta.dtype, gamma.dtype, beta_ln.dtype, w4.dtype, b4.dtype, wc.dtype,
-                      None if cvec is None else cvec.dtype)
+                      None if cvec is None else cvec.dtype, None if w1 is None else (w1.dtype, b1.dtype))
         if y_lp is not None:
             ctx.mark_non_differentiable(y_lp)
         ctx.set_materialize_grads(False)
@@ -127,7 +156,7 @@ class _AttnBlock(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy: Optional[Tensor], _dy_lp):
         xb, feat, proj, qt, abar, agg, m, z, s, beta, mean, rstd, w4c, wc3, cv, wb, gm, bl = ctx.saved_tensors
-        plan, cfg = ctx.plan, ctx.cfg
+        plan, cfg, rs = ctx.plan, ctx.cfg, ctx.rs
         cd, h = cfg.cd, cfg.heads
         n, hid = agg.shape
         c = hid // h
@@ -139,26 +168,42 @@ class _AttnBlock(torch.autograd.Function):
         dq, dk, dv, dxr = (dproj[:, i * hid:(i + 1) * hid] for i in range(4))
 
         dagg, dagg_lp, dparams = ops.raw_gate_ln_bwd2(dy, agg, xr, wb, gm, bl, beta, mean, rstd, dxr,
-                                                      cd != torch.float32, cfg.p_out, cfg.seed_out, cfg.off_out)
+                                                      cd != torch.float32, cfg.p_out, cfg.seed_out, cfg.off_out, rs)
         if dagg_lp is None:
             dagg_lp = dagg
         g3 = dagg_lp.unflatten(1, (h, c)).transpose(0, 1)                     # [h, n, C]
         gt = torch.bmm(g3, wc3)                                               # [h, n, H]
 
-        # feature gradient: shared accumulator (line graph) or a fresh buffer (atom graph / standalone)
         acc = cfg.accum
-        relu_mask = False
-        if acc is not None:
-            first = acc.visits == 0
-            acc.visits += 1
-            if acc.buf is None:
-                acc.buf = torch.empty_like(feat)
-            df_in, df_out = (None if first else acc.buf), acc.buf
-            relu_mask = cfg.is_last_visitor
+        df_out = dw1 = db1 = None
+        if cfg.lg is not None:
+            lg = cfg.lg
+            bbar = torch.empty(h, n, hid, dtype=cd, device=agg.device)
+            coef = ops.raw_lgattn_bwd(dagg, dagg_lp, agg, q, k, v, qt, gt, cv, lg.a_csr, lg.w1, lg.b1, m, z, plan, h,
+                                      dq, dk, dv, bbar, cfg.p_attn, cfg.seed_attn, cfg.off_attn, rs)
+            lg.coefs.append(coef); lg.qts.append(qt); lg.gts.append(gt)
+            if cfg.is_last_visitor:
+                dw1, db1 = ops.raw_lg_angle_grad(lg.a_csr, lg.w1, lg.b1, plan, lg.coefs, lg.qts, lg.gts)
+                lg.coefs, lg.qts, lg.gts = [], [], []
+        elif cfg.strided:
+            bbar = torch.empty(h, n, hid, dtype=cd, device=agg.device)
+            df_out = torch.empty_like(feat)
+            ops.raw_attn_bwd_s(dagg, dagg_lp, agg, q, k, v, qt, gt, cv, feat, m, z, plan, h, dq, dk, dv, bbar, df_out,
+                               cfg.p_attn, cfg.seed_attn, cfg.off_attn, rs)
         else:
-            df_in, df_out = None, torch.empty_like(feat)
-        bbar = ops.raw_edgeattn_bwd(dagg, dagg_lp, agg, q, k, v, qt, gt, cv, feat, m, z, plan, h, dq, dk, dv, df_in, df_out,
-                                    relu_mask, cfg.p_attn, cfg.seed_attn, cfg.off_attn)
+            # feature gradient: shared accumulator (line graph) or a fresh buffer (atom graph / standalone)
+            relu_mask = False
+            if acc is not None:
+                first = acc.visits == 0
+                acc.visits += 1
+                if acc.buf is None:
+                    acc.buf = torch.empty_like(feat)
+                df_in, df_out = (None if first else acc.buf), acc.buf
+                relu_mask = cfg.is_last_visitor
+            else:
+                df_in, df_out = None, torch.empty_like(feat)
+            bbar = ops.raw_edgeattn_bwd(dagg, dagg_lp, agg, q, k, v, qt, gt, cv, feat, m, z, plan, h, dq, dk, dv, df_in,
+                                        df_out, relu_mask, cfg.p_attn, cfg.seed_attn, cfg.off_attn)
 
         q3 = q.unflatten(1, (h, c)).transpose(0, 1)
         dq.unflatten(1, (h, c)).add_(torch.bmm(bbar, wc3.transpose(1, 2)).transpose(0, 1))   # dq += bbar_t Wc[t]^T
@@ -172,18 +217,23 @@ class _AttnBlock(torch.autograd.Function):
         dw4 = dproj.t() @ xb
         db4 = dproj.sum(0, dtype=torch.float32)
 
-        wshape, wdt, gdt, bdt, w4dt, b4dt, wcdt, cdt = ctx.shapes
+        wshape, wdt, gdt, bdt, w4dt, b4dt, wcdt, cdt, w1dts = ctx.shapes
         d_anchor = None
-        if ctx.needs_input_grad[3]:
+        if df_out is not None and ctx.needs_input_grad[3]:
             if acc is None or cfg.is_last_visitor:
                 d_anchor = df_out if cfg.anchor_dtype in (None, df_out.dtype) else df_out.to(cfg.anchor_dtype)
+        if dw1 is not None and w1dts is not None:
+            dw1, db1 = dw1.to(w1dts[0]), db1.to(w1dts[1])
+        else:
+            dw1 = db1 = None
         return (dx32, None, None, d_anchor, dw4.to(w4dt), db4.to(b4dt), dwc.to(wcdt),
                 None if dcvec is None else dcvec.to(cdt), dparams[:3 * hid].reshape(wshape).to(wdt),
-                dparams[3 * hid:4 * hid].to(gdt), dparams[4 * hid:].to(bdt), None, None)
+                dparams[3 * hid:4 * hid].to(gdt), dparams[4 * hid:].to(bdt), dw1, db1, None, None)
 
 
-def attn_block(x32: Tensor, xb: Optional[Tensor], feat: Tensor, anchor: Optional[Tensor], w4: Tensor, b4: Tensor,
-               wc: Tensor, cvec: Optional[Tensor], wbeta: Tensor, gamma: Tensor, beta_ln: Tensor, plan: GraphPlan,
-               cfg: BlockCfg):
-    """Returns ``(y fp32 [N, H], y in compute dtype)``; ``anchor`` is the tensor that receives ``df``."""
-    return _AttnBlock.apply(x32, xb, feat, anchor, w4, b4, wc, cvec, wbeta, gamma, beta_ln, plan, cfg)
+def attn_block(x32: Tensor, xb: Optional[Tensor], feat: Optional[Tensor], anchor: Optional[Tensor], w4: Tensor,
+               b4: Tensor, wc: Tensor, cvec: Optional[Tensor], wbeta: Tensor, gamma: Tensor, beta_ln: Tensor,
+               plan: GraphPlan, cfg: BlockCfg, w1: Optional[Tensor] = None, b1: Optional[Tensor] = None):
+    """Returns ``(y fp32 [N, H], y in compute dtype)``; ``anchor`` is the tensor that receives ``df``; ``w1 / b1`` (lg
+    family, the block backward visits last) receive the fused angle-encoder gradient."""
+    return _AttnBlock.apply(x32, xb, feat, anchor, w4, b4, wc, cvec, wbeta, gamma, beta_ln, w1, b1, plan, cfg)

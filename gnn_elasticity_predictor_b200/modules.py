@@ -30,7 +30,7 @@ import torch.nn.functional as F
 from torch import Tensor, nn
 
 from . import fused, ops
-from .fused import BlockCfg, FeatGradAccumulator
+from .fused import BlockCfg, FeatGradAccumulator, LgShared
 from .ops import GraphPlan
 
 
@@ -149,19 +149,21 @@ def _stack4(conv: TransformerConv) -> Tuple[Tensor, Tensor]:
 
 
 def _stream_block(conv: TransformerConv, norm: nn.LayerNorm, p_out: float, training: bool, x32: Tensor,
-                  xb: Optional[Tensor], feat: Tensor, anchor: Optional[Tensor], wc: Tensor, cvec: Optional[Tensor],
-                  plan: GraphPlan, cd: torch.dtype, accum: Optional[FeatGradAccumulator] = None,
-                  is_last_visitor: bool = False, want_lp: bool = True):
+                  xb: Optional[Tensor], feat: Optional[Tensor], anchor: Optional[Tensor], wc: Tensor,
+                  cvec: Optional[Tensor], plan: GraphPlan, cd: torch.dtype,
+                  accum: Optional[FeatGradAccumulator] = None, is_last_visitor: bool = False, want_lp: bool = True,
+                  lg: Optional[LgShared] = None, w1: Optional[Tensor] = None, b1: Optional[Tensor] = None):
     p_attn = conv.dropout if training else 0.0
     p_o = p_out if training else 0.0
     sa, oa = ops.next_dropout_key() if p_attn > 0.0 else (0, 0)
     so, oo = ops.next_dropout_key() if p_o > 0.0 else (0, 0)
     cfg = BlockCfg(heads=conv.heads, eps=norm.eps, p_attn=p_attn, p_out=p_o, seed_attn=sa, off_attn=oa, seed_out=so,
                    off_out=oo, cd=cd, want_lp=want_lp, accum=accum, is_last_visitor=is_last_visitor,
-                   anchor_dtype=None if anchor is None else anchor.dtype)
+                   anchor_dtype=None if anchor is None else anchor.dtype, lg=lg,
+                   strided=lg is None and accum is None and ops.mma_enabled(conv.in_channels, conv.heads, cd))
     w4, b4 = _stack4(conv)
     return fused.attn_block(x32.float(), xb, feat, anchor, w4, b4, wc, cvec, conv.lin_beta.weight, norm.weight,
-                            norm.bias, plan, cfg)
+                            norm.bias, plan, cfg, w1, b1)
 
 
 class EdgeUpdateBlock(nn.Module):
@@ -330,10 +332,18 @@ class AlignnRegressor(nn.Module):
             run_atoms = n_bonds > 0                       # NodeUpdateBlock's guard (train.py:331-332)
             n_layers = len(self.edge_blocks)
             fold_angle = False
-            h1 = w2 = b2 = None
+            h1 = w2 = b2 = lg = None
             if run_lg:
                 enc = self.angle_encoder
                 if enc is not None and data.lg_edge_attr.numel() > 0 and \
+                        ops.lgattn_enabled(self.hidden, self.heads, enc[0].in_features, cd):
+                    # h1 = relu(W1 a + b1) is rebuilt inside the kernels from the packed 32-byte angle rows
+                    w1p, b1p = enc[0].weight, enc[0].bias
+                    lg = LgShared(ops.pack_angles(data.lg_edge_attr, lg_plan), w1p.detach().contiguous().float(),
+                                  b1p.detach().contiguous().float(), n_layers)
+                    w2, b2 = enc[2].weight.float(), enc[2].bias.float()
+                    fold_angle = True
+                elif enc is not None and data.lg_edge_attr.numel() > 0 and \
                         ops.angle_supported(enc[0].in_features, self.hidden):
                     # h1 = relu(W1 a + b1); the second Linear is folded into every layer's edge projection
                     h1 = fused.angle_h1(data.lg_edge_attr, enc[0].weight, enc[0].bias, cd)
@@ -343,7 +353,7 @@ class AlignnRegressor(nn.Module):
                     h1 = _mlp2(enc, data.lg_edge_attr, cd)          # unusual angle_dim: plain features
                 else:
                     h1 = torch.zeros(n_angles, self.hidden, device=dev, dtype=cd)
-            accum = FeatGradAccumulator(n_layers) if run_lg else None
+            accum = FeatGradAccumulator(n_layers) if run_lg and lg is None else None
 
             edge_b = node_b = None
             for l, (eb, nb) in enumerate(zip(self.edge_blocks, self.node_blocks)):
@@ -353,8 +363,14 @@ class AlignnRegressor(nn.Module):
                         wc, cvec = we @ w2, we @ b2
                     else:
                         wc, cvec = we, None
-                    shared_h1 = fold_angle or not h1.requires_grad
-                    if shared_h1:
+                    shared_h1 = lg is None and (fold_angle or not h1.requires_grad)
+                    if lg is not None:
+                        # layer 0 is visited last by backward: it forms dW1, db1 from every layer's coefficients
+                        first = l == 0
+                        edge32, edge_b = _stream_block(eb.conv, eb.norm, eb.dropout.p, self.training, edge32, edge_b,
+                                                       None, None, wc, cvec, lg_plan, cd, is_last_visitor=first, lg=lg,
+                                                       w1=w1p if first else None, b1=b1p if first else None)
+                    elif shared_h1:
                         # layer 0 is visited last by backward: it masks the accumulated df and hands it to h1
                         edge32, edge_b = _stream_block(eb.conv, eb.norm, eb.dropout.p, self.training, edge32, edge_b,
                                                        h1.detach(), h1 if (l == 0 and fold_angle) else None, wc, cvec,

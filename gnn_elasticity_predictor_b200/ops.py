@@ -48,48 +48,70 @@ def _dtype_code(t: Tensor) -> int:
 # --------------------------------------------------------------------------------------------------
 class LaunchStats:
     """Counts kernels launched through the C ABI and, when ``events`` is on, brackets every call with
-    CUDA events on the launching stream so that per-kernel durations can be read after a sync."""
+    CUDA events on the launching stream so that per-kernel durations can be read after a sync.
+
+    Inside a CUDA-graph capture the calls are bracketed with EXTERNAL timing events instead (``graph_events`` on;
+    names in ``graph_filter`` if set): they become event-record nodes of the graph, are re-recorded by every replay,
+    and ``graph_durations_ms()`` reads the most recent replay's per-kernel durations."""
 
     def __init__(self):
         self.kernels = 0
         self.calls = 0
         self.events = False
         self.records = []   # (name, meta, start_event, end_event)
+        self.graph_events = False
+        self.graph_filter = None
+        self.graph_records = []
 
     def reset(self):
         self.kernels = self.calls = 0
         self.records = []
 
-    def durations_ms(self):
-        """name -> list of (ms, meta); call after torch.cuda.synchronize()."""
+    @staticmethod
+    def _durations(records):
         out = {}
-        for name, meta, a, b in self.records:
+        for name, meta, a, b in records:
             out.setdefault(name, []).append((a.elapsed_time(b), meta))
         return out
+
+    def durations_ms(self):
+        """name -> list of (ms, meta); call after torch.cuda.synchronize()."""
+        return self._durations(self.records)
+
+    def graph_durations_ms(self):
+        """Same for the event nodes captured into CUDA graphs (last replay of each graph)."""
+        return self._durations(self.graph_records)
 
 
 STATS = LaunchStats()
 
 
 class _Launch:
-    __slots__ = ("name", "n", "meta", "start")
+    __slots__ = ("name", "n", "meta", "start", "ext")
 
     def __init__(self, name: str, n_kernels: int, meta=None):
-        self.name, self.n, self.meta, self.start = name, n_kernels, meta, None
+        self.name, self.n, self.meta, self.start, self.ext = name, n_kernels, meta, None, False
 
     def __enter__(self):
         STATS.kernels += self.n
         STATS.calls += 1
-        if STATS.events:
-            self.start = torch.cuda.Event(enable_timing=True)
-            self.start.record()
+        if STATS.events or STATS.graph_events:
+            capturing = torch.cuda.is_current_stream_capturing()
+            if capturing:
+                if STATS.graph_events and (STATS.graph_filter is None or self.name in STATS.graph_filter):
+                    self.ext = True
+                    self.start = torch.cuda.Event(enable_timing=True, external=True)
+                    self.start.record()
+            elif STATS.events:
+                self.start = torch.cuda.Event(enable_timing=True)
+                self.start.record()
         return self
 
     def __exit__(self, *exc):
         if self.start is not None:
-            end = torch.cuda.Event(enable_timing=True)
+            end = torch.cuda.Event(enable_timing=True, external=self.ext)
             end.record()
-            STATS.records.append((self.name, self.meta, self.start, end))
+            (STATS.graph_records if self.ext else STATS.records).append((self.name, self.meta, self.start, end))
         return False
 
 
@@ -338,6 +360,16 @@ def edgeattn_supported(hidden: int, heads: int) -> bool:
 
 def angle_supported(in_dim: int, hidden: int) -> bool:
     return bool(_lib.load().alignn_angle_supported(int(in_dim), int(hidden)))
+
+
+USE_LG = True    # in-kernel-feature line-graph kernels (csrc/lgattn.cu) where supported (H=256, 4 heads, bf16)
+RNG_STEP: Optional[Tensor] = None   # device uint64 counter added to every dropout offset (set by engine.GraphedTrainStep
+                                    # so that CUDA-graph replays draw fresh masks); None in eager mode
+
+
+def lgattn_enabled(hidden: int, heads: int, in_dim: int, dtype: torch.dtype) -> bool:
+    return USE_LG and USE_MMA and dtype in _DT and bool(
+        _lib.load().alignn_lgattn_supported(int(hidden), int(heads), int(in_dim), _DT[dtype]))
 
 
 USE_MMA = True   # tensor-core (mma.sync) variants of the streaming kernels where supported (H=256, 4 heads, bf16)

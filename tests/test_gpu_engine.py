@@ -1,0 +1,110 @@
+"""GPU tests of the one-call training step (``engine.TrainStep``): the fused clip + AdamW kernel against
+``torch.nn.utils.clip_grad_norm_`` + ``torch.optim.AdamW`` (what the reference runs after the hot path,
+scripts/train.py:690-699, optimizer built at :1516-1540), CUDA-graph replay against the eager step, fresh dropout masks
+across replays, and the in-kernel-feature line-graph family against the stored-feature family on the whole model."""
+import copy
+
+import pytest
+import torch
+
+from conftest import rel_err
+import gnn_elasticity_predictor_b200 as pkg
+from gnn_elasticity_predictor_b200 import engine, ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+CTOR = dict(node_dim=206, edge_dim=36, angle_dim=11, global_dim=289, target_dim=2, hidden=256, layers=2, heads=4)
+
+
+def _model(dropout=0.0, seed=0, **over):
+    torch.manual_seed(seed)
+    m = pkg.HeteroAlignnRegressor(pkg.AlignnRegressor(dropout=dropout, **{**CTOR, **over}), 2).to(DEV)
+    m.train()
+    return m
+
+
+def test_fused_clip_adamw_matches_torch_two_lr_groups():
+    """fp32 regime, dropout 0: three steps of TrainStep == clip_grad_norm_(5.0) + torch AdamW with the reference's two
+    parameter groups (base + mean heads | log-variance heads)."""
+    a = _model()
+    b = copy.deepcopy(a)
+    batch = pkg.synthetic_batch(6, 8, 4, seed=3).to(DEV)
+    tz = pkg.zscore_targets(batch.y, batch.num_graphs)
+    ts = engine.TrainStep(a, lr=2e-3, lr_sigma=5e-4, weight_decay=1e-2, max_norm=0.05, graph=False)
+    base = list(b.base.parameters()) + list(b.mean_heads.parameters())
+    opt = torch.optim.AdamW([{"params": base, "lr": 2e-3}, {"params": list(b.logvar_heads.parameters()), "lr": 5e-4}],
+                            weight_decay=1e-2)
+    for _ in range(3):
+        loss_a, _, _ = ts.step(batch, tz)
+        opt.zero_grad(set_to_none=True)
+        mean, logvar = b(batch)
+        loss_b = pkg.gaussian_nll_loss(mean, logvar, tz)
+        loss_b.backward()
+        norm_b = torch.nn.utils.clip_grad_norm_(b.parameters(), max_norm=0.05)
+        opt.step()
+        assert rel_err(loss_a, loss_b) < 1e-5
+        assert rel_err(ts.opt.norm, norm_b) < 1e-4 and float(norm_b) > 0.05      # the clip is active
+    pa, pb = dict(a.named_parameters()), dict(b.named_parameters())
+    for k in pb:
+        assert rel_err(pa[k], pb[k]) < 2e-5, k
+    assert float(ts.opt.step_count) == 3.0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_graph_replay_matches_eager_step(dtype):
+    """dropout 0: the replayed graph and the eager step are the same kernels on the same data -> identical results,
+    including on a second batch copied into the graph's static buffers."""
+    a = _model(seed=1)
+    b = copy.deepcopy(a)
+    a.base.compute_dtype = b.base.compute_dtype = dtype
+    batches = [pkg.synthetic_batch(5, 8, 4, seed=s).to(DEV) for s in (0, 1)]
+    tzs = [pkg.zscore_targets(x.y, x.num_graphs) for x in batches]
+    tg = engine.TrainStep(a, graph=True, graph_warmup=1)
+    te = engine.TrainStep(b, graph=False)
+    for i in range(5):
+        la, ma, va = tg.step(batches[i % 2], tzs[i % 2])
+        lb, mb, vb = te.step(batches[i % 2], tzs[i % 2])
+        assert torch.equal(la, lb) and torch.equal(ma, mb) and torch.equal(va, vb), i
+    assert tg.replays == 4 and tg.eager_steps == 1
+    for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert torch.equal(pa, pb), k
+    # a new signature falls back to eager steps until captured
+    other = pkg.synthetic_batch(3, 8, 4, seed=5).to(DEV)
+    tg.step(other, pkg.zscore_targets(other.y, 3))
+    assert tg.eager_steps == 2
+
+
+def test_graph_replays_draw_fresh_dropout_masks():
+    a = _model(dropout=0.3, seed=2)
+    a.base.compute_dtype = torch.bfloat16
+    batch = pkg.synthetic_batch(8, 8, 4, seed=0).to(DEV)
+    tz = pkg.zscore_targets(batch.y, batch.num_graphs)
+    ts = engine.TrainStep(a, graph=True, graph_warmup=1, lr=0.0, weight_decay=0.0)     # frozen weights
+    losses = [float(ts.step(batch, tz)[0]) for _ in range(6)]
+    assert ts.replays == 5
+    assert len({round(x, 6) for x in losses[1:]}) >= 4, losses      # same weights, same batch: only the masks differ
+    assert all(torch.isfinite(torch.tensor(losses)))
+
+
+def test_lg_family_matches_stored_feature_family_on_the_model(monkeypatch):
+    """bf16, default arch: in-kernel angle features (csrc/lgattn.cu) vs stored h1 (csrc/edgeattn_mma.cu)."""
+    m = _model(seed=4, layers=4)
+    m.base.compute_dtype = torch.bfloat16
+    batch = pkg.synthetic_batch(16, 16, 12, seed=2).to(DEV)
+    tz = pkg.zscore_targets(batch.y, batch.num_graphs)
+    out = {}
+    for use_lg in (True, False):
+        monkeypatch.setattr(ops, "USE_LG", use_lg)
+        m.zero_grad(set_to_none=True)
+        k0 = ops.STATS.kernels
+        mean, logvar = m(batch)
+        loss = pkg.gaussian_nll_loss(mean.float(), logvar.float(), tz)
+        loss.backward()
+        out[use_lg] = (mean, logvar, {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None},
+                       ops.STATS.kernels - k0)
+    a, b = out[True], out[False]
+    assert rel_err(a[0], b[0]) < 2e-2 and rel_err(a[1], b[1]) < 2e-2
+    gmax = max(float(g.abs().max()) for g in b[2].values())
+    assert set(a[2]) == set(b[2])
+    for k, g in b[2].items():
+        assert float((a[2][k] - g).abs().max()) < 2e-2 * max(float(g.abs().max()), 1e-2 * gmax), k
