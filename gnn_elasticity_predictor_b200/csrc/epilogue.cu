@@ -39,6 +39,7 @@ struct GateExtra {
     const float *stat_s;   // [rows, heads] f32: S = sum_j a~
     float *agg_out;        // [rows, hidden] f32: full aggregate, saved for backward (may be null)
     void *dagg_lp;         // backward: storage-dtype copy of dagg (may be null)
+    bool dcvec;            // backward: also reduce dc = sum_rows dagg * S (needs stat_s, heads) -> 6 parameter vectors
     int heads;
     int64_t ldxr, lddxr;   // row strides (elements) of xr and dxr
     const uint64_t *rng_step;   // optional device counter added to the dropout offset (CUDA-graph replays)
@@ -137,19 +138,21 @@ gate_ln_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ agg, 
                    int64_t n_rows, int hidden, float p_drop, float inv_keep, uint64_t seed, uint64_t offset,
                    const GateExtra X) {
     constexpr int RPW = 32 / LANES;
-    __shared__ float red[EPI_WARPS][5][LANES * 8];
+    __shared__ float red[EPI_WARPS][LANES * 8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane % LANES;
     const int ch = sub * 8;
+    const int nvec = X.dcvec ? 6 : 5;                    // 6th vector: dc[ch] = sum_rows dagg[row, ch] * S[row, head(ch)]
+    const int head = X.dcvec ? ch / (hidden / X.heads) : 0;
     const int64_t slots = (int64_t)gridDim.x * EPI_WARPS * RPW;
     const int64_t slot = ((int64_t)blockIdx.x * EPI_WARPS + warp) * RPW + lane / LANES;
     const int64_t iters = (n_rows + slots - 1) / slots;
 
     const F8 w1 = ld8(wbeta + ch), w2 = ld8(wbeta + hidden + ch), w3 = ld8(wbeta + 2 * hidden + ch);
     const F8 gm = ld8(gamma + ch), bs = ld8(bias + ch);
-    F8 a1, a2, a3, ag, ab;
+    F8 a1, a2, a3, ag, ab, ac;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) a1.v[c] = a2.v[c] = a3.v[c] = ag.v[c] = ab.v[c] = 0.f;
+    for (int c = 0; c < 8; ++c) a1.v[c] = a2.v[c] = a3.v[c] = ag.v[c] = ab.v[c] = ac.v[c] = 0.f;
     const float inv_h = 1.0f / (float)hidden;
 
     for (int64_t it = 0; it < iters; ++it) {
@@ -199,6 +202,7 @@ gate_ln_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ agg, 
         const float dz = dbeta * beta * (1.0f - beta);
         if (ok) {
             F8 da, ds;
+            const float srow = X.dcvec ? __ldg(X.stat_s + row * X.heads + head) : 0.f;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 da.v[c] = (1.0f - beta) * dof.v[c] + dz * (w1.v[c] + w3.v[c]);
@@ -206,6 +210,7 @@ gate_ln_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ agg, 
                 a1.v[c] = fmaf(dz, af.v[c], a1.v[c]);
                 a2.v[c] = fmaf(dz, sf.v[c], a2.v[c]);
                 a3.v[c] = fmaf(dz, af.v[c] - sf.v[c], a3.v[c]);
+                ac.v[c] = fmaf(da.v[c], srow, ac.v[c]);
             }
             st8(dagg + row * hidden + ch, da);
             if (X.dagg_lp) st8(reinterpret_cast<T *>(X.dagg_lp) + row * hidden + ch, da);
@@ -223,26 +228,26 @@ gate_ln_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ agg, 
                 a3.v[c] += __shfl_xor_sync(FULL, a3.v[c], off);
                 ag.v[c] += __shfl_xor_sync(FULL, ag.v[c], off);
                 ab.v[c] += __shfl_xor_sync(FULL, ab.v[c], off);
+                ac.v[c] += __shfl_xor_sync(FULL, ac.v[c], off);
             }
         }
     }
-    if (lane < LANES) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            red[warp][0][ch + c] = a1.v[c];
-            red[warp][1][ch + c] = a2.v[c];
-            red[warp][2][ch + c] = a3.v[c];
-            red[warp][3][ch + c] = ag.v[c];
-            red[warp][4][ch + c] = ab.v[c];
+    for (int which = 0; which < 6; ++which) {          // one vector at a time through an 8 KB staging buffer
+        if (which >= nvec) break;                      // block-uniform
+        const F8 &src = which == 0 ? a1 : which == 1 ? a2 : which == 2 ? a3 : which == 3 ? ag : which == 4 ? ab : ac;
+        if (lane < LANES) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) red[warp][ch + c] = src.v[c];
         }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 5 * hidden; i += EPI_THREADS) {
-        const int which = i / hidden, c = i % hidden;
-        float s = 0.f;
+        __syncthreads();
+        for (int c = threadIdx.x; c < hidden; c += EPI_THREADS) {
+            float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < EPI_WARPS; ++w) s += red[w][which][c];
-        partials[((int64_t)blockIdx.x * 5 + which) * hidden + c] = s;
+            for (int w = 0; w < EPI_WARPS; ++w) s += red[w][c];
+            partials[((int64_t)blockIdx.x * nvec + which) * hidden + c] = s;
+        }
+        __syncthreads();
     }
 }
 
@@ -465,7 +470,7 @@ static int dispatch_epi_bwd(const float *dy, const float *agg, const void *xr, c
     }
 #undef EPI_BWD
     ALIGNN_LAUNCH_CHECK();
-    const int width = 5 * hidden;
+    const int width = (X.dcvec ? 6 : 5) * hidden;
     reduce_partials_kernel<<<(width + 255) / 256, 256, 0, st>>>(partials, dparams, EPI_PARTIAL_BLOCKS, width);
     ALIGNN_LAUNCH_CHECK();
     return ALIGNN_OK;
@@ -479,7 +484,7 @@ extern "C" int64_t alignn_gate_ln_bwd_partial_rows(void) { return EPI_PARTIAL_BL
 
 static GateExtra plain_extra(int hidden) {
     GateExtra X;
-    X.agge = nullptr; X.cvec = nullptr; X.stat_s = nullptr; X.agg_out = nullptr; X.dagg_lp = nullptr;
+    X.agge = nullptr; X.cvec = nullptr; X.stat_s = nullptr; X.agg_out = nullptr; X.dagg_lp = nullptr; X.dcvec = false;
     X.heads = 1; X.ldxr = hidden; X.lddxr = hidden; X.rng_step = nullptr;
     return X;
 }
@@ -565,6 +570,22 @@ extern "C" int alignn_gate_ln_bwd(const float *dy, const float *agg, const void 
                             hidden, dtype, p_drop, seed, offset, plain_extra(hidden), false, stream);
 }
 
+extern "C" int alignn_gate_ln_bwd3(const float *dy, const float *agg, const void *xr, int64_t ldxr,
+                                   const float *wbeta, const float *gamma, const float *bias,
+                                   const float *beta, const float *mean, const float *rstd,
+                                   const float *stat_s, int heads,
+                                   float *dagg, void *dagg_lp, void *dxr, int64_t lddxr, float *partials, float *dparams,
+                                   int64_t n_rows, int hidden, int dtype,
+                                   float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step, void *stream) {
+    GateExtra X = plain_extra(hidden);
+    X.dagg_lp = dagg_lp; X.ldxr = ldxr; X.lddxr = lddxr; X.rng_step = rng_step;
+    X.stat_s = stat_s; X.heads = heads; X.dcvec = true;
+    if (!stat_s || heads <= 0 || hidden % heads || (hidden / heads) % 8) return ALIGNN_ERR_BAD_ARG;
+    if (hidden % 8 || hidden > 256 || (256 % hidden)) return ALIGNN_ERR_BAD_SHAPE;   // fast mapping only
+    return gate_ln_bwd_impl(dy, agg, xr, wbeta, gamma, bias, beta, mean, rstd, dagg, dxr, partials, dparams, n_rows,
+                            hidden, dtype, p_drop, seed, offset, X, true, stream);
+}
+
 extern "C" int alignn_gate_ln_bwd2(const float *dy, const float *agg, const void *xr, int64_t ldxr,
                                    const float *wbeta, const float *gamma, const float *bias,
                                    const float *beta, const float *mean, const float *rstd,
@@ -576,4 +597,72 @@ extern "C" int alignn_gate_ln_bwd2(const float *dy, const float *agg, const void
     if (rng_step && (hidden % 8 || hidden > 256 || (256 % hidden))) return ALIGNN_ERR_BAD_SHAPE;
     return gate_ln_bwd_impl(dy, agg, xr, wbeta, gamma, bias, beta, mean, rstd, dagg, dxr, partials, dparams, n_rows,
                             hidden, dtype, p_drop, seed, offset, X, true, stream);
+}
+
+// ---- column sums of a [rows, width] matrix (bias gradients of the stacked node projections) -----------------------
+// Replaces `dproj.sum(0)` of torch autograd's AddmmBackward for lin_query/key/value/skip (reference train.py:691 through
+// PyG TransformerConv's four Linears).  Deterministic: per-thread register sums over a fixed row stride, fixed-order fold
+// of the row groups of a CTA, then reduce_partials_kernel over the CTAs.
+namespace alignn {
+
+constexpr int CS_THREADS = 256;
+constexpr int CS_BLOCKS = 296;
+
+template <typename T>
+__global__ void __launch_bounds__(CS_THREADS)
+colsum_kernel(const T *__restrict__ x, int64_t ld, int64_t n_rows, int width, float *__restrict__ partials) {
+    __shared__ float red[CS_THREADS * 8];
+    const int lanes = width >> 3;                   // threads per row
+    const int groups = CS_THREADS / lanes;          // rows per CTA iteration
+    const int sub = threadIdx.x % lanes, grp = threadIdx.x / lanes;
+    const int64_t stride = (int64_t)gridDim.x * groups;
+    F8 acc;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc.v[c] = 0.f;
+    int64_t row = (int64_t)blockIdx.x * groups + grp;
+    for (; row + 3 * stride < n_rows; row += 4 * stride) {      // 4 independent 16-byte loads in flight per thread
+        const F8 a = ld8(x + row * ld + sub * 8), b = ld8(x + (row + stride) * ld + sub * 8);
+        const F8 c2 = ld8(x + (row + 2 * stride) * ld + sub * 8), d = ld8(x + (row + 3 * stride) * ld + sub * 8);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc.v[c] += (a.v[c] + b.v[c]) + (c2.v[c] + d.v[c]);
+    }
+    for (; row < n_rows; row += stride) {
+        const F8 a = ld8(x + row * ld + sub * 8);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc.v[c] += a.v[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) red[threadIdx.x * 8 + c] = acc.v[c];
+    __syncthreads();
+    for (int i = threadIdx.x; i < width; i += CS_THREADS) {
+        const int s8 = i >> 3, c = i & 7;
+        float s = 0.f;
+        for (int g2 = 0; g2 < groups; ++g2) s += red[(g2 * lanes + s8) * 8 + c];
+        partials[(int64_t)blockIdx.x * width + i] = s;
+    }
+}
+
+}  // namespace alignn
+
+extern "C" int64_t alignn_colsum_partial_floats(int width) { return (int64_t)CS_BLOCKS * width; }
+
+extern "C" int alignn_colsum_supported(int width) {
+    return width >= 8 && width <= 2048 && width % 8 == 0 && CS_THREADS % (width / 8) == 0;
+}
+
+extern "C" int alignn_colsum(const void *x, int64_t ld, int64_t n_rows, int width, int dtype, float *partials,
+                             float *out, void *stream) {
+    if (!alignn_colsum_supported(width) || n_rows < 0 || ld < width || (ld % 8)) return ALIGNN_ERR_BAD_SHAPE;
+    if (!out || !partials || (n_rows > 0 && !x) || !aligned16(x)) return ALIGNN_ERR_BAD_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == ALIGNN_F32)
+        colsum_kernel<float><<<CS_BLOCKS, CS_THREADS, 0, st>>>((const float *)x, ld, n_rows, width, partials);
+    else if (dtype == ALIGNN_BF16)
+        colsum_kernel<__nv_bfloat16><<<CS_BLOCKS, CS_THREADS, 0, st>>>((const __nv_bfloat16 *)x, ld, n_rows, width, partials);
+    else
+        return ALIGNN_ERR_BAD_DTYPE;
+    ALIGNN_LAUNCH_CHECK();
+    reduce_partials_kernel<<<(width + 255) / 256, 256, 0, st>>>(partials, out, CS_BLOCKS, width);
+    ALIGNN_LAUNCH_CHECK();
+    return ALIGNN_OK;
 }

@@ -72,6 +72,31 @@ class FlatGradBucket:
         for p, off in zip(self.params, self.offsets):
             p.grad = self.flat[off:off + p.numel()].view_as(p)
 
+    def detach_grads(self) -> None:
+        """``param.grad = None`` for every parameter: autograd then hands over its gradient tensors instead of
+        launching one accumulate kernel per parameter; :meth:`gather` moves them into the bucket in one fused copy."""
+        for p in self.params:
+            p.grad = None
+
+    def gather(self) -> None:
+        """Copy the gradients autograd produced into the flat bucket (one multi-tensor copy), zero the slices of
+        parameters that received none, and re-point ``param.grad`` at the bucket."""
+        views = [self.flat[off:off + p.numel()].view_as(p) for p, off in zip(self.params, self.offsets)]
+        src, dst = [], []
+        written = getattr(self, "_written", None)
+        now = set()
+        for i, (p, v) in enumerate(zip(self.params, views)):
+            g = p.grad
+            if g is not None and g.data_ptr() != v.data_ptr():
+                src.append(g if g.dtype == v.dtype else g.to(v.dtype)); dst.append(v); now.add(i)
+            elif g is None and (written is None or i in written):
+                v.zero_()
+        if src:
+            torch._foreach_copy_(dst, src)
+        self._written = now
+        for p, v in zip(self.params, views):
+            p.grad = v
+
     def zero(self) -> None:
         self.flat.zero_()
         self.attach()   # in case something replaced .grad (e.g. zero_grad(set_to_none=True))

@@ -124,11 +124,12 @@ class TrainStep:
 
     # -- the step itself (eager; also what gets captured) ------------------------------------------------------
     def _fwd_bwd(self, batch, tz: Tensor):
-        self.bucket.zero()
+        self.bucket.detach_grads()
         self.model.base.build_plans(batch)                 # CSR/CSC sorts of this batch: part of every step
         mean, logvar = self.model(batch)
         loss = gaussian_nll_loss(mean.float(), logvar.float(), tz, self.log_sigma_l2, self.floor)
         (loss * self.loss_scale).backward()
+        self.bucket.gather()                               # one multi-tensor copy into the flat gradient bucket
         return loss.detach(), mean.detach(), logvar.detach()
 
     def _finish(self):

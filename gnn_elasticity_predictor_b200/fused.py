@@ -231,6 +231,128 @@ class _AttnBlock(torch.autograd.Function):
                 dparams[3 * hid:4 * hid].to(gdt), dparams[4 * hid:].to(bdt), dw1, db1, None, None)
 
 
+class _AttnBlock8(torch.autograd.Function):
+    """bf16 tensor-core families (``cfg.lg`` / ``cfg.strided``) with the query-side fold moved INTO the node projection:
+
+        proj8 = x [Wq; Wk; Wv; Ws; Wc[0]^T Wq_0; ..; Wc[3]^T Wq_3]^T + b8        ->  q | k | v | x_r | qt_0 .. qt_3
+
+    one ``[n, H] x [H, 8H]`` GEMM instead of the 4H projection + a batched ``q_t Wc[t]`` product, and in backward the
+    kernels write ``dq | dk | dv | dx_r | bbar_0..3`` straight into one ``[n, 8H]`` buffer, so that ``dx = dy + dproj8 W8``
+    (fp32 accumulate-into GEMM), ``dW8 = dproj8^T x`` and ``db8 = colsum(dproj8)`` replace five GEMMs, a strided add and
+    two reductions.  ``W8 / b8`` are built from the parameters with autograd (tiny [H, H] products), which carries the chain
+    rule back to ``lin_query`` and the folded edge projection."""
+
+    @staticmethod
+    def forward(ctx, x32: Tensor, xb: Optional[Tensor], feat: Optional[Tensor], anchor: Optional[Tensor], w8: Tensor,
+                b8: Tensor, wc: Tensor, cvec: Optional[Tensor], wbeta: Tensor, gamma: Tensor, beta_ln: Tensor,
+                w1: Optional[Tensor], b1: Optional[Tensor], plan: GraphPlan, cfg: BlockCfg):
+        cd, h = cfg.cd, cfg.heads
+        n, hid = x32.shape
+        c = hid // h
+        rs = ops.RNG_STEP
+        x32 = x32.contiguous()
+        if xb is None or xb.dtype != cd:
+            xb = x32.to(cd)
+        if cfg.lg is None:
+            feat = feat.contiguous()
+            if feat.dtype != cd:
+                feat = feat.to(cd)
+        else:
+            feat = None
+        w8c, b8c = w8.to(cd), b8.to(cd)
+        proj = torch.addmm(b8c, xb, w8c.t())                                  # [n, 8H]
+        wc3 = wc.to(cd).view(h, c, hid)                                       # Wc[t] : [C, H]
+        q, k, v, xr = (proj[:, i * hid:(i + 1) * hid] for i in range(4))
+        qt = proj[:, 4 * hid:].unflatten(1, (h, hid)).transpose(0, 1)         # [h, n, H] view (row stride 8H)
+        if cfg.lg is not None:
+            lg = cfg.lg
+            aggv, abar, m, z, s = ops.raw_lgattn_fwd(q, k, v, qt, lg.a_csr, lg.w1, lg.b1, plan, h, cfg.p_attn,
+                                                     cfg.seed_attn, cfg.off_attn, rs)
+        else:
+            aggv, abar, m, z, s = ops.raw_attn_fwd_s(q, k, v, qt, feat, plan, h, cfg.p_attn, cfg.seed_attn,
+                                                     cfg.off_attn, rs)
+        agge = torch.bmm(abar, wc3.transpose(1, 2))                           # [h, n, C]
+        cv = cvec.detach().contiguous().float() if cvec is not None else None
+        wb = wbeta.detach().reshape(-1).contiguous().float()
+        gm, bl = gamma.detach().contiguous().float(), beta_ln.detach().contiguous().float()
+        y, y_lp, agg, beta, mean, rstd = ops.raw_gate_ln_fwd2(aggv, agge, cv, s if cv is not None else None, h, xr, x32,
+                                                              wb, gm, bl, cfg.eps, cfg.p_out, cfg.seed_out, cfg.off_out,
+                                                              cfg.want_lp, rs)
+        ctx.save_for_backward(xb, feat, proj, abar, agg, m, z, s, beta, mean, rstd, w8c, wc3, cv, wb, gm, bl)
+        ctx.plan, ctx.cfg, ctx.rs = plan, cfg, rs
+        ctx.shapes = (wbeta.shape, wbeta.dtype, gamma.dtype, beta_ln.dtype, w8.dtype, b8.dtype, wc.dtype,
+                      None if cvec is None else cvec.dtype, None if w1 is None else (w1.dtype, b1.dtype))
+        if y_lp is not None:
+            ctx.mark_non_differentiable(y_lp)
+        ctx.set_materialize_grads(False)
+        return y, y_lp
+
+    @staticmethod
+    def backward(ctx, dy: Optional[Tensor], _dy_lp):
+        xb, feat, proj, abar, agg, m, z, s, beta, mean, rstd, w8c, wc3, cv, wb, gm, bl = ctx.saved_tensors
+        plan, cfg, rs = ctx.plan, ctx.cfg, ctx.rs
+        cd, h = cfg.cd, cfg.heads
+        n, hid = agg.shape
+        c = hid // h
+        if dy is None:
+            dy = torch.zeros_like(agg)
+        dy = dy.contiguous().float()
+        q, k, v, xr = (proj[:, i * hid:(i + 1) * hid] for i in range(4))
+        qt = proj[:, 4 * hid:].unflatten(1, (h, hid)).transpose(0, 1)
+        dproj = torch.empty_like(proj)
+        dq, dk, dv, dxr = (dproj[:, i * hid:(i + 1) * hid] for i in range(4))
+        bbar = dproj[:, 4 * hid:].unflatten(1, (h, hid)).transpose(0, 1)      # [h, n, H] view of the same buffer
+
+        if cv is not None:
+            dagg, dagg_lp, dparams = ops.raw_gate_ln_bwd3(dy, agg, xr, wb, gm, bl, beta, mean, rstd, s, h, dxr,
+                                                          cfg.p_out, cfg.seed_out, cfg.off_out, rs)
+            dcvec = dparams[5 * hid:]
+        else:
+            dagg, dagg_lp, dparams = ops.raw_gate_ln_bwd2(dy, agg, xr, wb, gm, bl, beta, mean, rstd, dxr, True,
+                                                          cfg.p_out, cfg.seed_out, cfg.off_out, rs)
+            dcvec = None
+        g3 = dagg_lp.unflatten(1, (h, c)).transpose(0, 1)                     # [h, n, C]
+        gt = torch.bmm(g3, wc3)                                               # [h, n, H]
+
+        df_out = dw1 = db1 = None
+        if cfg.lg is not None:
+            lg = cfg.lg
+            coef = ops.raw_lgattn_bwd(dagg, dagg_lp, agg, q, k, v, qt, gt, cv, lg.a_csr, lg.w1, lg.b1, m, z, plan, h,
+                                      dq, dk, dv, bbar, cfg.p_attn, cfg.seed_attn, cfg.off_attn, rs)
+            lg.coefs.append(coef); lg.qts.append(qt); lg.gts.append(gt)
+            if cfg.is_last_visitor:
+                dw1, db1 = ops.raw_lg_angle_grad(lg.a_csr, lg.w1, lg.b1, plan, lg.coefs, lg.qts, lg.gts)
+                lg.coefs, lg.qts, lg.gts = [], [], []
+        else:
+            df_out = torch.empty_like(feat)
+            ops.raw_attn_bwd_s(dagg, dagg_lp, agg, q, k, v, qt, gt, cv, feat, m, z, plan, h, dq, dk, dv, bbar, df_out,
+                               cfg.p_attn, cfg.seed_attn, cfg.off_attn, rs)
+
+        dwc = torch.bmm(g3.transpose(1, 2), abar).reshape(hid, hid)           # dWc[t] = dagg_t^T abar_t  (+ via W8)
+        dx32 = torch.addmm(dy, dproj, w8c, out_dtype=torch.float32)           # dy + dproj8 W8, fp32 accumulate
+        dw8 = torch.mm(dproj.t(), xb, out_dtype=torch.float32)                # [8H, H]
+        db8 = ops.colsum(dproj)
+
+        wshape, wdt, gdt, bdt, w8dt, b8dt, wcdt, cdt, w1dts = ctx.shapes
+        d_anchor = None
+        if df_out is not None and ctx.needs_input_grad[3]:
+            d_anchor = df_out if cfg.anchor_dtype in (None, df_out.dtype) else df_out.to(cfg.anchor_dtype)
+        if dw1 is not None and w1dts is not None:
+            dw1, db1 = dw1.to(w1dts[0]), db1.to(w1dts[1])
+        else:
+            dw1 = db1 = None
+        return (dx32, None, None, d_anchor, dw8.to(w8dt), db8.to(b8dt), dwc.to(wcdt),
+                None if dcvec is None else dcvec.to(cdt), dparams[:3 * hid].reshape(wshape).to(wdt),
+                dparams[3 * hid:4 * hid].to(gdt), dparams[4 * hid:5 * hid].to(bdt), dw1, db1, None, None)
+
+
+def attn_block8(x32: Tensor, xb: Optional[Tensor], feat: Optional[Tensor], anchor: Optional[Tensor], w8: Tensor,
+                b8: Tensor, wc: Tensor, cvec: Optional[Tensor], wbeta: Tensor, gamma: Tensor, beta_ln: Tensor,
+                plan: GraphPlan, cfg: BlockCfg, w1: Optional[Tensor] = None, b1: Optional[Tensor] = None):
+    """bf16 tensor-core families with the 8H stacked projection (see :class:`_AttnBlock8`)."""
+    return _AttnBlock8.apply(x32, xb, feat, anchor, w8, b8, wc, cvec, wbeta, gamma, beta_ln, w1, b1, plan, cfg)
+
+
 def attn_block(x32: Tensor, xb: Optional[Tensor], feat: Optional[Tensor], anchor: Optional[Tensor], w4: Tensor,
                b4: Tensor, wc: Tensor, cvec: Optional[Tensor], wbeta: Tensor, gamma: Tensor, beta_ln: Tensor,
                plan: GraphPlan, cfg: BlockCfg, w1: Optional[Tensor] = None, b1: Optional[Tensor] = None):

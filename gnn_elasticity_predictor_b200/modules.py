@@ -148,6 +148,18 @@ def _stack4(conv: TransformerConv) -> Tuple[Tensor, Tensor]:
     return w4, b4
 
 
+def _stack8(conv: TransformerConv, wc: Tensor) -> Tuple[Tensor, Tensor]:
+    """``[Wq; Wk; Wv; Ws; Wc[t]^T Wq_t (t < heads)]`` and its bias: ``qt_t = q_t Wc[t]`` becomes one more slice of the node
+    projection (``wc``: folded edge projection ``[H, H]``, fp32, autograd-tracked)."""
+    h, hid = conv.heads, conv.in_channels
+    c = hid // h
+    w4, b4 = _stack4(conv)
+    wc3 = wc.float().view(h, c, hid)
+    wqt = torch.bmm(wc3.transpose(1, 2), conv.lin_query.weight.float().view(h, c, hid)).reshape(h * hid, hid)
+    bqt = torch.bmm(conv.lin_query.bias.float().view(h, 1, c), wc3).reshape(h * hid)
+    return torch.cat([w4.float(), wqt], dim=0), torch.cat([b4.float(), bqt], dim=0)
+
+
 def _stream_block(conv: TransformerConv, norm: nn.LayerNorm, p_out: float, training: bool, x32: Tensor,
                   xb: Optional[Tensor], feat: Optional[Tensor], anchor: Optional[Tensor], wc: Tensor,
                   cvec: Optional[Tensor], plan: GraphPlan, cd: torch.dtype,
@@ -161,6 +173,10 @@ def _stream_block(conv: TransformerConv, norm: nn.LayerNorm, p_out: float, train
                    off_out=oo, cd=cd, want_lp=want_lp, accum=accum, is_last_visitor=is_last_visitor,
                    anchor_dtype=None if anchor is None else anchor.dtype, lg=lg,
                    strided=lg is None and accum is None and ops.mma_enabled(conv.in_channels, conv.heads, cd))
+    if cfg.lg is not None or cfg.strided:
+        w8, b8 = _stack8(conv, wc)
+        return fused.attn_block8(x32.float(), xb, feat, anchor, w8, b8, wc, cvec, conv.lin_beta.weight, norm.weight,
+                                 norm.bias, plan, cfg, w1, b1)
     w4, b4 = _stack4(conv)
     return fused.attn_block(x32.float(), xb, feat, anchor, w4, b4, wc, cvec, conv.lin_beta.weight, norm.weight,
                             norm.bias, plan, cfg, w1, b1)

@@ -629,6 +629,43 @@ def raw_gate_ln_bwd2(dy: Tensor, agg: Tensor, xr: Tensor, wbeta: Tensor, gamma: 
     return dagg, dagg_lp, dparams
 
 
+def raw_gate_ln_bwd3(dy: Tensor, agg: Tensor, xr: Tensor, wbeta: Tensor, gamma: Tensor, bias: Tensor, beta: Tensor,
+                     mean: Tensor, rstd: Tensor, stat_s: Tensor, heads: int, dxr: Tensor, p_drop: float, seed: int,
+                     offset: int, rng_step: Optional[Tensor] = None):
+    """As :func:`raw_gate_ln_bwd2` (always emits the storage-dtype copy of dagg) plus the gradient of the folded
+    edge-projection bias: returns (dagg f32, dagg_lp, dparams f32 [6*hidden] = dw_beta x3 | dgamma | dbias | dcvec)."""
+    lib = _lib.load()
+    n_rows, hidden = agg.shape
+    dev = agg.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    dagg = torch.empty(n_rows, hidden, **f32)
+    dagg_lp = torch.empty(n_rows, hidden, dtype=xr.dtype, device=dev)
+    partials = torch.empty(int(lib.alignn_gate_ln_bwd_partial_rows()) * 6 * hidden, **f32)
+    dparams = torch.empty(6 * hidden, **f32)
+    with torch.cuda.device(dev), _Launch("gate_ln_bwd", 2, (n_rows, hidden, xr.element_size())):
+        rc = lib.alignn_gate_ln_bwd3(_p(dy), _p(agg), _p(xr), _ld(xr), _p(wbeta), _p(gamma), _p(bias), _p(beta),
+                                     _p(mean), _p(rstd), _p(stat_s), heads, _p(dagg), _p(dagg_lp), _p(dxr), _ld(dxr),
+                                     _p(partials), _p(dparams), n_rows, hidden, _dtype_code(xr), float(p_drop), seed,
+                                     offset, _p(rng_step), _stream())
+    _lib.check(rc, "alignn_gate_ln_bwd3")
+    return dagg, dagg_lp, dparams
+
+
+def colsum(x: Tensor) -> Tensor:
+    """fp32 column sums of a 2-D tensor with unit column stride (deterministic hand-written reduction)."""
+    lib = _lib.load()
+    n_rows, width = x.shape
+    if not lib.alignn_colsum_supported(width) or x.dtype not in _DT or _ld(x) % 8:
+        return x.sum(0, dtype=torch.float32)
+    f32 = dict(dtype=torch.float32, device=x.device)
+    partials = torch.empty(int(lib.alignn_colsum_partial_floats(width)), **f32)
+    out = torch.empty(width, **f32)
+    with torch.cuda.device(x.device), _Launch("colsum", 2, (n_rows, width, x.element_size())):
+        rc = lib.alignn_colsum(_p(x), _ld(x), n_rows, width, _dtype_code(x), _p(partials), _p(out), _stream())
+    _lib.check(rc, "alignn_colsum")
+    return out
+
+
 def raw_angle_h1_fwd(a: Tensor, w1: Tensor, b1: Tensor, dtype: torch.dtype) -> Tensor:
     lib = _lib.load()
     n_edges, in_dim = a.shape

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define ALIGNN_ABI_VERSION 8
+#define ALIGNN_ABI_VERSION 9
 
 #define ALIGNN_F32 0
 #define ALIGNN_BF16 1
@@ -277,6 +277,26 @@ int alignn_gate_ln_bwd2(const float *dy, const float *agg, const void *xr, int64
                         float *dagg, void *dagg_lp, void *dxr, int64_t lddxr, float *partials, float *dparams,
                         int64_t n_rows, int hidden, int dtype,
                         float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step, void *stream);
+
+/* As alignn_gate_ln_bwd2, plus the gradient of the folded edge-projection bias c: dparams[5*hidden + ch] =
+ * sum_rows dagg[row, ch] * stat_s[row, head(ch)] (the `c_t * S_t` term of the aggregate; c = W_e b of the Linear folded
+ * into lin_edge, reference train.py:324,333 / :360-364).  partials: [partial_rows * 6 * hidden], dparams: [6 * hidden];
+ * hidden in {8..256} dividing 256 only. */
+int alignn_gate_ln_bwd3(const float *dy, const float *agg, const void *xr, int64_t ldxr,
+                        const float *wbeta, const float *gamma, const float *bias,
+                        const float *beta, const float *mean, const float *rstd,
+                        const float *stat_s, int heads,
+                        float *dagg, void *dagg_lp, void *dxr, int64_t lddxr, float *partials, float *dparams,
+                        int64_t n_rows, int hidden, int dtype,
+                        float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step, void *stream);
+
+/* Column sums out[c] = sum_r x[r * ld + c], c < width: the bias gradients of the stacked node projections
+ * (lin_query/key/value/skip of PyG TransformerConv, constructed at reference train.py:308,326; torch autograd's
+ * `grad.sum(0)`).  Deterministic two-stage reduction; partials: f32 [alignn_colsum_partial_floats(width)]. */
+int alignn_colsum_supported(int width);
+int64_t alignn_colsum_partial_floats(int width);
+int alignn_colsum(const void *x, int64_t ld, int64_t n_rows, int width, int dtype, float *partials, float *out,
+                  void *stream);
 
 /* First angle-encoder layer: h1 = relu(W1 a + b1) (reference scripts/train.py:360-362 applied at :554) and its
  * parameter gradients from the ReLU-masked feature gradient dpre: out[f*256 + c] = dW1[c,f] (f < in_dim),

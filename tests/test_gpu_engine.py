@@ -108,3 +108,33 @@ def test_lg_family_matches_stored_feature_family_on_the_model(monkeypatch):
     assert set(a[2]) == set(b[2])
     for k, g in b[2].items():
         assert float((a[2][k] - g).abs().max()) < 2e-2 * max(float(g.abs().max()), 1e-2 * gmax), k
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("shape", [(98304, 2048), (1000, 1024), (37, 256), (5, 8), (12, 48)])
+def test_colsum_matches_fp64(shape, dtype):
+    g = torch.Generator().manual_seed(shape[0])
+    big = torch.randn(shape[0], shape[1] + 64, generator=g).to(dtype).to(DEV)
+    x = big[:, 32:32 + shape[1]] if (shape[1] % 8 == 0) else big[:, :shape[1]]      # strided rows, 16-byte aligned
+    got = ops.colsum(x)
+    want = x.double().sum(0)
+    assert got.dtype == torch.float32 and rel_err(got, want) < 2e-6
+    assert torch.equal(ops.colsum(x), got)                                            # deterministic
+
+
+def test_gate_ln_bwd3_adds_the_folded_bias_gradient():
+    n, hid, h = 1237, 256, 4
+    g = torch.Generator().manual_seed(7)
+    dy, agg = torch.randn(n, hid, generator=g).to(DEV), torch.randn(n, hid, generator=g).to(DEV)
+    proj = torch.randn(n, 4 * hid, generator=g).to(torch.bfloat16).to(DEV)
+    xr = proj[:, 3 * hid:]
+    wb, gm, bl = (torch.randn(k, generator=g).to(DEV) * 0.1 for k in (3 * hid, hid, hid))
+    beta, mean, rstd = (torch.rand(n, generator=g).to(DEV) for _ in range(3))
+    s = torch.rand(n, h, generator=g).to(DEV)
+    d2 = torch.zeros_like(proj); d3 = torch.zeros_like(proj)
+    a2 = ops.raw_gate_ln_bwd2(dy, agg, xr, wb, gm, bl, beta, mean, rstd, d2[:, 3 * hid:], True, 0.1, 5, 9)
+    a3 = ops.raw_gate_ln_bwd3(dy, agg, xr, wb, gm, bl, beta, mean, rstd, s, h, d3[:, 3 * hid:], 0.1, 5, 9)
+    assert torch.equal(a2[0], a3[0]) and torch.equal(a2[1], a3[1]) and torch.equal(d2, d3)
+    assert torch.equal(a2[2], a3[2][:5 * hid])
+    want = (a3[0].double().view(n, h, hid // h) * s.double().unsqueeze(-1)).sum(0).reshape(hid)
+    assert rel_err(a3[2][5 * hid:], want) < 1e-5
