@@ -51,7 +51,7 @@ SIGNATURES = {
                                           c_float, c_uint64, c_uint64, _P, _P]),
     "alignn_edgeattn_mma_bwd_dst_s": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, _P, c_int64, c_int64,
                                               _P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P, c_int64,
-                                              c_int64, _P, _P, _P, c_int, c_int64, c_int64, c_int, c_int, c_int,
+                                              c_int64, _P, _P, _P, c_int64, c_int, c_int64, c_int64, c_int, c_int, c_int,
                                               c_float, c_uint64, c_uint64, _P, _P]),
     "alignn_lgattn_supported": (c_int, [c_int, c_int, c_int, c_int]),
     "alignn_lg_pack_angles": (c_int, [_P, _P, _P, c_int64, c_int, _P]),
@@ -71,7 +71,7 @@ SIGNATURES = {
                                     c_int64, c_int, c_int, c_float, c_float, c_uint64, c_uint64, _P, _P]),
     "alignn_gate_ln_bwd2": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P, _P,
                                     c_int64, c_int, c_int, c_float, c_uint64, c_uint64, _P, _P]),
-    "alignn_gate_ln_bwd3": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, c_int64, _P, _P,
+    "alignn_gate_ln_bwd3": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, c_int64, _P, _P,
                                     c_int64, c_int, c_int, c_float, c_uint64, c_uint64, _P, _P]),
     "alignn_colsum_supported": (c_int, [c_int]),
     "alignn_colsum_partial_floats": (c_int64, [c_int]),
@@ -84,7 +84,7 @@ SIGNATURES = {
     "alignn_segment_mean_bwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P]),
 }
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 F32, BF16 = 0, 1
 
 

@@ -302,7 +302,8 @@ struct MmBwdParams {
     __nv_bfloat16 *bbar;                     // [4, Nn, 256]
     float *coef;                             // [Ne, 8] by caller edge id: (a~_0..3, ds_0..3)
     const __nv_bfloat16 *df_in;              // [Ne, 256] running sum or null
-    __nv_bfloat16 *df_out;                   // [Ne, 256] or null (feature gradient not wanted)
+    __nv_bfloat16 *df_out;                   // [Ne, 256] (row stride lddf) or null (feature gradient not wanted)
+    int64_t lddf;                            // row stride (elements) of df_in / df_out
     int64_t n_nodes, n_edges;
     int64_t ldq, ldk, ldv, lddq;
     int64_t ldqt, hsqt, ldgt, hsgt, ldbb, hsbb;
@@ -514,8 +515,8 @@ edgeattn_mma_bwd_kernel(const MmBwdParams P) {
         if (P.df_out) {
             const uint32_t a_lo = lo_half ? ds_lo : pack_bf16(at00, at01);   // k 0..3: ds (x QT rows), k 4..7: a~ (x GT rows)
             const uint32_t a_hi = lo_half ? ds_hi : pack_bf16(at10, at11);
-            __nv_bfloat16 *o0 = P.df_out + (int64_t)id0 * MM_HID + 8 * q, *o1 = P.df_out + (int64_t)id1 * MM_HID + 8 * q;
-            const __nv_bfloat16 *i0 = P.df_in + (int64_t)id0 * MM_HID + 8 * q, *i1 = P.df_in + (int64_t)id1 * MM_HID + 8 * q;
+            __nv_bfloat16 *o0 = P.df_out + (int64_t)id0 * P.lddf + 8 * q, *o1 = P.df_out + (int64_t)id1 * P.lddf + 8 * q;
+            const __nv_bfloat16 *i0 = P.df_in + (int64_t)id0 * P.lddf + 8 * q, *i1 = P.df_in + (int64_t)id1 * P.lddf + 8 * q;
             const uint32_t fa = ftile + g * MM_ROWB + q * 16;
 #pragma unroll
             for (int cb = 0; cb < 8; ++cb) {
@@ -671,7 +672,7 @@ extern "C" int alignn_edgeattn_mma_bwd_dst_s(const float *dagg, const void *dagg
                                              const void *feat, const float *stat_m, const float *stat_z,
                                              const int32_t *rowptr, const int32_t *col, const int32_t *eid,
                                              void *dq, int64_t lddq, void *bbar, int64_t ldbb, int64_t hsbb, float *coef,
-                                             const void *df_in, void *df_out, int relu_mask,
+                                             const void *df_in, void *df_out, int64_t lddf, int relu_mask,
                                              int64_t n_nodes, int64_t n_edges, int hidden, int heads, int dtype,
                                              float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step,
                                              void *stream) {
@@ -683,6 +684,7 @@ extern "C" int alignn_edgeattn_mma_bwd_dst_s(const float *dagg, const void *dagg
         return ALIGNN_ERR_BAD_ARG;
     if (n_edges > 0 && (!feat || !col || !eid || !coef)) return ALIGNN_ERR_BAD_ARG;
     if (df_in && !df_out) return ALIGNN_ERR_BAD_ARG;
+    if (df_out && (lddf < MM_HID || (lddf % 8))) return ALIGNN_ERR_BAD_ARG;
     if (!aligned16(dagg) || !aligned16(dagg_lp) || !aligned16(agg) || !aligned16(q) || !aligned16(k) || !aligned16(v) ||
         !aligned16(qt) || !aligned16(gt) || !aligned16(cvec) || !aligned16(feat) || !aligned16(dq) || !aligned16(bbar) ||
         !aligned16(coef) || !aligned16(df_in) || !aligned16(df_out) || (ldq % 8) || (ldk % 8) || (ldv % 8) || (lddq % 8) ||
@@ -695,7 +697,7 @@ extern "C" int alignn_edgeattn_mma_bwd_dst_s(const float *dagg, const void *dagg
     p.feat = (const __nv_bfloat16 *)feat; p.stat_m = stat_m; p.stat_z = stat_z;
     p.rowptr = rowptr; p.col = col; p.eid = eid;
     p.dq = (__nv_bfloat16 *)dq; p.bbar = (__nv_bfloat16 *)bbar; p.coef = coef;
-    p.df_in = (const __nv_bfloat16 *)df_in; p.df_out = (__nv_bfloat16 *)df_out;
+    p.df_in = (const __nv_bfloat16 *)df_in; p.df_out = (__nv_bfloat16 *)df_out; p.lddf = lddf;
     p.n_nodes = n_nodes; p.n_edges = n_edges; p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.lddq = lddq;
     p.ldqt = ldqt; p.hsqt = hsqt; p.ldgt = ldgt; p.hsgt = hsgt; p.ldbb = ldbb; p.hsbb = hsbb; p.rng_step = rng_step;
     p.scale = 1.0f / sqrtf((float)(hidden / heads));
@@ -739,6 +741,6 @@ extern "C" int alignn_edgeattn_mma_bwd_dst(const float *dagg, const void *dagg_l
                                            float p_drop, uint64_t seed, uint64_t offset, void *stream) {
     return alignn_edgeattn_mma_bwd_dst_s(dagg, dagg_lp, agg, q, k, v, ldq, ldk, ldv, qt, MM_HID, n_nodes * MM_HID, gt,
                                          MM_HID, n_nodes * MM_HID, cvec, feat, stat_m, stat_z, rowptr, col, eid, dq, lddq,
-                                         bbar, MM_HID, n_nodes * MM_HID, coef, df_in, df_out, relu_mask, n_nodes, n_edges,
+                                         bbar, MM_HID, n_nodes * MM_HID, coef, df_in, df_out, MM_HID, relu_mask, n_nodes, n_edges,
                                          hidden, heads, dtype, p_drop, seed, offset, nullptr, stream);
 }

@@ -39,6 +39,8 @@ struct GateExtra {
     const float *stat_s;   // [rows, heads] f32: S = sum_j a~
     float *agg_out;        // [rows, hidden] f32: full aggregate, saved for backward (may be null)
     void *dagg_lp;         // backward: storage-dtype copy of dagg (may be null)
+    const void *dy2;       // backward: second upstream-gradient addend in storage dtype (may be null)
+    int64_t lddy2;
     bool dcvec;            // backward: also reduce dc = sum_rows dagg * S (needs stat_s, heads) -> 6 parameter vectors
     int heads;
     int64_t ldxr, lddxr;   // row strides (elements) of xr and dxr
@@ -163,7 +165,12 @@ gate_ln_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ agg, 
 #pragma unroll
         for (int c = 0; c < 8; ++c) gf.v[c] = af.v[c] = sf.v[c] = 0.f;
         if (ok) {
-            gf = ld8(dy + row * hidden + ch);
+            if (dy) gf = ld8(dy + row * hidden + ch);
+            if (X.dy2) {
+                const F8 g2 = ld8(reinterpret_cast<const T *>(X.dy2) + row * X.lddy2 + ch);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) gf.v[c] += g2.v[c];
+            }
             af = ld8(agg + row * hidden + ch);
             sf = ld8(xr + row * X.ldxr + ch);
             beta = __ldg(beta_in + row);
@@ -484,7 +491,7 @@ extern "C" int64_t alignn_gate_ln_bwd_partial_rows(void) { return EPI_PARTIAL_BL
 
 static GateExtra plain_extra(int hidden) {
     GateExtra X;
-    X.agge = nullptr; X.cvec = nullptr; X.stat_s = nullptr; X.agg_out = nullptr; X.dagg_lp = nullptr; X.dcvec = false;
+    X.agge = nullptr; X.cvec = nullptr; X.stat_s = nullptr; X.agg_out = nullptr; X.dagg_lp = nullptr; X.dcvec = false; X.dy2 = nullptr; X.lddy2 = hidden;
     X.heads = 1; X.ldxr = hidden; X.lddxr = hidden; X.rng_step = nullptr;
     return X;
 }
@@ -546,7 +553,7 @@ static int gate_ln_bwd_impl(const float *dy, const float *agg, const void *xr,
     if (n_rows < 0 || hidden <= 0 || hidden > 2048) return ALIGNN_ERR_BAD_SHAPE;
     if (!(p_drop >= 0.f && p_drop < 1.f)) return ALIGNN_ERR_BAD_ARG;
     if (!partials || !dparams || !wbeta || !gamma || !bias) return ALIGNN_ERR_BAD_ARG;
-    if (n_rows > 0 && (!dy || !agg || !xr || !beta || !mean || !rstd || !dagg || !dxr)) return ALIGNN_ERR_BAD_ARG;
+    if (n_rows > 0 && ((!dy && !X.dy2) || !agg || !xr || !beta || !mean || !rstd || !dagg || !dxr)) return ALIGNN_ERR_BAD_ARG;
     if (!aligned16(dy) || !aligned16(agg) || !aligned16(xr) || !aligned16(wbeta) || !aligned16(gamma) ||
         !aligned16(bias) || !aligned16(dagg) || !aligned16(dxr) || !aligned16(X.dagg_lp) || (X.ldxr % 8) || (X.lddxr % 8))
         return ALIGNN_ERR_BAD_ARG;
@@ -570,7 +577,7 @@ extern "C" int alignn_gate_ln_bwd(const float *dy, const float *agg, const void 
                             hidden, dtype, p_drop, seed, offset, plain_extra(hidden), false, stream);
 }
 
-extern "C" int alignn_gate_ln_bwd3(const float *dy, const float *agg, const void *xr, int64_t ldxr,
+extern "C" int alignn_gate_ln_bwd3(const float *dy, const void *dy2, int64_t lddy2, const float *agg, const void *xr, int64_t ldxr,
                                    const float *wbeta, const float *gamma, const float *bias,
                                    const float *beta, const float *mean, const float *rstd,
                                    const float *stat_s, int heads,
@@ -579,7 +586,8 @@ extern "C" int alignn_gate_ln_bwd3(const float *dy, const float *agg, const void
                                    float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step, void *stream) {
     GateExtra X = plain_extra(hidden);
     X.dagg_lp = dagg_lp; X.ldxr = ldxr; X.lddxr = lddxr; X.rng_step = rng_step;
-    X.stat_s = stat_s; X.heads = heads; X.dcvec = true;
+    X.stat_s = stat_s; X.heads = heads; X.dcvec = true; X.dy2 = dy2; X.lddy2 = lddy2;
+    if ((!dy && !dy2) || (dy2 && (lddy2 % 8 || !aligned16(dy2)))) return ALIGNN_ERR_BAD_ARG;
     if (!stat_s || heads <= 0 || hidden % heads || (hidden / heads) % 8) return ALIGNN_ERR_BAD_ARG;
     if (hidden % 8 || hidden > 256 || (256 % hidden)) return ALIGNN_ERR_BAD_SHAPE;   // fast mapping only
     return gate_ln_bwd_impl(dy, agg, xr, wbeta, gamma, bias, beta, mean, rstd, dagg, dxr, partials, dparams, n_rows,

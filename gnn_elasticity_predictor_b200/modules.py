@@ -29,7 +29,7 @@ import torch
 import torch.nn.functional as F
 from torch import Tensor, nn
 
-from . import fused, ops
+from . import fused, ops, trunk as trunk_mod
 from .fused import BlockCfg, FeatGradAccumulator, LgShared
 from .ops import GraphPlan
 
@@ -334,11 +334,14 @@ class AlignnRegressor(nn.Module):
         dev = data.x.device
         n_bonds, n_angles = data.edge_index.size(1), data.lg_edge_index.size(1)
         with torch.autocast("cuda", enabled=False):
-            node32 = _mlp2(self.node_encoder, data.x, cd).float()
+            node_b0 = _mlp2(self.node_encoder, data.x, cd)
+            node32 = node_b0.float()
             if data.edge_attr.numel() > 0:
-                edge32 = _mlp2(self.edge_encoder, data.edge_attr, cd).float()
+                edge_b0 = _mlp2(self.edge_encoder, data.edge_attr, cd)
+                edge32 = edge_b0.float()
             else:
                 edge32 = torch.zeros(n_bonds, self.hidden, device=dev)
+                edge_b0 = edge32.to(cd)
             plans = getattr(data, "_alignn_plans", None)
             if plans is None:
                 plans = self.build_plans(data)
@@ -369,6 +372,10 @@ class AlignnRegressor(nn.Module):
                     h1 = _mlp2(enc, data.lg_edge_attr, cd)          # unusual angle_dim: plain features
                 else:
                     h1 = torch.zeros(n_angles, self.hidden, device=dev, dtype=cd)
+            if lg is not None and run_atoms and getattr(self, "fused_trunk", True) and \
+                    len(self.edge_blocks) == len(self.node_blocks):
+                node32 = self._run_fused_trunk(node32, node_b0, edge32, edge_b0, lg, lg_plan, g_plan, w2, b2)
+                return self._head_features(node32, data, pool_plan)
             accum = FeatGradAccumulator(n_layers) if run_lg and lg is None else None
 
             edge_b = node_b = None
@@ -401,6 +408,51 @@ class AlignnRegressor(nn.Module):
                     node32, node_b = _stream_block(nb.conv, nb.norm, nb.dropout.p, self.training, node32, node_b, feat,
                                                    edge32, wc, cvec, g_plan, cd)
             return self._head_features(node32, data, pool_plan)
+
+    def _run_fused_trunk(self, node32: Tensor, node_b: Tensor, edge32: Tensor, edge_b: Tensor, lg: LgShared,
+                         lg_plan: GraphPlan, g_plan: GraphPlan, w2: Tensor, b2: Tensor) -> Tensor:
+        """All blocks as one explicit forward / backward program (``trunk.py``).  The weight folds of every block are
+        batched here under autograd: ``Wc = W_e W2`` (line graph, second angle-encoder Linear folded into ``lin_edge``),
+        ``Wc = W_e W_p`` (atom graph, ``edge_proj`` folded), and the query-side fold ``Wc[t]^T Wq_t`` that turns
+        ``qt_t = q_t Wc[t]`` into four more slices of the node projection."""
+        nl, h, hid = len(self.edge_blocks), self.heads, self.hidden
+        c = hid // h
+        blocks = [b for pair in zip(self.edge_blocks, self.node_blocks) for b in pair]       # 2l: edge, 2l+1: node
+        convs = [b.conv for b in blocks]
+        f = lambda ts: torch.stack([t.float() for t in ts])                                  # noqa: E731
+        we_lg = f([b.conv.lin_edge.weight for b in self.edge_blocks])                        # [L, H, H]
+        we_at = f([b.conv.lin_edge.weight for b in self.node_blocks])
+        wc_lg, cv_lg = we_lg @ w2, we_lg @ b2
+        wp, bp = f([b.edge_proj.weight for b in self.node_blocks]), f([b.edge_proj.bias for b in self.node_blocks])
+        wc_at, cv_at = torch.bmm(we_at, wp), torch.bmm(we_at, bp.unsqueeze(-1)).squeeze(-1)
+        wc = torch.stack([wc_lg, wc_at], dim=1).reshape(2 * nl, hid, hid)
+        cvec = torch.stack([cv_lg, cv_at], dim=1).reshape(2 * nl, hid)
+        wq, bq = f([cv.lin_query.weight for cv in convs]), f([cv.lin_query.bias for cv in convs])
+        zeros = torch.zeros(hid, device=node32.device)
+        w4 = [wq, f([cv.lin_key.weight for cv in convs]), f([cv.lin_value.weight for cv in convs]),
+              f([cv.lin_skip.weight for cv in convs])]
+        b4 = [bq, f([cv.lin_key.bias for cv in convs]), f([cv.lin_value.bias for cv in convs]),
+              f([cv.lin_skip.bias if cv.lin_skip.bias is not None else zeros for cv in convs])]
+        wc3 = wc.view(2 * nl * h, c, hid)
+        wqt = torch.bmm(wc3.transpose(1, 2), wq.view(2 * nl * h, c, hid)).view(2 * nl, h * hid, hid)
+        bqt = torch.bmm(bq.view(2 * nl * h, 1, c), wc3).view(2 * nl, h * hid)
+        w8 = torch.cat(w4 + [wqt], dim=1)                                                    # [2L, 8H, H]
+        b8 = torch.cat(b4 + [bqt], dim=1)                                                    # [2L, 8H]
+        wbeta = f([cv.lin_beta.weight.reshape(-1) for cv in convs])
+        gamma, beta_ln = f([b.norm.weight for b in blocks]), f([b.norm.bias for b in blocks])
+        train = self.training
+        p_attn = [cv.dropout if train else 0.0 for cv in convs]
+        p_out = [b.dropout.p if train else 0.0 for b in blocks]
+        keys = []
+        for pa, po in zip(p_attn, p_out):
+            sa, oa = ops.next_dropout_key() if pa > 0.0 else (0, 0)
+            so, oo = ops.next_dropout_key() if po > 0.0 else (0, 0)
+            keys.append((sa, oa, so, oo))
+        cfg = trunk_mod.TrunkCfg(heads=h, n_layers=nl, eps=[b.norm.eps for b in blocks], p_attn=p_attn, p_out=p_out,
+                                 keys=keys, lg_plan=lg_plan, g_plan=g_plan, a_csr=lg.a_csr, w1=lg.w1, b1=lg.b1)
+        enc = self.angle_encoder
+        return trunk_mod.run_trunk(node32, node_b, edge32, edge_b, w8, b8, wc, cvec, wbeta, gamma, beta_ln,
+                                   enc[0].weight, enc[0].bias, cfg)
 
     def build_plans(self, data):
         """CSR/CSC plans of the line graph and the atom graph + pooling plan: once per batch, reused by all

@@ -407,15 +407,18 @@ def raw_edgeattn_fwd(q: Tensor, k: Tensor, v: Tensor, qt: Tensor, feat: Tensor, 
 
 
 def raw_attn_fwd_s(q: Tensor, k: Tensor, v: Tensor, qt: Tensor, feat: Tensor, plan: GraphPlan, heads: int,
-                   p_drop: float, seed: int, offset: int, rng_step: Optional[Tensor] = None):
-    """Stored-feature tensor-core forward; ``qt`` is a [heads, n, 256] view with arbitrary row / head strides."""
+                   p_drop: float, seed: int, offset: int, rng_step: Optional[Tensor] = None,
+                   abar: Optional[Tensor] = None):
+    """Stored-feature tensor-core forward; ``qt`` (and ``abar`` when given) are [heads, n, 256] views with arbitrary row /
+    head strides."""
     lib = _lib.load()
     n_nodes, hidden = q.shape
     n_edges = plan.n_edges
     dev = q.device
     f32 = dict(dtype=torch.float32, device=dev)
     aggv = torch.empty(n_nodes, hidden, **f32)
-    abar = torch.empty(heads, n_nodes, hidden, dtype=q.dtype, device=dev)
+    if abar is None:
+        abar = torch.empty(heads, n_nodes, hidden, dtype=q.dtype, device=dev)
     m, z, s = (torch.empty(n_nodes, heads, **f32) for _ in range(3))
     with torch.cuda.device(dev), _Launch("edgeattn_fwd", 1, (n_nodes, n_edges, hidden, heads, q.element_size())):
         rc = lib.alignn_edgeattn_mma_fwd_s(_p(q), _p(k), _p(v), _ld(q), _ld(k), _ld(v), _p(qt), int(qt.stride(1)),
@@ -443,7 +446,8 @@ def raw_attn_bwd_s(dagg: Tensor, dagg_lp: Tensor, agg: Tensor, q: Tensor, k: Ten
                 _p(dagg), _p(dagg_lp), _p(agg), _p(q), _p(k), _p(v), _ld(q), _ld(k), _ld(v), _p(qt), int(qt.stride(1)),
                 int(qt.stride(0)), _p(gt), int(gt.stride(1)), int(gt.stride(0)), _p(cvec), _p(feat), _p(m), _p(z),
                 _p(plan.rowptr), _p(plan.col), _p(plan.eid), _p(dq), _ld(dq), _p(bbar), int(bbar.stride(1)),
-                int(bbar.stride(0)), _p(coef), None, _p(df_out), 0, n_nodes, n_edges, hidden, heads, _dtype_code(q),
+                int(bbar.stride(0)), _p(coef), None, _p(df_out), _ld(df_out) if df_out is not None else hidden, 0,
+                n_nodes, n_edges, hidden, heads, _dtype_code(q),
                 float(p_drop), seed, offset, _p(rng_step), _stream())
         _lib.check(rc, "alignn_edgeattn_mma_bwd_dst_s")
         with _Launch("edgeattn_bwd_src", 1, (n_nodes, n_edges, hidden, heads, q.element_size())):
@@ -466,15 +470,18 @@ def pack_angles(a: Tensor, plan: GraphPlan) -> Tensor:
 
 
 def raw_lgattn_fwd(q: Tensor, k: Tensor, v: Tensor, qt: Tensor, a_csr: Tensor, w1: Tensor, b1: Tensor, plan: GraphPlan,
-                   heads: int, p_drop: float, seed: int, offset: int, rng_step: Optional[Tensor] = None):
-    """``qt``: [heads, n, 256] view (any row / head strides, unit channel stride).  Returns (aggv, abar, m, z, s)."""
+                   heads: int, p_drop: float, seed: int, offset: int, rng_step: Optional[Tensor] = None,
+                   abar: Optional[Tensor] = None):
+    """``qt`` (and ``abar`` when given): [heads, n, 256] views (any row / head strides, unit channel stride).
+    Returns (aggv, abar, m, z, s)."""
     lib = _lib.load()
     n_nodes, hidden = q.shape
     n_edges = plan.n_edges
     dev = q.device
     f32 = dict(dtype=torch.float32, device=dev)
     aggv = torch.empty(n_nodes, hidden, **f32)
-    abar = torch.empty(heads, n_nodes, hidden, dtype=q.dtype, device=dev)
+    if abar is None:
+        abar = torch.empty(heads, n_nodes, hidden, dtype=q.dtype, device=dev)
     m, z, s = (torch.empty(n_nodes, heads, **f32) for _ in range(3))
     with torch.cuda.device(dev), _Launch("lgattn_fwd", 1, (n_nodes, n_edges, hidden, heads, q.element_size())):
         rc = lib.alignn_lgattn_fwd(_p(q), _p(k), _p(v), _ld(q), _ld(k), _ld(v), _p(qt), int(qt.stride(1)),
@@ -629,9 +636,9 @@ def raw_gate_ln_bwd2(dy: Tensor, agg: Tensor, xr: Tensor, wbeta: Tensor, gamma: 
     return dagg, dagg_lp, dparams
 
 
-def raw_gate_ln_bwd3(dy: Tensor, agg: Tensor, xr: Tensor, wbeta: Tensor, gamma: Tensor, bias: Tensor, beta: Tensor,
+def raw_gate_ln_bwd3(dy: Optional[Tensor], agg: Tensor, xr: Tensor, wbeta: Tensor, gamma: Tensor, bias: Tensor, beta: Tensor,
                      mean: Tensor, rstd: Tensor, stat_s: Tensor, heads: int, dxr: Tensor, p_drop: float, seed: int,
-                     offset: int, rng_step: Optional[Tensor] = None):
+                     offset: int, rng_step: Optional[Tensor] = None, dy2: Optional[Tensor] = None):
     """As :func:`raw_gate_ln_bwd2` (always emits the storage-dtype copy of dagg) plus the gradient of the folded
     edge-projection bias: returns (dagg f32, dagg_lp, dparams f32 [6*hidden] = dw_beta x3 | dgamma | dbias | dcvec)."""
     lib = _lib.load()
@@ -643,7 +650,7 @@ def raw_gate_ln_bwd3(dy: Tensor, agg: Tensor, xr: Tensor, wbeta: Tensor, gamma: 
     partials = torch.empty(int(lib.alignn_gate_ln_bwd_partial_rows()) * 6 * hidden, **f32)
     dparams = torch.empty(6 * hidden, **f32)
     with torch.cuda.device(dev), _Launch("gate_ln_bwd", 2, (n_rows, hidden, xr.element_size())):
-        rc = lib.alignn_gate_ln_bwd3(_p(dy), _p(agg), _p(xr), _ld(xr), _p(wbeta), _p(gamma), _p(bias), _p(beta),
+        rc = lib.alignn_gate_ln_bwd3(_p(dy), _p(dy2), _ld(dy2) if dy2 is not None else hidden, _p(agg), _p(xr), _ld(xr), _p(wbeta), _p(gamma), _p(bias), _p(beta),
                                      _p(mean), _p(rstd), _p(stat_s), heads, _p(dagg), _p(dagg_lp), _p(dxr), _ld(dxr),
                                      _p(partials), _p(dparams), n_rows, hidden, _dtype_code(xr), float(p_drop), seed,
                                      offset, _p(rng_step), _stream())

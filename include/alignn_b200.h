@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define ALIGNN_ABI_VERSION 9
+#define ALIGNN_ABI_VERSION 10
 
 #define ALIGNN_F32 0
 #define ALIGNN_BF16 1
@@ -205,7 +205,7 @@ int alignn_edgeattn_mma_bwd_dst_s(const float *dagg, const void *dagg_lp, const 
                                   const float *cvec, const void *feat, const float *stat_m, const float *stat_z,
                                   const int32_t *rowptr, const int32_t *col, const int32_t *eid,
                                   void *dq, int64_t lddq, void *bbar, int64_t ldbb, int64_t hsbb, float *coef,
-                                  const void *df_in, void *df_out, int relu_mask,
+                                  const void *df_in, void *df_out, int64_t lddf, int relu_mask,
                                   int64_t n_nodes, int64_t n_edges, int hidden, int heads, int dtype,
                                   float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step, void *stream);
 
@@ -281,8 +281,10 @@ int alignn_gate_ln_bwd2(const float *dy, const float *agg, const void *xr, int64
 /* As alignn_gate_ln_bwd2, plus the gradient of the folded edge-projection bias c: dparams[5*hidden + ch] =
  * sum_rows dagg[row, ch] * stat_s[row, head(ch)] (the `c_t * S_t` term of the aggregate; c = W_e b of the Linear folded
  * into lin_edge, reference train.py:324,333 / :360-364).  partials: [partial_rows * 6 * hidden], dparams: [6 * hidden];
- * hidden in {8..256} dividing 256 only. */
-int alignn_gate_ln_bwd3(const float *dy, const float *agg, const void *xr, int64_t ldxr,
+ * hidden in {8..256} dividing 256 only.  The upstream gradient is dy (f32, may be null = 0) + dy2 (storage dtype, row
+ * stride lddy2, may be null): the second addend is the feature gradient the atom-graph conv sends to the bond states
+ * (autograd's sum over the two consumers of `edge_state`, train.py:559-560), added on load instead of in its own pass. */
+int alignn_gate_ln_bwd3(const float *dy, const void *dy2, int64_t lddy2, const float *agg, const void *xr, int64_t ldxr,
                         const float *wbeta, const float *gamma, const float *bias,
                         const float *beta, const float *mean, const float *rstd,
                         const float *stat_s, int heads,

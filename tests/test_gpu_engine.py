@@ -138,3 +138,27 @@ def test_gate_ln_bwd3_adds_the_folded_bias_gradient():
     assert torch.equal(a2[2], a3[2][:5 * hid])
     want = (a3[0].double().view(n, h, hid // h) * s.double().unsqueeze(-1)).sum(0).reshape(hid)
     assert rel_err(a3[2][5 * hid:], want) < 1e-5
+
+
+@pytest.mark.parametrize("lg_inc", ["pyg", "bonds"])
+def test_fused_trunk_matches_per_block_autograd_path(lg_inc):
+    """The explicit trunk program (trunk.py: folded gradient sums, stacked weight folds) against one autograd node per
+    block (fused.py) on the same bf16 kernels: outputs and every parameter gradient."""
+    m = _model(seed=6, layers=3)
+    m.base.compute_dtype = torch.bfloat16
+    batch = pkg.synthetic_batch(12, 16, 12, seed=4, lg_inc=lg_inc).to(DEV)
+    tz = pkg.zscore_targets(batch.y, batch.num_graphs)
+    out = {}
+    for fused_trunk in (True, False):
+        m.base.fused_trunk = fused_trunk
+        m.zero_grad(set_to_none=True)
+        mean, logvar = m(batch)
+        loss = pkg.gaussian_nll_loss(mean.float(), logvar.float(), tz)
+        loss.backward()
+        out[fused_trunk] = (mean, logvar, {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None})
+    a, b = out[True], out[False]
+    assert rel_err(a[0], b[0]) < 1e-2 and rel_err(a[1], b[1]) < 1e-2
+    assert set(a[2]) == set(b[2])
+    gmax = max(float(g.abs().max()) for g in b[2].values())
+    for k, g in b[2].items():
+        assert float((a[2][k] - g).abs().max()) < 1.5e-2 * max(float(g.abs().max()), 1e-2 * gmax), k
