@@ -40,6 +40,8 @@ SIGNATURES = {
                                         c_int64, c_int64, c_int, c_int, c_int, c_float, c_uint64, c_uint64, _P]),
     "alignn_edgeattn_bwd_src": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64,
                                         c_int, c_int, c_int, _P]),
+    "alignn_edgeattn_bwd_src_lp": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64,
+                                           c_int, c_int, c_int, _P]),
     "alignn_edgeattn_mma_supported": (c_int, [c_int, c_int, c_int]),
     "alignn_edgeattn_mma_fwd": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                         c_int64, c_int64, c_int, c_int, c_int, c_float, c_uint64, c_uint64, _P]),
@@ -84,7 +86,7 @@ SIGNATURES = {
     "alignn_segment_mean_bwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P]),
 }
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 F32, BF16 = 0, 1
 
 

@@ -261,13 +261,14 @@ conv_bwd_dst_kernel(const float *__restrict__ dagg, const float *__restrict__ ag
 // ------------------------------------------------------------------------------------------------
 // backward, source-sorted pass: dk_j = sum_i dss_ij q_i ; dv_j = sum_i a~_ij dagg_i
 // ------------------------------------------------------------------------------------------------
-template <typename T, int LANES>
+template <typename T, int LANES, typename G = float>
 __global__ void __launch_bounds__(CONV_THREADS)
-conv_bwd_src_kernel(const float *__restrict__ dagg, const T *__restrict__ q, const float *__restrict__ coef,
+conv_bwd_src_kernel(const G *__restrict__ dagg, const T *__restrict__ q, const float *__restrict__ coef,
                     const int32_t *__restrict__ rowptr_t, const int32_t *__restrict__ col_t,
                     const int32_t *__restrict__ eid_t, T *__restrict__ dk, T *__restrict__ dv,
                     int64_t n_nodes, int hidden, int heads, int lph, int64_t ldq, int64_t ldd) {
     constexpr int RPW = 32 / LANES;
+    constexpr int U = 4;                       // edges in flight per lane: the pass is bound by L2 gather bandwidth
     const int lane = threadIdx.x & 31;
     const int sub = lane % LANES;
     const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -280,27 +281,32 @@ conv_bwd_src_kernel(const float *__restrict__ dagg, const T *__restrict__ q, con
 #pragma unroll
     for (int c = 0; c < 8; ++c) dkf.v[c] = dvf.v[c] = 0.f;
     int p = beg;
-    for (; p + 1 < end; p += 2) {
-        const int i0 = __ldg(col_t + p), i1 = __ldg(col_t + p + 1);
-        const int id0 = __ldg(eid_t + p), id1 = __ldg(eid_t + p + 1);
-        const F8 g0 = ld8(dagg + (int64_t)i0 * hidden + ch), g1 = ld8(dagg + (int64_t)i1 * hidden + ch);
-        const F8 q0 = ld8(q + (int64_t)i0 * ldq + ch), q1 = ld8(q + (int64_t)i1 * ldq + ch);
-        const float at0 = __ldg(coef + (int64_t)id0 * 2 * heads + head);
-        const float ds0 = __ldg(coef + (int64_t)id0 * 2 * heads + heads + head);
-        const float at1 = __ldg(coef + (int64_t)id1 * 2 * heads + head);
-        const float ds1 = __ldg(coef + (int64_t)id1 * 2 * heads + heads + head);
+    for (; p + U <= end; p += U) {
+        int i[U], id[U];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            dvf.v[c] = fmaf(at0, g0.v[c], dvf.v[c]);
-            dkf.v[c] = fmaf(ds0, q0.v[c], dkf.v[c]);
+        for (int u = 0; u < U; ++u) {
+            i[u] = __ldg(col_t + p + u);
+            id[u] = __ldg(eid_t + p + u);
+        }
+        F8 g[U], qq[U];
+        float at[U], ds[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            g[u] = ld8(dagg + (int64_t)i[u] * hidden + ch);
+            qq[u] = ld8(q + (int64_t)i[u] * ldq + ch);
+            at[u] = __ldg(coef + (int64_t)id[u] * 2 * heads + head);
+            ds[u] = __ldg(coef + (int64_t)id[u] * 2 * heads + heads + head);
         }
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            dvf.v[c] = fmaf(at1, g1.v[c], dvf.v[c]);
-            dkf.v[c] = fmaf(ds1, q1.v[c], dkf.v[c]);
+        for (int u = 0; u < U; ++u) {        // accumulation in edge order: same sums as the one-at-a-time loop
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                dvf.v[c] = fmaf(at[u], g[u].v[c], dvf.v[c]);
+                dkf.v[c] = fmaf(ds[u], qq[u].v[c], dkf.v[c]);
+            }
         }
     }
-    if (p < end) {
+    for (; p < end; ++p) {
         const int i0 = __ldg(col_t + p);
         const int id0 = __ldg(eid_t + p);
         const F8 g0 = ld8(dagg + (int64_t)i0 * hidden + ch);
@@ -644,6 +650,28 @@ extern "C" int alignn_conv_bwd(const float *dagg, const float *agg,
     if (dtype == ALIGNN_F32) return dispatch_bwd<float>(a);
     if (dtype == ALIGNN_BF16) return dispatch_bwd<__nv_bfloat16>(a);
     return ALIGNN_ERR_BAD_DTYPE;
+}
+
+// same pass with the upstream gradient in STORAGE dtype (bf16): the pass is bound by L2 gather bandwidth
+// (1.5 KB per edge with an fp32 dagg row, 1 KB with a bf16 one)
+extern "C" int alignn_edgeattn_bwd_src_lp(const void *dagg_lp, const void *q, int64_t ldq, const float *coef,
+                                          const int32_t *rowptr_t, const int32_t *col_t, const int32_t *eid_t,
+                                          void *dk, void *dv, int64_t ldd, int64_t n_nodes, int64_t n_edges,
+                                          int hidden, int heads, int dtype, void *stream) {
+    int rc = check_shape(n_nodes, n_edges, hidden, heads, 0.f);
+    if (rc != ALIGNN_OK) return rc;
+    int lanes = 0, lph = 0;
+    if (!fast_shape(hidden, heads, &lanes, &lph) || lanes != 32) return ALIGNN_ERR_BAD_SHAPE;
+    if (dtype != ALIGNN_BF16) return ALIGNN_ERR_BAD_DTYPE;
+    if (n_nodes == 0) return ALIGNN_OK;
+    if (!dagg_lp || !q || !rowptr_t || !dk || !dv || (n_edges > 0 && (!coef || !col_t || !eid_t))) return ALIGNN_ERR_BAD_ARG;
+    if (!aligned16(dagg_lp) || !aligned16(q) || !aligned16(dk) || !aligned16(dv) || (ldq % 8) || (ldd % 8)) return ALIGNN_ERR_BAD_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    conv_bwd_src_kernel<__nv_bfloat16, 32, __nv_bfloat16><<<fast_grid(n_nodes, 32), CONV_THREADS, 0, st>>>(
+        (const __nv_bfloat16 *)dagg_lp, (const __nv_bfloat16 *)q, coef, rowptr_t, col_t, eid_t, (__nv_bfloat16 *)dk,
+        (__nv_bfloat16 *)dv, n_nodes, hidden, heads, lph, ldq, ldd);
+    ALIGNN_LAUNCH_CHECK();
+    return ALIGNN_OK;
 }
 
 // source-sorted pass on strided operands (q, dk, dv are column slices of [N, 4H] projection buffers)

@@ -131,7 +131,7 @@ gate_ln_fwd_kernel(const float *__restrict__ agg, const T *__restrict__ xr, cons
 }
 
 template <typename T, int LANES>
-__global__ void __launch_bounds__(EPI_THREADS)
+__global__ void __launch_bounds__(EPI_THREADS, 2)
 gate_ln_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ agg, const T *__restrict__ xr,
                    const float *__restrict__ wbeta, const float *__restrict__ gamma,
                    const float *__restrict__ bias, const float *__restrict__ beta_in,
@@ -258,13 +258,24 @@ gate_ln_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ agg, 
     }
 }
 
-__global__ void reduce_partials_kernel(const float *__restrict__ partials, float *__restrict__ out, int n_blocks,
-                                       int width) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= width) return;
+// out[i] = sum_b partials[b * width + i]: 8 threads per column stride the blocks, then a fixed-order fold (deterministic)
+constexpr int RP_COLS = 32, RP_ROWS = 8;
+__global__ void __launch_bounds__(RP_COLS * RP_ROWS)
+reduce_partials_kernel(const float *__restrict__ partials, float *__restrict__ out, int n_blocks, int width) {
+    __shared__ float red[RP_ROWS][RP_COLS];
+    const int tx = threadIdx.x % RP_COLS, ty = threadIdx.x / RP_COLS;
+    const int i = blockIdx.x * RP_COLS + tx;
     float s = 0.f;
-    for (int b = 0; b < n_blocks; ++b) s += partials[(int64_t)b * width + i];
-    out[i] = s;
+    if (i < width)
+        for (int b = ty; b < n_blocks; b += RP_ROWS) s += partials[(int64_t)b * width + i];
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && i < width) {
+        float t = 0.f;
+#pragma unroll
+        for (int r = 0; r < RP_ROWS; ++r) t += red[r][tx];
+        out[i] = t;
+    }
 }
 
 // ---- generic (any hidden): one warp per row, lanes stride channels -----------------------------------
@@ -478,7 +489,7 @@ static int dispatch_epi_bwd(const float *dy, const float *agg, const void *xr, c
 #undef EPI_BWD
     ALIGNN_LAUNCH_CHECK();
     const int width = (X.dcvec ? 6 : 5) * hidden;
-    reduce_partials_kernel<<<(width + 255) / 256, 256, 0, st>>>(partials, dparams, EPI_PARTIAL_BLOCKS, width);
+    reduce_partials_kernel<<<(width + RP_COLS - 1) / RP_COLS, RP_COLS * RP_ROWS, 0, st>>>(partials, dparams, EPI_PARTIAL_BLOCKS, width);
     ALIGNN_LAUNCH_CHECK();
     return ALIGNN_OK;
 }
@@ -670,7 +681,7 @@ extern "C" int alignn_colsum(const void *x, int64_t ld, int64_t n_rows, int widt
     else
         return ALIGNN_ERR_BAD_DTYPE;
     ALIGNN_LAUNCH_CHECK();
-    reduce_partials_kernel<<<(width + 255) / 256, 256, 0, st>>>(partials, out, CS_BLOCKS, width);
+    reduce_partials_kernel<<<(width + RP_COLS - 1) / RP_COLS, RP_COLS * RP_ROWS, 0, st>>>(partials, out, CS_BLOCKS, width);
     ALIGNN_LAUNCH_CHECK();
     return ALIGNN_OK;
 }

@@ -451,10 +451,10 @@ def raw_attn_bwd_s(dagg: Tensor, dagg_lp: Tensor, agg: Tensor, q: Tensor, k: Ten
                 float(p_drop), seed, offset, _p(rng_step), _stream())
         _lib.check(rc, "alignn_edgeattn_mma_bwd_dst_s")
         with _Launch("edgeattn_bwd_src", 1, (n_nodes, n_edges, hidden, heads, q.element_size())):
-            rc = lib.alignn_edgeattn_bwd_src(_p(dagg), _p(q), _ld(q), _p(coef), _p(plan.rowptr_t), _p(plan.col_t),
-                                             _p(plan.eid_t), _p(dk), _p(dv), _ld(dk), n_nodes, n_edges, hidden, heads,
-                                             _dtype_code(q), _stream())
-        _lib.check(rc, "alignn_edgeattn_bwd_src")
+            rc = lib.alignn_edgeattn_bwd_src_lp(_p(dagg_lp), _p(q), _ld(q), _p(coef), _p(plan.rowptr_t), _p(plan.col_t),
+                                                _p(plan.eid_t), _p(dk), _p(dv), _ld(dk), n_nodes, n_edges, hidden, heads,
+                                                _dtype_code(q), _stream())
+        _lib.check(rc, "alignn_edgeattn_bwd_src_lp")
 
 
 def pack_angles(a: Tensor, plan: GraphPlan) -> Tensor:
@@ -526,10 +526,10 @@ def raw_lgattn_bwd(dagg: Tensor, dagg_lp: Tensor, agg: Tensor, q: Tensor, k: Ten
                 heads, _dtype_code(q), float(p_drop), seed, offset, _p(rng_step), _stream())
         _lib.check(rc, "alignn_lgattn_bwd_dst")
         with _Launch("edgeattn_bwd_src", 1, (n_nodes, n_edges, hidden, heads, q.element_size())):
-            rc = lib.alignn_edgeattn_bwd_src(_p(dagg), _p(q), _ld(q), _p(coef), _p(plan.rowptr_t), _p(plan.col_t),
-                                             _p(pos_t), _p(dk), _p(dv), _ld(dk), n_nodes, n_edges, hidden, heads,
-                                             _dtype_code(q), _stream())
-        _lib.check(rc, "alignn_edgeattn_bwd_src")
+            rc = lib.alignn_edgeattn_bwd_src_lp(_p(dagg_lp), _p(q), _ld(q), _p(coef), _p(plan.rowptr_t), _p(plan.col_t),
+                                                _p(pos_t), _p(dk), _p(dv), _ld(dk), n_nodes, n_edges, hidden, heads,
+                                                _dtype_code(q), _stream())
+        _lib.check(rc, "alignn_edgeattn_bwd_src_lp")
     return coef
 
 

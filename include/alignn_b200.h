@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define ALIGNN_ABI_VERSION 10
+#define ALIGNN_ABI_VERSION 11
 
 #define ALIGNN_F32 0
 #define ALIGNN_BF16 1
@@ -167,6 +167,12 @@ int alignn_edgeattn_bwd_src(const float *dagg, const void *q, int64_t ldq, const
                             const int32_t *rowptr_t, const int32_t *col_t, const int32_t *eid_t,
                             void *dk, void *dv, int64_t ldd, int64_t n_nodes, int64_t n_edges,
                             int hidden, int heads, int dtype, void *stream);
+
+/* alignn_edgeattn_bwd_src with the upstream gradient in storage dtype (bf16 only): one third less gather traffic. */
+int alignn_edgeattn_bwd_src_lp(const void *dagg_lp, const void *q, int64_t ldq, const float *coef,
+                               const int32_t *rowptr_t, const int32_t *col_t, const int32_t *eid_t,
+                               void *dk, void *dv, int64_t ldd, int64_t n_nodes, int64_t n_edges,
+                               int hidden, int heads, int dtype, void *stream);
 
 /* Tensor-core variants of the streaming kernels (hidden = 256, heads = 4, bf16 storage): identical contract to
  * alignn_edgeattn_fwd / _bwd_dst, with the per-edge contractions on mma.sync (chunks of 16 in-edges of one target
