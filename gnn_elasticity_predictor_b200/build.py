@@ -44,8 +44,8 @@ def _digest() -> str:
     files = sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh"))
     files.append(os.path.join(PKG_DIR, "..", "include", "alignn_b200.h"))
     for f in files:
-        with open(f, "rb") as fh:
-            h.update(f.encode() + b"\0" + fh.read())
+        with open(f, "rb") as fh:       # keyed by file NAME, not path: the snapshot lives elsewhere on the GPU box
+            h.update(os.path.basename(f).encode() + b"\0" + fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
 
@@ -63,6 +63,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     nvcc = _nvcc()
     os.makedirs(BUILD_DIR, exist_ok=True)
+    # one builder at a time (torchrun starts one process per GPU); the others wait and then find a current library
+    import fcntl
+    lock = open(os.path.join(BUILD_DIR, ".lock"), "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if not force and is_current():
+            return LIB_PATH
+        return _build_locked(nvcc, verbose)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(nvcc: str, verbose: bool) -> str:
 
     def compile_one(src: str) -> str:
         obj = os.path.join(BUILD_DIR, os.path.basename(src)[:-3] + ".o")
@@ -79,10 +93,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, len(sources()))) as pool:
         objs = list(pool.map(compile_one, sources()))
-    link = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    tmp = LIB_PATH + f".tmp{os.getpid()}"
+    link = [nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    os.replace(tmp, LIB_PATH)           # atomic: a concurrent loader never maps a half-written file
     with open(STAMP, "w") as fh:
         fh.write(_digest())
     return LIB_PATH
