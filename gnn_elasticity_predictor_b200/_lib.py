@@ -73,7 +73,9 @@ SIGNATURES = {
                                     c_int64, c_int, c_int, c_float, c_float, c_uint64, c_uint64, _P, _P]),
     "alignn_gate_ln_bwd2": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P, _P,
                                     c_int64, c_int, c_int, c_float, c_uint64, c_uint64, _P, _P]),
-    "alignn_gate_ln_bwd3": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, c_int64, _P, _P,
+    "alignn_gate_ln_fwd3": (c_int, [_P, _P, _P, _P, c_int, c_int64, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                    c_int64, c_int, c_int, c_float, c_float, c_uint64, c_uint64, _P, _P]),
+    "alignn_gate_ln_bwd3": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, c_int, c_int64, _P, _P, _P, c_int64, _P, _P,
                                     c_int64, c_int, c_int, c_float, c_uint64, c_uint64, _P, _P]),
     "alignn_colsum_supported": (c_int, [c_int]),
     "alignn_colsum_partial_floats": (c_int64, [c_int]),
@@ -86,7 +88,7 @@ SIGNATURES = {
     "alignn_segment_mean_bwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P]),
 }
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 F32, BF16 = 0, 1
 
 

@@ -41,6 +41,7 @@ struct GateExtra {
     void *dagg_lp;         // backward: storage-dtype copy of dagg (may be null)
     const void *dy2;       // backward: second upstream-gradient addend in storage dtype (may be null)
     int64_t lddy2;
+    int64_t agg_rows;      // rows >= agg_rows have no aggregate (agg = 0, nothing read or written for it); < 0: all rows
     bool dcvec;            // backward: also reduce dc = sum_rows dagg * S (needs stat_s, heads) -> 6 parameter vectors
     int heads;
     int64_t ldxr, lddxr;   // row strides (elements) of xr and dxr
@@ -65,13 +66,15 @@ gate_ln_fwd_kernel(const float *__restrict__ agg, const T *__restrict__ xr, cons
     F8 af, sf, xf;
 #pragma unroll
     for (int c = 0; c < 8; ++c) af.v[c] = sf.v[c] = xf.v[c] = 0.f;
+    const int64_t agg_rows = X.agg_rows < 0 ? n_rows : X.agg_rows;
+    const bool has_agg = row < agg_rows;
     if (ok) {
-        af = ld8(agg + row * hidden + ch);
+        if (has_agg) af = ld8(agg + row * hidden + ch);
         sf = ld8(xr + row * X.ldxr + ch);
         xf = ld8(x + row * hidden + ch);
-        if (X.agge) {   // agg = aggv + (Wc[t] abar_t)  [HEADS, rows, C]  + c_t * S_t
+        if (X.agge && has_agg) {   // agg = aggv + (Wc[t] abar_t)  [HEADS, agg_rows, C]  + c_t * S_t
             const int C = hidden / X.heads, t = ch / C;
-            const F8 ef = ld8(reinterpret_cast<const T *>(X.agge) + ((int64_t)t * n_rows + row) * C + (ch - t * C));
+            const F8 ef = ld8(reinterpret_cast<const T *>(X.agge) + ((int64_t)t * agg_rows + row) * C + (ch - t * C));
             float sv = 0.f;
             F8 cf;
 #pragma unroll
@@ -83,7 +86,7 @@ gate_ln_fwd_kernel(const float *__restrict__ agg, const T *__restrict__ xr, cons
 #pragma unroll
             for (int c = 0; c < 8; ++c) af.v[c] += ef.v[c] + cf.v[c] * sv;
         }
-        if (X.agg_out) st8(X.agg_out + row * hidden + ch, af);
+        if (X.agg_out && has_agg) st8(X.agg_out + row * hidden + ch, af);
     }
     const F8 w1 = ld8(wbeta + ch), w2 = ld8(wbeta + hidden + ch), w3 = ld8(wbeta + 2 * hidden + ch);
     float zp = 0.f;
@@ -171,7 +174,7 @@ gate_ln_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ agg, 
 #pragma unroll
                 for (int c = 0; c < 8; ++c) gf.v[c] += g2.v[c];
             }
-            af = ld8(agg + row * hidden + ch);
+            if (X.agg_rows < 0 || row < X.agg_rows) af = ld8(agg + row * hidden + ch);
             sf = ld8(xr + row * X.ldxr + ch);
             beta = __ldg(beta_in + row);
             mean = __ldg(mean_in + row);
@@ -209,7 +212,8 @@ gate_ln_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ agg, 
         const float dz = dbeta * beta * (1.0f - beta);
         if (ok) {
             F8 da, ds;
-            const float srow = X.dcvec ? __ldg(X.stat_s + row * X.heads + head) : 0.f;
+            const bool has_agg = X.agg_rows < 0 || row < X.agg_rows;
+            const float srow = X.dcvec && has_agg ? __ldg(X.stat_s + row * X.heads + head) : 0.f;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 da.v[c] = (1.0f - beta) * dof.v[c] + dz * (w1.v[c] + w3.v[c]);
@@ -219,8 +223,10 @@ gate_ln_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ agg, 
                 a3.v[c] = fmaf(dz, af.v[c] - sf.v[c], a3.v[c]);
                 ac.v[c] = fmaf(da.v[c], srow, ac.v[c]);
             }
-            st8(dagg + row * hidden + ch, da);
-            if (X.dagg_lp) st8(reinterpret_cast<T *>(X.dagg_lp) + row * hidden + ch, da);
+            if (has_agg) {
+                st8(dagg + row * hidden + ch, da);
+                if (X.dagg_lp) st8(reinterpret_cast<T *>(X.dagg_lp) + row * hidden + ch, da);
+            }
             st8(dxr + row * X.lddxr + ch, ds);
         }
     }
@@ -502,7 +508,7 @@ extern "C" int64_t alignn_gate_ln_bwd_partial_rows(void) { return EPI_PARTIAL_BL
 
 static GateExtra plain_extra(int hidden) {
     GateExtra X;
-    X.agge = nullptr; X.cvec = nullptr; X.stat_s = nullptr; X.agg_out = nullptr; X.dagg_lp = nullptr; X.dcvec = false; X.dy2 = nullptr; X.lddy2 = hidden;
+    X.agge = nullptr; X.cvec = nullptr; X.stat_s = nullptr; X.agg_out = nullptr; X.dagg_lp = nullptr; X.dcvec = false; X.dy2 = nullptr; X.lddy2 = hidden; X.agg_rows = -1;
     X.heads = 1; X.ldxr = hidden; X.lddxr = hidden; X.rng_step = nullptr;
     return X;
 }
@@ -588,16 +594,32 @@ extern "C" int alignn_gate_ln_bwd(const float *dy, const float *agg, const void 
                             hidden, dtype, p_drop, seed, offset, plain_extra(hidden), false, stream);
 }
 
+extern "C" int alignn_gate_ln_fwd3(const float *aggv, const void *agge, const float *cvec, const float *stat_s,
+                                   int heads, int64_t agg_rows, const void *xr, int64_t ldxr, const float *x,
+                                   const float *wbeta, const float *gamma, const float *bias,
+                                   float *agg_out, float *y, void *y_lp, float *beta, float *mean, float *rstd,
+                                   int64_t n_rows, int hidden, int dtype, float eps,
+                                   float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step, void *stream) {
+    GateExtra X = plain_extra(hidden);
+    X.agge = agge; X.cvec = cvec; X.stat_s = stat_s; X.agg_out = agg_out; X.heads = heads; X.ldxr = ldxr;
+    X.rng_step = rng_step;
+    X.agg_rows = (agg_rows < 0 || agg_rows > n_rows) ? -1 : agg_rows;
+    if (hidden % 8 || hidden > 256 || (256 % hidden)) return ALIGNN_ERR_BAD_SHAPE;   // fast mapping only
+    return gate_ln_fwd_impl(aggv, xr, x, wbeta, gamma, bias, y, y_lp, beta, mean, rstd, n_rows, hidden, dtype, eps,
+                            p_drop, seed, offset, X, true, stream);
+}
+
 extern "C" int alignn_gate_ln_bwd3(const float *dy, const void *dy2, int64_t lddy2, const float *agg, const void *xr, int64_t ldxr,
                                    const float *wbeta, const float *gamma, const float *bias,
                                    const float *beta, const float *mean, const float *rstd,
-                                   const float *stat_s, int heads,
+                                   const float *stat_s, int heads, int64_t agg_rows,
                                    float *dagg, void *dagg_lp, void *dxr, int64_t lddxr, float *partials, float *dparams,
                                    int64_t n_rows, int hidden, int dtype,
                                    float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step, void *stream) {
     GateExtra X = plain_extra(hidden);
     X.dagg_lp = dagg_lp; X.ldxr = ldxr; X.lddxr = lddxr; X.rng_step = rng_step;
     X.stat_s = stat_s; X.heads = heads; X.dcvec = true; X.dy2 = dy2; X.lddy2 = lddy2;
+    X.agg_rows = (agg_rows < 0 || agg_rows > n_rows) ? -1 : agg_rows;
     if ((!dy && !dy2) || (dy2 && (lddy2 % 8 || !aligned16(dy2)))) return ALIGNN_ERR_BAD_ARG;
     if (!stat_s || heads <= 0 || hidden % heads || (hidden / heads) % 8) return ALIGNN_ERR_BAD_ARG;
     if (hidden % 8 || hidden > 256 || (256 % hidden)) return ALIGNN_ERR_BAD_SHAPE;   // fast mapping only

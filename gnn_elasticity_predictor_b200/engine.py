@@ -152,12 +152,12 @@ class TrainStep:
     # -- capture ---------------------------------------------------------------------------------------------------
     @staticmethod
     def signature(batch) -> Tuple:
-        return tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(batch.tensors().items())) + (batch.num_graphs,)
+        return tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(batch.tensors().items())) + (
+            batch.num_graphs, getattr(batch, "lg_active_rows", None))
 
     def _capture(self, batch: GraphBatch, tz: Tensor) -> _Captured:
         cap = _Captured()
-        cap.batch = GraphBatch.__new__(GraphBatch)
-        cap.batch.num_graphs, cap.batch.lg_inc = batch.num_graphs, batch.lg_inc
+        cap.batch = batch._like()
         for k in GraphBatch._TENSORS:
             v = getattr(batch, k)
             setattr(cap.batch, k, v.clone() if isinstance(v, Tensor) else v)

@@ -374,7 +374,10 @@ class AlignnRegressor(nn.Module):
                     h1 = torch.zeros(n_angles, self.hidden, device=dev, dtype=cd)
             if lg is not None and run_atoms and getattr(self, "fused_trunk", True) and \
                     len(self.edge_blocks) == len(self.node_blocks):
-                node32 = self._run_fused_trunk(node32, node_b0, edge32, edge_b0, lg, lg_plan, g_plan, w2, b2)
+                lg_active = getattr(data, "lg_active_rows", None)
+                node32 = self._run_fused_trunk(node32, node_b0, edge32, edge_b0, lg, lg_plan, g_plan, w2, b2,
+                                               -1 if lg_active is None or not getattr(self, "elide_isolated", True)
+                                               else int(lg_active))
                 return self._head_features(node32, data, pool_plan)
             accum = FeatGradAccumulator(n_layers) if run_lg and lg is None else None
 
@@ -410,7 +413,7 @@ class AlignnRegressor(nn.Module):
             return self._head_features(node32, data, pool_plan)
 
     def _run_fused_trunk(self, node32: Tensor, node_b: Tensor, edge32: Tensor, edge_b: Tensor, lg: LgShared,
-                         lg_plan: GraphPlan, g_plan: GraphPlan, w2: Tensor, b2: Tensor) -> Tensor:
+                         lg_plan: GraphPlan, g_plan: GraphPlan, w2: Tensor, b2: Tensor, lg_active: int = -1) -> Tensor:
         """All blocks as one explicit forward / backward program (``trunk.py``).  The weight folds of every block are
         batched here under autograd: ``Wc = W_e W2`` (line graph, second angle-encoder Linear folded into ``lin_edge``),
         ``Wc = W_e W_p`` (atom graph, ``edge_proj`` folded), and the query-side fold ``Wc[t]^T Wq_t`` that turns
@@ -436,8 +439,8 @@ class AlignnRegressor(nn.Module):
         wc3 = wc.view(2 * nl * h, c, hid)
         wqt = torch.bmm(wc3.transpose(1, 2), wq.view(2 * nl * h, c, hid)).view(2 * nl, h * hid, hid)
         bqt = torch.bmm(bq.view(2 * nl * h, 1, c), wc3).view(2 * nl, h * hid)
-        w8 = torch.cat(w4 + [wqt], dim=1)                                                    # [2L, 8H, H]
-        b8 = torch.cat(b4 + [bqt], dim=1)                                                    # [2L, 8H]
+        w8 = torch.cat(w4[:3] + [wqt, w4[3]], dim=1)                  # [2L, 8H, H]: q | k | v | qt_0..3 | x_r
+        b8 = torch.cat(b4[:3] + [bqt, b4[3]], dim=1)                  # [2L, 8H]
         wbeta = f([cv.lin_beta.weight.reshape(-1) for cv in convs])
         gamma, beta_ln = f([b.norm.weight for b in blocks]), f([b.norm.bias for b in blocks])
         train = self.training
@@ -449,7 +452,8 @@ class AlignnRegressor(nn.Module):
             so, oo = ops.next_dropout_key() if po > 0.0 else (0, 0)
             keys.append((sa, oa, so, oo))
         cfg = trunk_mod.TrunkCfg(heads=h, n_layers=nl, eps=[b.norm.eps for b in blocks], p_attn=p_attn, p_out=p_out,
-                                 keys=keys, lg_plan=lg_plan, g_plan=g_plan, a_csr=lg.a_csr, w1=lg.w1, b1=lg.b1)
+                                 keys=keys, lg_plan=lg_plan, g_plan=g_plan, a_csr=lg.a_csr, w1=lg.w1, b1=lg.b1,
+                                 lg_active=lg_active)
         enc = self.angle_encoder
         return trunk_mod.run_trunk(node32, node_b, edge32, edge_b, w8, b8, wc, cvec, wbeta, gamma, beta_ln,
                                    enc[0].weight, enc[0].bias, cfg)

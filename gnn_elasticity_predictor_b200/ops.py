@@ -597,9 +597,11 @@ def raw_edgeattn_bwd(dagg: Tensor, dagg_lp: Optional[Tensor], agg: Tensor, q: Te
 
 def raw_gate_ln_fwd2(aggv: Tensor, agge: Optional[Tensor], cvec: Optional[Tensor], stat_s: Optional[Tensor],
                      heads: int, xr: Tensor, x: Tensor, wbeta: Tensor, gamma: Tensor, bias: Tensor, eps: float,
-                     p_drop: float, seed: int, offset: int, want_lp: bool, rng_step: Optional[Tensor] = None):
+                     p_drop: float, seed: int, offset: int, want_lp: bool, rng_step: Optional[Tensor] = None,
+                     agg_rows: int = -1):
+    """``agg_rows >= 0``: only the first ``agg_rows`` rows have an aggregate (``agge`` is ``[heads, agg_rows, C]``)."""
     lib = _lib.load()
-    n_rows, hidden = aggv.shape
+    n_rows, hidden = x.shape
     dev = aggv.device
     f32 = dict(dtype=torch.float32, device=dev)
     agg = torch.empty(n_rows, hidden, **f32)
@@ -607,11 +609,17 @@ def raw_gate_ln_fwd2(aggv: Tensor, agge: Optional[Tensor], cvec: Optional[Tensor
     y_lp = torch.empty(n_rows, hidden, dtype=xr.dtype, device=dev) if want_lp else None
     beta, mean, rstd = (torch.empty(n_rows, **f32) for _ in range(3))
     with torch.cuda.device(dev), _Launch("gate_ln_fwd", 1, (n_rows, hidden, xr.element_size())):
-        rc = lib.alignn_gate_ln_fwd2(_p(aggv), _p(agge), _p(cvec), _p(stat_s), heads, _p(xr), _ld(xr), _p(x), _p(wbeta),
-                                     _p(gamma), _p(bias), _p(agg), _p(y), _p(y_lp), _p(beta), _p(mean), _p(rstd),
-                                     n_rows, hidden, _dtype_code(xr), float(eps), float(p_drop), seed, offset,
-                                     _p(rng_step), _stream())
-    _lib.check(rc, "alignn_gate_ln_fwd2")
+        if agg_rows >= 0:
+            rc = lib.alignn_gate_ln_fwd3(_p(aggv), _p(agge), _p(cvec), _p(stat_s), heads, int(agg_rows), _p(xr), _ld(xr),
+                                         _p(x), _p(wbeta), _p(gamma), _p(bias), _p(agg), _p(y), _p(y_lp), _p(beta),
+                                         _p(mean), _p(rstd), n_rows, hidden, _dtype_code(xr), float(eps), float(p_drop),
+                                         seed, offset, _p(rng_step), _stream())
+        else:
+            rc = lib.alignn_gate_ln_fwd2(_p(aggv), _p(agge), _p(cvec), _p(stat_s), heads, _p(xr), _ld(xr), _p(x),
+                                         _p(wbeta), _p(gamma), _p(bias), _p(agg), _p(y), _p(y_lp), _p(beta), _p(mean),
+                                         _p(rstd), n_rows, hidden, _dtype_code(xr), float(eps), float(p_drop), seed,
+                                         offset, _p(rng_step), _stream())
+    _lib.check(rc, "alignn_gate_ln_fwd2/3")
     return y, y_lp, agg, beta, mean, rstd
 
 
@@ -638,7 +646,7 @@ def raw_gate_ln_bwd2(dy: Tensor, agg: Tensor, xr: Tensor, wbeta: Tensor, gamma: 
 
 def raw_gate_ln_bwd3(dy: Optional[Tensor], agg: Tensor, xr: Tensor, wbeta: Tensor, gamma: Tensor, bias: Tensor, beta: Tensor,
                      mean: Tensor, rstd: Tensor, stat_s: Tensor, heads: int, dxr: Tensor, p_drop: float, seed: int,
-                     offset: int, rng_step: Optional[Tensor] = None, dy2: Optional[Tensor] = None):
+                     offset: int, rng_step: Optional[Tensor] = None, dy2: Optional[Tensor] = None, agg_rows: int = -1):
     """As :func:`raw_gate_ln_bwd2` (always emits the storage-dtype copy of dagg) plus the gradient of the folded
     edge-projection bias: returns (dagg f32, dagg_lp, dparams f32 [6*hidden] = dw_beta x3 | dgamma | dbias | dcvec)."""
     lib = _lib.load()
@@ -651,7 +659,8 @@ def raw_gate_ln_bwd3(dy: Optional[Tensor], agg: Tensor, xr: Tensor, wbeta: Tenso
     dparams = torch.empty(6 * hidden, **f32)
     with torch.cuda.device(dev), _Launch("gate_ln_bwd", 2, (n_rows, hidden, xr.element_size())):
         rc = lib.alignn_gate_ln_bwd3(_p(dy), _p(dy2), _ld(dy2) if dy2 is not None else hidden, _p(agg), _p(xr), _ld(xr), _p(wbeta), _p(gamma), _p(bias), _p(beta),
-                                     _p(mean), _p(rstd), _p(stat_s), heads, _p(dagg), _p(dagg_lp), _p(dxr), _ld(dxr),
+                                     _p(mean), _p(rstd), _p(stat_s), heads, int(agg_rows), _p(dagg), _p(dagg_lp), _p(dxr),
+                                     _ld(dxr),
                                      _p(partials), _p(dparams), n_rows, hidden, _dtype_code(xr), float(p_drop), seed,
                                      offset, _p(rng_step), _stream())
     _lib.check(rc, "alignn_gate_ln_bwd3")

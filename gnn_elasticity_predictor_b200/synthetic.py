@@ -64,18 +64,26 @@ class GraphBatch:
             setattr(self, k, kw.pop(k, None))
         if kw:
             raise TypeError(f"unexpected fields {sorted(kw)}")
+        # host-side fact known at collate time: bond rows >= this bound have no line-graph neighbours (with PyG's
+        # default collate the reference offsets lg_edge_index by atoms, so for B > 1 most bond rows are isolated)
+        lg = self.lg_edge_index
+        self.lg_active_rows = (int(lg.max()) + 1 if lg.numel() > 0 else 0) if isinstance(lg, Tensor) and not lg.is_cuda \
+            else None
+
+    def _like(self) -> "GraphBatch":
+        out = GraphBatch.__new__(GraphBatch)
+        out.num_graphs, out.lg_inc, out.lg_active_rows = self.num_graphs, self.lg_inc, self.lg_active_rows
+        return out
 
     def to(self, device, non_blocking: bool = False) -> "GraphBatch":
-        out = GraphBatch.__new__(GraphBatch)
-        out.num_graphs, out.lg_inc = self.num_graphs, self.lg_inc
+        out = self._like()
         for k in self._TENSORS:
             v = getattr(self, k)
             setattr(out, k, v.to(device, non_blocking=non_blocking) if isinstance(v, Tensor) else v)
         return out
 
     def pin_memory(self) -> "GraphBatch":
-        out = GraphBatch.__new__(GraphBatch)
-        out.num_graphs, out.lg_inc = self.num_graphs, self.lg_inc
+        out = self._like()
         for k in self._TENSORS:
             v = getattr(self, k)
             setattr(out, k, v.pin_memory() if isinstance(v, Tensor) else v)

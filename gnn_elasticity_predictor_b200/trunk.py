@@ -18,6 +18,14 @@ so the gradient sum is folded into a GEMM that runs anyway (an identity block ap
 of size [E, H] is added, copied or converted on its own, and the angle-encoder gradient is formed once at the end from
 all layers' coefficients.  Parameters arrive STACKED over blocks (index 2l = EdgeUpdateBlock_l, 2l+1 =
 NodeUpdateBlock_l) so that the weight folds of all blocks are a handful of batched [H, H] products (``modules.py``).
+
+Column layout of the stacked projection: ``q | k | v | qt_0..3 | x_r`` (x_r last, next to the df columns of the gradient
+buffer).  ISOLATED bond rows: with PyG's default collate the reference offsets ``lg_edge_index`` by atoms,
+so in a batch of B > 1 crystals only the first ``lg_active`` bond rows have line-graph neighbours at all -- 8 544 of
+98 304 at BASELINE config 2.  For the rows beyond that bound a block is just ``x + drop(relu(LN(beta x_r)))``: only the
+``x_r`` slice of the projection (and of every gradient GEMM) is computed for them, and the attention kernels, the
+``abar`` products and the column sums run on the active prefix only.  The bound is a host integer the batch carries
+(``GraphBatch.lg_active_rows``, the largest line-graph index + 1, known at collate time); without it all rows are active.
 """
 from __future__ import annotations
 
@@ -45,6 +53,7 @@ class TrunkCfg:
     w1: Tensor = None                    # fp32 [H, angle_dim], detached, contiguous
     b1: Tensor = None
     want_node_lp: bool = False
+    lg_active: int = -1                  # bond rows >= lg_active are isolated in the line graph (< 0: unknown, all active)
 
 
 def _block_forward(idx: int, is_lg: bool, x32: Tensor, xb: Tensor, feat: Optional[Tensor], w8c: Tensor, b8c: Tensor,
@@ -53,20 +62,27 @@ def _block_forward(idx: int, is_lg: bool, x32: Tensor, xb: Tensor, feat: Optiona
     h = cfg.heads
     n, hid = x32.shape
     sa, oa, so, oo = cfg.keys[idx]
-    proj = torch.addmm(b8c, xb, w8c.t())                                      # [n, 8H]: q | k | v | x_r | qt_0..3
-    q, k, v, xr = (proj[:, i * hid:(i + 1) * hid] for i in range(4))
-    qt = proj[:, 4 * hid:].unflatten(1, (h, hid)).transpose(0, 1)             # [h, n, H] view, row stride 8H
-    abar_rows = torch.empty(n, h, hid, dtype=xb.dtype, device=xb.device)      # row-interleaved: [n, 4H] for the dWc GEMM
-    abar = abar_rows.transpose(0, 1)                                          # [h, n, H] view
+    na = cfg.lg_active if (is_lg and 0 <= cfg.lg_active < n) else n            # active prefix
+    # [n, 8H]: q | k | v | qt_0..3 | x_r.  Two GEMMs with the same shapes whether or not rows are elided (x_r over all rows,
+    # the other seven slices over the active prefix), so elision changes no rounding anywhere.
+    proj = torch.empty(n, 8 * hid, dtype=xb.dtype, device=xb.device)
+    torch.addmm(b8c[7 * hid:], xb, w8c[7 * hid:].t(), out=proj[:, 7 * hid:])
+    torch.addmm(b8c[:7 * hid], xb[:na], w8c[:7 * hid].t(), out=proj[:na, :7 * hid])
+    q, k, v = (proj[:na, i * hid:(i + 1) * hid] for i in range(3))
+    xr = proj[:, 7 * hid:]
+    qt = proj[:na, 3 * hid:7 * hid].unflatten(1, (h, hid)).transpose(0, 1)    # [h, na, H] view, row stride 8H
+    abar_rows = torch.empty(na, h, hid, dtype=xb.dtype, device=xb.device)     # row-interleaved: [na, 4H] for the dWc GEMM
+    abar = abar_rows.transpose(0, 1)                                          # [h, na, H] view
     if is_lg:
         aggv, _, m, z, s = ops.raw_lgattn_fwd(q, k, v, qt, cfg.a_csr, cfg.w1, cfg.b1, cfg.lg_plan, h, cfg.p_attn[idx],
                                               sa, oa, rs, abar=abar)
     else:
         aggv, _, m, z, s = ops.raw_attn_fwd_s(q, k, v, qt, feat, cfg.g_plan, h, cfg.p_attn[idx], sa, oa, rs, abar=abar)
-    agge = torch.bmm(abar, wc3.transpose(1, 2))                               # [h, n, C]
+    agge = torch.bmm(abar, wc3.transpose(1, 2))                               # [h, na, C]
     y, y_lp, agg, beta, mean, rstd = ops.raw_gate_ln_fwd2(aggv, agge, cv, s, h, xr, x32, wb, gm, bl, cfg.eps[idx],
-                                                          cfg.p_out[idx], so, oo, want_lp, rs)
-    st = dict(xb=xb, feat=feat, proj=proj, abar_rows=abar_rows, agg=agg, m=m, z=z, s=s, beta=beta, mean=mean, rstd=rstd)
+                                                          cfg.p_out[idx], so, oo, want_lp, rs, agg_rows=na)
+    st = dict(xb=xb, feat=feat, proj=proj, abar_rows=abar_rows, agg=agg, m=m, z=z, s=s, beta=beta, mean=mean, rstd=rstd,
+              na=na)
     return y, y_lp, st
 
 
@@ -131,18 +147,22 @@ class _Trunk(torch.autograd.Function):
                            df_out: Optional[Tensor]) -> Tensor:
             st = saved[idx]
             sa, oa, so, oo = cfg.keys[idx]
-            proj, xb, agg, s = st["proj"], st["xb"], st["agg"], st["s"]
-            q, k, v, xr = (proj[:, i * hid:(i + 1) * hid] for i in range(4))
-            qt = proj[:, 4 * hid:].unflatten(1, (h, hid)).transpose(0, 1)
+            proj, xb, agg, s, na = st["proj"], st["xb"], st["agg"], st["s"], st["na"]
+            n = proj.size(0)
+            q, k, v = (proj[:na, i * hid:(i + 1) * hid] for i in range(3))
+            xr = proj[:, 7 * hid:]
+            qt = proj[:na, 3 * hid:7 * hid].unflatten(1, (h, hid)).transpose(0, 1)
             dproj = dbuf[:, :8 * hid]
-            dq, dk, dv, dxr = (dproj[:, i * hid:(i + 1) * hid] for i in range(4))
-            bbar = dproj[:, 4 * hid:].unflatten(1, (h, hid)).transpose(0, 1)
+            dq, dk, dv = (dbuf[:na, i * hid:(i + 1) * hid] for i in range(3))
+            dxr = dbuf[:, 7 * hid:8 * hid]
+            bbar = dbuf[:na, 3 * hid:7 * hid].unflatten(1, (h, hid)).transpose(0, 1)
             dagg, dagg_lp, dparams = ops.raw_gate_ln_bwd3(dy, agg, xr, wbf[idx], gmf[idx], blf[idx], st["beta"],
                                                           st["mean"], st["rstd"], s, h, dxr, cfg.p_out[idx], so, oo, rs,
-                                                          dy2=dy2)
+                                                          dy2=dy2, agg_rows=na)
             d_par[idx].copy_(dparams)
-            g3 = dagg_lp.unflatten(1, (h, c)).transpose(0, 1)                 # [h, n, C]
-            gt = torch.bmm(g3, wc3[idx])                                      # [h, n, H]
+            dagg, dagg_lp, agg = dagg[:na], dagg_lp[:na], agg[:na]
+            g3 = dagg_lp.unflatten(1, (h, c)).transpose(0, 1)                 # [h, na, C]
+            gt = torch.bmm(g3, wc3[idx])                                      # [h, na, H]
             if is_lg:
                 coef = ops.raw_lgattn_bwd(dagg, dagg_lp, agg, q, k, v, qt, gt, cvf[idx], cfg.a_csr, cfg.w1, cfg.b1,
                                           st["m"], st["z"], cfg.lg_plan, h, dq, dk, dv, bbar, cfg.p_attn[idx], sa, oa, rs)
@@ -150,16 +170,32 @@ class _Trunk(torch.autograd.Function):
             else:
                 ops.raw_attn_bwd_s(dagg, dagg_lp, agg, q, k, v, qt, gt, cvf[idx], st["feat"], st["m"], st["z"],
                                    cfg.g_plan, h, dq, dk, dv, bbar, df_out, cfg.p_attn[idx], sa, oa, rs)
-            # dWc[t] = dagg_t^T abar_t: diagonal blocks of one dense [H, n] x [n, 4H] product (K = n is what costs)
+            # dWc[t] = dagg_t^T abar_t: diagonal blocks of one dense [H, na] x [na, 4H] product (K = na is what costs)
             gfull = torch.mm(dagg_lp.t(), st["abar_rows"].view(-1, h * hid), out_dtype=torch.float32)   # [H, 4H]
             d_wc[idx].copy_(torch.stack([gfull[t * c:(t + 1) * c, t * hid:(t + 1) * hid] for t in range(h)]).view(hid, hid))
-            wext = w8c[idx] if dbuf.size(1) == 8 * hid else torch.cat([w8c[idx], eye], dim=0)
-            if dy is not None:
-                dx = torch.addmm(dy, dbuf, wext, out_dtype=torch.float32)     # dy (+ df through the identity block)
+            ext = dbuf.size(1) == 9 * hid
+            wext = torch.cat([w8c[idx], eye], dim=0) if ext else w8c[idx]     # [9H | 8H, H]: identity block adds df
+            if na == n:
+                if dy is not None:
+                    dx = torch.addmm(dy, dbuf, wext, out_dtype=torch.float32)
+                else:
+                    dx = torch.mm(dbuf, wext, out_dtype=torch.float32)
+                torch.mm(dproj.t(), xb, out_dtype=torch.float32, out=d_w8[idx])
+                d_b8[idx].copy_(ops.colsum(dproj))
             else:
-                dx = torch.mm(dbuf, wext, out_dtype=torch.float32)
-            torch.mm(dproj.t(), xb, out_dtype=torch.float32, out=d_w8[idx])
-            d_b8[idx].copy_(ops.colsum(dproj))
+                dx = torch.empty(n, hid, **f32)
+                tail, wtail = dbuf[na:, 7 * hid:], wext[7 * hid:]             # isolated rows: dx_r (| df) only
+                if dy is not None:
+                    torch.addmm(dy[:na], dbuf[:na], wext, out_dtype=torch.float32, out=dx[:na])
+                    torch.addmm(dy[na:], tail, wtail, out_dtype=torch.float32, out=dx[na:])
+                else:
+                    torch.mm(dbuf[:na], wext, out_dtype=torch.float32, out=dx[:na])
+                    torch.mm(tail, wtail, out_dtype=torch.float32, out=dx[na:])
+                torch.mm(dproj[:na].t(), xb[:na], out_dtype=torch.float32, out=d_w8[idx])
+                ws_tail = torch.mm(dxr[na:].t(), xb[na:], out_dtype=torch.float32)
+                d_w8[idx, 7 * hid:].add_(ws_tail)
+                d_b8[idx].copy_(ops.colsum(dproj[:na]))
+                d_b8[idx, 7 * hid:].add_(ops.colsum(dxr[na:]))
             st.clear()
             return dx
 

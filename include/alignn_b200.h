@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define ALIGNN_ABI_VERSION 11
+#define ALIGNN_ABI_VERSION 12
 
 #define ALIGNN_F32 0
 #define ALIGNN_BF16 1
@@ -284,6 +284,18 @@ int alignn_gate_ln_bwd2(const float *dy, const float *agg, const void *xr, int64
                         int64_t n_rows, int hidden, int dtype,
                         float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step, void *stream);
 
+/* alignn_gate_ln_fwd2 for batches whose trailing rows are ISOLATED (no in-edges): rows >= agg_rows take agg = 0 without
+ * reading aggv / agge / stat_s (agge is [heads, agg_rows, C]) and agg_out is written for rows < agg_rows only.  With
+ * PyG's default collate the reference offsets lg_edge_index by atoms, so for B > 1 most bond rows of the line graph
+ * are isolated; agg_rows < 0 means all rows.  alignn_gate_ln_bwd3 takes the same bound (dagg / dagg_lp
+ * are written for rows < agg_rows only). */
+int alignn_gate_ln_fwd3(const float *aggv, const void *agge, const float *cvec, const float *stat_s,
+                        int heads, int64_t agg_rows, const void *xr, int64_t ldxr, const float *x,
+                        const float *wbeta, const float *gamma, const float *bias,
+                        float *agg_out, float *y, void *y_lp, float *beta, float *mean, float *rstd,
+                        int64_t n_rows, int hidden, int dtype, float eps,
+                        float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step, void *stream);
+
 /* As alignn_gate_ln_bwd2, plus the gradient of the folded edge-projection bias c: dparams[5*hidden + ch] =
  * sum_rows dagg[row, ch] * stat_s[row, head(ch)] (the `c_t * S_t` term of the aggregate; c = W_e b of the Linear folded
  * into lin_edge, reference train.py:324,333 / :360-364).  partials: [partial_rows * 6 * hidden], dparams: [6 * hidden];
@@ -293,7 +305,7 @@ int alignn_gate_ln_bwd2(const float *dy, const float *agg, const void *xr, int64
 int alignn_gate_ln_bwd3(const float *dy, const void *dy2, int64_t lddy2, const float *agg, const void *xr, int64_t ldxr,
                         const float *wbeta, const float *gamma, const float *bias,
                         const float *beta, const float *mean, const float *rstd,
-                        const float *stat_s, int heads,
+                        const float *stat_s, int heads, int64_t agg_rows,
                         float *dagg, void *dagg_lp, void *dxr, int64_t lddxr, float *partials, float *dparams,
                         int64_t n_rows, int hidden, int dtype,
                         float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step, void *stream);
