@@ -7,12 +7,12 @@ line-graph block (residual stream) AND by the atom-graph block of the same layer
 is scheduled by hand:
 
     for l = L-1 .. 0:
-        NodeUpdateBlock_l backward   -> writes the bond-feature gradient df_l (bf16) into the LAST H columns of the
-                                        [E, 9H] buffer that the line-graph block of the same layer uses for its
-                                        projection gradients
-        EdgeUpdateBlock_l backward   -> gate/LayerNorm backward reads dy = d_edge (fp32, from block l+1) + df_l on load;
-                                        kernels fill columns [0, 8H) with dq | dk | dv | dx_r | bbar_0..3;
-                                        d_edge <- d_edge + [dproj8 | df_l] . [W8 ; I]       (one fp32-accumulating GEMM)
+        NodeUpdateBlock_l backward   -> writes the bond-feature gradient df_l (bf16) into the right half of the [E, 2H]
+                                        buffer whose left half will hold the line-graph block's dx_r
+        EdgeUpdateBlock_l backward   -> gate/LayerNorm backward reads dy = d_edge (fp32, from block l+1) + df_l on load
+                                        and writes dx_r next to df_l; the attention kernels fill dq | dk | dv | bbar_0..3;
+                                        d_edge <- d_edge + [dx_r | df_l] . [Ws ; I] + [dq|dk|dv|bbar] . [Wq;Wk;Wv;WQT]
+                                        (fp32-accumulating GEMMs)
 
 so the gradient sum is folded into a GEMM that runs anyway (an identity block appended to the stacked weights), nothing
 of size [E, H] is added, copied or converted on its own, and the angle-encoder gradient is formed once at the end from
@@ -63,14 +63,13 @@ def _block_forward(idx: int, is_lg: bool, x32: Tensor, xb: Tensor, feat: Optiona
     n, hid = x32.shape
     sa, oa, so, oo = cfg.keys[idx]
     na = cfg.lg_active if (is_lg and 0 <= cfg.lg_active < n) else n            # active prefix
-    # [n, 8H]: q | k | v | qt_0..3 | x_r.  Two GEMMs with the same shapes whether or not rows are elided (x_r over all rows,
-    # the other seven slices over the active prefix), so elision changes no rounding anywhere.
-    proj = torch.empty(n, 8 * hid, dtype=xb.dtype, device=xb.device)
-    torch.addmm(b8c[7 * hid:], xb, w8c[7 * hid:].t(), out=proj[:, 7 * hid:])
-    torch.addmm(b8c[:7 * hid], xb[:na], w8c[:7 * hid].t(), out=proj[:na, :7 * hid])
-    q, k, v = (proj[:na, i * hid:(i + 1) * hid] for i in range(3))
-    xr = proj[:, 7 * hid:]
-    qt = proj[:na, 3 * hid:7 * hid].unflatten(1, (h, hid)).transpose(0, 1)    # [h, na, H] view, row stride 8H
+    # q | k | v | qt_0..3 over the ACTIVE prefix ([na, 7H]) and x_r over all rows ([n, H]): two contiguous GEMM outputs
+    # with the same shapes per row whether or not rows are elided, so elision changes no rounding anywhere.
+    w7, b7, ws, bs = w8c[:7 * hid], b8c[:7 * hid], w8c[7 * hid:], b8c[7 * hid:]
+    xr = torch.addmm(bs, xb, ws.t())                                          # [n, H]
+    proj = torch.addmm(b7, xb[:na], w7.t())                                   # [na, 7H]
+    q, k, v = (proj[:, i * hid:(i + 1) * hid] for i in range(3))
+    qt = proj[:, 3 * hid:].unflatten(1, (h, hid)).transpose(0, 1)             # [h, na, H] view, row stride 7H
     abar_rows = torch.empty(na, h, hid, dtype=xb.dtype, device=xb.device)     # row-interleaved: [na, 4H] for the dWc GEMM
     abar = abar_rows.transpose(0, 1)                                          # [h, na, H] view
     if is_lg:
@@ -81,8 +80,8 @@ def _block_forward(idx: int, is_lg: bool, x32: Tensor, xb: Tensor, feat: Optiona
     agge = torch.bmm(abar, wc3.transpose(1, 2))                               # [h, na, C]
     y, y_lp, agg, beta, mean, rstd = ops.raw_gate_ln_fwd2(aggv, agge, cv, s, h, xr, x32, wb, gm, bl, cfg.eps[idx],
                                                           cfg.p_out[idx], so, oo, want_lp, rs, agg_rows=na)
-    st = dict(xb=xb, feat=feat, proj=proj, abar_rows=abar_rows, agg=agg, m=m, z=z, s=s, beta=beta, mean=mean, rstd=rstd,
-              na=na)
+    st = dict(xb=xb, feat=feat, proj=proj, xr=xr, abar_rows=abar_rows, agg=agg, m=m, z=z, s=s, beta=beta, mean=mean,
+              rstd=rstd, na=na)
     return y, y_lp, st
 
 
@@ -143,19 +142,20 @@ class _Trunk(torch.autograd.Function):
         de: Optional[Tensor] = None                    # fp32 gradient of the bond residual stream (None above the top)
         coefs, qts, gts = [], [], []
 
-        def block_backward(idx: int, is_lg: bool, dy: Optional[Tensor], dy2: Optional[Tensor], dbuf: Tensor,
-                           df_out: Optional[Tensor]) -> Tensor:
+        def block_backward(idx: int, is_lg: bool, dy: Optional[Tensor], dtail: Tensor, df_out: Optional[Tensor]) -> Tensor:
+            """``dtail``: [n, H] (dx_r) or [n, 2H] (dx_r | df from the atom-graph block of the same layer, already written);
+            ``df_out``: where THIS block writes its edge-feature gradient (atom-graph blocks)."""
             st = saved[idx]
             sa, oa, so, oo = cfg.keys[idx]
-            proj, xb, agg, s, na = st["proj"], st["xb"], st["agg"], st["s"], st["na"]
-            n = proj.size(0)
-            q, k, v = (proj[:na, i * hid:(i + 1) * hid] for i in range(3))
-            xr = proj[:, 7 * hid:]
-            qt = proj[:na, 3 * hid:7 * hid].unflatten(1, (h, hid)).transpose(0, 1)
-            dproj = dbuf[:, :8 * hid]
-            dq, dk, dv = (dbuf[:na, i * hid:(i + 1) * hid] for i in range(3))
-            dxr = dbuf[:, 7 * hid:8 * hid]
-            bbar = dbuf[:na, 3 * hid:7 * hid].unflatten(1, (h, hid)).transpose(0, 1)
+            proj, xr, xb, agg, s, na = st["proj"], st["xr"], st["xb"], st["agg"], st["s"], st["na"]
+            n = xr.size(0)
+            q, k, v = (proj[:, i * hid:(i + 1) * hid] for i in range(3))
+            qt = proj[:, 3 * hid:].unflatten(1, (h, hid)).transpose(0, 1)
+            dbuf = torch.empty(na, 7 * hid, dtype=cd, device=dev)             # dq | dk | dv | bbar_0..3 (active prefix)
+            dq, dk, dv = (dbuf[:, i * hid:(i + 1) * hid] for i in range(3))
+            bbar = dbuf[:, 3 * hid:].unflatten(1, (h, hid)).transpose(0, 1)
+            dxr = dtail[:, :hid]
+            dy2 = dtail[:, hid:] if dtail.size(1) == 2 * hid else None
             dagg, dagg_lp, dparams = ops.raw_gate_ln_bwd3(dy, agg, xr, wbf[idx], gmf[idx], blf[idx], st["beta"],
                                                           st["mean"], st["rstd"], s, h, dxr, cfg.p_out[idx], so, oo, rs,
                                                           dy2=dy2, agg_rows=na)
@@ -173,38 +173,26 @@ class _Trunk(torch.autograd.Function):
             # dWc[t] = dagg_t^T abar_t: diagonal blocks of one dense [H, na] x [na, 4H] product (K = na is what costs)
             gfull = torch.mm(dagg_lp.t(), st["abar_rows"].view(-1, h * hid), out_dtype=torch.float32)   # [H, 4H]
             d_wc[idx].copy_(torch.stack([gfull[t * c:(t + 1) * c, t * hid:(t + 1) * hid] for t in range(h)]).view(hid, hid))
-            ext = dbuf.size(1) == 9 * hid
-            wext = torch.cat([w8c[idx], eye], dim=0) if ext else w8c[idx]     # [9H | 8H, H]: identity block adds df
-            if na == n:
-                if dy is not None:
-                    dx = torch.addmm(dy, dbuf, wext, out_dtype=torch.float32)
-                else:
-                    dx = torch.mm(dbuf, wext, out_dtype=torch.float32)
-                torch.mm(dproj.t(), xb, out_dtype=torch.float32, out=d_w8[idx])
-                d_b8[idx].copy_(ops.colsum(dproj))
+            # dx = dy + [dx_r | df] [Ws ; I]  (all rows; the identity block adds df)  +  dbuf [Wq; Wk; Wv; WQT]  (active rows)
+            w7, ws = w8c[idx, :7 * hid], w8c[idx, 7 * hid:]
+            wtail = torch.cat([ws, eye], dim=0) if dy2 is not None else ws
+            if dy is not None:
+                dx = torch.addmm(dy, dtail, wtail, out_dtype=torch.float32)
             else:
-                dx = torch.empty(n, hid, **f32)
-                tail, wtail = dbuf[na:, 7 * hid:], wext[7 * hid:]             # isolated rows: dx_r (| df) only
-                if dy is not None:
-                    torch.addmm(dy[:na], dbuf[:na], wext, out_dtype=torch.float32, out=dx[:na])
-                    torch.addmm(dy[na:], tail, wtail, out_dtype=torch.float32, out=dx[na:])
-                else:
-                    torch.mm(dbuf[:na], wext, out_dtype=torch.float32, out=dx[:na])
-                    torch.mm(tail, wtail, out_dtype=torch.float32, out=dx[na:])
-                torch.mm(dproj[:na].t(), xb[:na], out_dtype=torch.float32, out=d_w8[idx])
-                ws_tail = torch.mm(dxr[na:].t(), xb[na:], out_dtype=torch.float32)
-                d_w8[idx, 7 * hid:].add_(ws_tail)
-                d_b8[idx].copy_(ops.colsum(dproj[:na]))
-                d_b8[idx, 7 * hid:].add_(ops.colsum(dxr[na:]))
+                dx = torch.mm(dtail, wtail, out_dtype=torch.float32)
+            torch.addmm(dx[:na], dbuf, w7, out_dtype=torch.float32, out=dx[:na])
+            torch.mm(dbuf.t(), xb[:na], out_dtype=torch.float32, out=d_w8[idx, :7 * hid])
+            torch.mm(dxr.t(), xb, out_dtype=torch.float32, out=d_w8[idx, 7 * hid:])
+            d_b8[idx, :7 * hid].copy_(ops.colsum(dbuf))
+            d_b8[idx, 7 * hid:].copy_(ops.colsum(dxr))
             st.clear()
             return dx
 
         for l in reversed(range(nl)):
-            dpe = torch.empty(n_bonds, 9 * hid, dtype=cd, device=dev)         # LG block l: dproj8 | df_l
-            dpa = torch.empty(n_atoms, 8 * hid, dtype=cd, device=dev)
-            df = dpe[:, 8 * hid:]
-            dn = block_backward(2 * l + 1, False, dn, None, dpa, df)
-            de = block_backward(2 * l, True, de, df, dpe, None)
+            tail_e = torch.empty(n_bonds, 2 * hid, dtype=cd, device=dev)      # LG block l: dx_r | df_l
+            tail_a = torch.empty(n_atoms, hid, dtype=cd, device=dev)
+            dn = block_backward(2 * l + 1, False, dn, tail_a, tail_e[:, hid:])
+            de = block_backward(2 * l, True, de, tail_e, None)
         dw1, db1 = ops.raw_lg_angle_grad(cfg.a_csr, cfg.w1, cfg.b1, cfg.lg_plan, coefs, qts, gts)
 
         t = ctx.dtypes
