@@ -350,12 +350,21 @@ def main_b200(args):
         h2d = host_batches[0].nbytes()
         out_host = [torch.empty(1 + 4 * n_graphs, dtype=torch.float32).pin_memory() for _ in range(2)]
 
+        # two device staging batches, allocated once: per-step device allocations on the copy stream make the caching
+        # allocator wait on cross-stream events (or fall back to cudaMalloc) and serialise the pipeline
+        staging = [host_batches[j].to(dev) for j in range(2)]
+        consumed = [None, None]                    # event: the step that read staging[j] has been enqueued and finished
+
         def upload(i):
+            j = i % 2
             with torch.cuda.stream(copy_stream):
-                b = host_batches[i % 2].to(dev, non_blocking=True)
+                if consumed[j] is not None:
+                    copy_stream.wait_event(consumed[j])
+                for k2, dst in staging[j].tensors().items():
+                    dst.copy_(getattr(host_batches[j], k2), non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
-            return b, ev
+            return staging[j], ev, j
 
         def e2e_loop(n_steps):
             """Software pipeline, one step deep: while step i runs on the GPU the host uploads batch i+1 (copy stream)
@@ -364,19 +373,19 @@ def main_b200(args):
             pending = None
             seen = 0.0
             for i in range(n_steps):
-                b, ev = nxt
+                b, ev, j = nxt
                 main_stream.wait_event(ev)
                 if i + 1 < n_steps:
                     nxt = upload(i + 1)            # next batch's H2D overlaps this step's compute
                 tz = pkg.zscore_targets(b.y, b.num_graphs)
                 loss, mean, logvar = step(i, b, tz)
+                consumed[j] = torch.cuda.Event()
+                consumed[j].record(main_stream)
                 packed = torch.cat([loss.detach().float().reshape(1), mean.detach().float().reshape(-1),
                                     logvar.detach().float().reshape(-1)])
                 out_host[i % 2].copy_(packed, non_blocking=True)
                 done = torch.cuda.Event()
                 done.record(main_stream)
-                for tns in b.tensors().values():
-                    tns.record_stream(main_stream)
                 if pending is not None:
                     pending[0].synchronize()       # results of the previous step are on the host
                     seen += float(out_host[pending[1]][0])

@@ -73,6 +73,37 @@ class BlockCfg:
     strided: bool = False              # stored-feature tensor-core family with strided operands + device RNG counter
 
 
+class _LinearCS(torch.autograd.Function):
+    """``x W^T + b`` (cuBLAS) whose backward forms the bias gradient with the deterministic ``colsum`` kernel instead of
+    torch's generic reduction (the encoders' second Linears see ``[E, 256]`` gradients: reference ``train.py:350-359``)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, w: Tensor, b: Tensor, relu: bool):
+        y = torch.addmm(b, x, w.t())
+        if relu:
+            y = torch.relu_(y)
+        ctx.save_for_backward(x, w, y if relu else None)
+        ctx.relu = relu
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        x, w, y = ctx.saved_tensors
+        dy = dy.contiguous()
+        if ctx.relu:
+            dy = dy * (y > 0)
+        dx = dy @ w if ctx.needs_input_grad[0] else None
+        dw = torch.mm(dy.t(), x, out_dtype=torch.float32) if dy.dtype != torch.float32 else dy.t() @ x
+        db = ops.colsum(dy)
+        return dx, dw.to(w.dtype), db.to(w.dtype), None
+
+
+def mlp2(x: Tensor, w0: Tensor, b0: Tensor, w2: Tensor, b2: Tensor, cd: torch.dtype) -> Tensor:
+    """``Linear -> ReLU -> Linear`` encoder in compute dtype ``cd`` (reference ``train.py:350-359``)."""
+    h = _LinearCS.apply(x.to(cd), w0.to(cd), b0.to(cd), True)
+    return _LinearCS.apply(h, w2.to(cd), b2.to(cd), False)
+
+
 class _AngleH1(torch.autograd.Function):
     """``h1 = relu(W1 a + b1)`` (first angle-encoder layer).  Its backward expects the ALREADY ReLU-masked gradient
     (the last line-graph block's backward kernel applies the mask while accumulating)."""

@@ -334,10 +334,11 @@ class AlignnRegressor(nn.Module):
         dev = data.x.device
         n_bonds, n_angles = data.edge_index.size(1), data.lg_edge_index.size(1)
         with torch.autocast("cuda", enabled=False):
-            node_b0 = _mlp2(self.node_encoder, data.x, cd)
+            enc_n, enc_e = self.node_encoder, self.edge_encoder
+            node_b0 = fused.mlp2(data.x, enc_n[0].weight, enc_n[0].bias, enc_n[2].weight, enc_n[2].bias, cd)
             node32 = node_b0.float()
             if data.edge_attr.numel() > 0:
-                edge_b0 = _mlp2(self.edge_encoder, data.edge_attr, cd)
+                edge_b0 = fused.mlp2(data.edge_attr, enc_e[0].weight, enc_e[0].bias, enc_e[2].weight, enc_e[2].bias, cd)
                 edge32 = edge_b0.float()
             else:
                 edge32 = torch.zeros(n_bonds, self.hidden, device=dev)
@@ -453,7 +454,7 @@ class AlignnRegressor(nn.Module):
             keys.append((sa, oa, so, oo))
         cfg = trunk_mod.TrunkCfg(heads=h, n_layers=nl, eps=[b.norm.eps for b in blocks], p_attn=p_attn, p_out=p_out,
                                  keys=keys, lg_plan=lg_plan, g_plan=g_plan, a_csr=lg.a_csr, w1=lg.w1, b1=lg.b1,
-                                 lg_active=lg_active)
+                                 lg_active=lg_active, overlap=bool(getattr(self, "overlap_streams", True)))
         enc = self.angle_encoder
         return trunk_mod.run_trunk(node32, node_b, edge32, edge_b, w8, b8, wc, cvec, wbeta, gamma, beta_ln,
                                    enc[0].weight, enc[0].bias, cfg)

@@ -646,7 +646,8 @@ def raw_gate_ln_bwd2(dy: Tensor, agg: Tensor, xr: Tensor, wbeta: Tensor, gamma: 
 
 def raw_gate_ln_bwd3(dy: Optional[Tensor], agg: Tensor, xr: Tensor, wbeta: Tensor, gamma: Tensor, bias: Tensor, beta: Tensor,
                      mean: Tensor, rstd: Tensor, stat_s: Tensor, heads: int, dxr: Tensor, p_drop: float, seed: int,
-                     offset: int, rng_step: Optional[Tensor] = None, dy2: Optional[Tensor] = None, agg_rows: int = -1):
+                     offset: int, rng_step: Optional[Tensor] = None, dy2: Optional[Tensor] = None, agg_rows: int = -1,
+                     dparams: Optional[Tensor] = None):
     """As :func:`raw_gate_ln_bwd2` (always emits the storage-dtype copy of dagg) plus the gradient of the folded
     edge-projection bias: returns (dagg f32, dagg_lp, dparams f32 [6*hidden] = dw_beta x3 | dgamma | dbias | dcvec)."""
     lib = _lib.load()
@@ -656,7 +657,8 @@ def raw_gate_ln_bwd3(dy: Optional[Tensor], agg: Tensor, xr: Tensor, wbeta: Tenso
     dagg = torch.empty(n_rows, hidden, **f32)
     dagg_lp = torch.empty(n_rows, hidden, dtype=xr.dtype, device=dev)
     partials = torch.empty(int(lib.alignn_gate_ln_bwd_partial_rows()) * 6 * hidden, **f32)
-    dparams = torch.empty(6 * hidden, **f32)
+    if dparams is None:
+        dparams = torch.empty(6 * hidden, **f32)
     with torch.cuda.device(dev), _Launch("gate_ln_bwd", 2, (n_rows, hidden, xr.element_size())):
         rc = lib.alignn_gate_ln_bwd3(_p(dy), _p(dy2), _ld(dy2) if dy2 is not None else hidden, _p(agg), _p(xr), _ld(xr), _p(wbeta), _p(gamma), _p(bias), _p(beta),
                                      _p(mean), _p(rstd), _p(stat_s), heads, int(agg_rows), _p(dagg), _p(dagg_lp), _p(dxr),
@@ -667,15 +669,18 @@ def raw_gate_ln_bwd3(dy: Optional[Tensor], agg: Tensor, xr: Tensor, wbeta: Tenso
     return dagg, dagg_lp, dparams
 
 
-def colsum(x: Tensor) -> Tensor:
-    """fp32 column sums of a 2-D tensor with unit column stride (deterministic hand-written reduction)."""
+def colsum(x: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """fp32 column sums of a 2-D tensor with unit column stride (deterministic hand-written reduction); ``out``: optional
+    contiguous fp32 ``[width]`` destination."""
     lib = _lib.load()
     n_rows, width = x.shape
-    if not lib.alignn_colsum_supported(width) or x.dtype not in _DT or _ld(x) % 8:
-        return x.sum(0, dtype=torch.float32)
+    if n_rows == 0 or not lib.alignn_colsum_supported(width) or x.dtype not in _DT or _ld(x) % 8 or x.data_ptr() % 16:
+        res = x.sum(0, dtype=torch.float32)
+        return res if out is None else out.copy_(res)
     f32 = dict(dtype=torch.float32, device=x.device)
     partials = torch.empty(int(lib.alignn_colsum_partial_floats(width)), **f32)
-    out = torch.empty(width, **f32)
+    if out is None:
+        out = torch.empty(width, **f32)
     with torch.cuda.device(x.device), _Launch("colsum", 2, (n_rows, width, x.element_size())):
         rc = lib.alignn_colsum(_p(x), _ld(x), n_rows, width, _dtype_code(x), _p(partials), _p(out), _stream())
     _lib.check(rc, "alignn_colsum")

@@ -54,6 +54,21 @@ class TrunkCfg:
     b1: Tensor = None
     want_node_lp: bool = False
     lg_active: int = -1                  # bond rows >= lg_active are isolated in the line graph (< 0: unknown, all active)
+    overlap: bool = True                 # run the atom-graph chain on a second stream (fork/join; capturable)
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device: torch.device) -> torch.cuda.Stream:
+    """One extra stream per device for the atom-graph chain.  NodeUpdateBlock_l only depends on EdgeUpdateBlock_l and
+    NodeUpdateBlock_{l-1}, so it can run beside EdgeUpdateBlock_{l+1} (forward) / its backward beside EdgeUpdateBlock_{l+1}'s
+    (backward); under CUDA-graph capture the fork/join events become graph edges."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return st
 
 
 def _block_forward(idx: int, is_lg: bool, x32: Tensor, xb: Tensor, feat: Optional[Tensor], w8c: Tensor, b8c: Tensor,
@@ -105,17 +120,33 @@ class _Trunk(torch.autograd.Function):
             nb = nb.to(cd)
         if eb.dtype != cd:
             eb = eb.to(cd)
-        saved = []
+        saved = [None] * (2 * nl)
+        main = torch.cuda.current_stream()
+        side = _side_stream(node32.device) if cfg.overlap else None
+        if side is not None:
+            side.wait_stream(main)
+            for t in (n32, nb):
+                t.record_stream(side)
         for l in range(nl):
             i = 2 * l
-            e32, eb, st = _block_forward(i, True, e32, eb, None, w8c[i], b8c[i], wc3[i], cvf[i], wbf[i], gmf[i], blf[i],
-                                         cfg, True, rs)
-            saved.append(st)
+            e32, eb, saved[i] = _block_forward(i, True, e32, eb, None, w8c[i], b8c[i], wc3[i], cvf[i], wbf[i], gmf[i],
+                                               blf[i], cfg, True, rs)
             i = 2 * l + 1
-            last = l == nl - 1
-            n32, nb, st = _block_forward(i, False, n32, nb, eb, w8c[i], b8c[i], wc3[i], cvf[i], wbf[i], gmf[i], blf[i],
-                                         cfg, (not last) or cfg.want_node_lp, rs)
-            saved.append(st)
+            want_lp = (l < nl - 1) or cfg.want_node_lp
+            if side is None:
+                n32, nb, saved[i] = _block_forward(i, False, n32, nb, eb, w8c[i], b8c[i], wc3[i], cvf[i], wbf[i], gmf[i],
+                                                   blf[i], cfg, want_lp, rs)
+            else:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                eb.record_stream(side)
+                with torch.cuda.stream(side):
+                    side.wait_event(ev)
+                    n32, nb, saved[i] = _block_forward(i, False, n32, nb, eb, w8c[i], b8c[i], wc3[i], cvf[i], wbf[i],
+                                                       gmf[i], blf[i], cfg, want_lp, rs)
+        if side is not None:
+            main.wait_stream(side)
+            n32.record_stream(main)
         ctx.saved, ctx.cfg, ctx.rs = saved, cfg, rs
         ctx.weights = (w8c, wc3, cvf, wbf, gmf, blf)
         ctx.dtypes = (w8.dtype, b8.dtype, wc.dtype, cvec.dtype, wbeta.dtype, gamma.dtype, beta_ln.dtype, w1.dtype, b1.dtype)
@@ -158,8 +189,7 @@ class _Trunk(torch.autograd.Function):
             dy2 = dtail[:, hid:] if dtail.size(1) == 2 * hid else None
             dagg, dagg_lp, dparams = ops.raw_gate_ln_bwd3(dy, agg, xr, wbf[idx], gmf[idx], blf[idx], st["beta"],
                                                           st["mean"], st["rstd"], s, h, dxr, cfg.p_out[idx], so, oo, rs,
-                                                          dy2=dy2, agg_rows=na)
-            d_par[idx].copy_(dparams)
+                                                          dy2=dy2, agg_rows=na, dparams=d_par[idx])
             dagg, dagg_lp, agg = dagg[:na], dagg_lp[:na], agg[:na]
             g3 = dagg_lp.unflatten(1, (h, c)).transpose(0, 1)                 # [h, na, C]
             gt = torch.bmm(g3, wc3[idx])                                      # [h, na, H]
@@ -183,16 +213,32 @@ class _Trunk(torch.autograd.Function):
             torch.addmm(dx[:na], dbuf, w7, out_dtype=torch.float32, out=dx[:na])
             torch.mm(dbuf.t(), xb[:na], out_dtype=torch.float32, out=d_w8[idx, :7 * hid])
             torch.mm(dxr.t(), xb, out_dtype=torch.float32, out=d_w8[idx, 7 * hid:])
-            d_b8[idx, :7 * hid].copy_(ops.colsum(dbuf))
-            d_b8[idx, 7 * hid:].copy_(ops.colsum(dxr))
+            ops.colsum(dbuf, out=d_b8[idx, :7 * hid])
+            ops.colsum(dxr, out=d_b8[idx, 7 * hid:])
             st.clear()
             return dx
 
+        main = torch.cuda.current_stream()
+        side = _side_stream(dev) if cfg.overlap else None
+        tails = [torch.empty(n_bonds, 2 * hid, dtype=cd, device=dev) for _ in range(nl)]   # LG block l: dx_r | df_l
+        if side is not None:
+            side.wait_stream(main)
+            for t in tails + [dn, d_w8, d_b8, d_wc, d_par, eye]:
+                t.record_stream(side)
         for l in reversed(range(nl)):
-            tail_e = torch.empty(n_bonds, 2 * hid, dtype=cd, device=dev)      # LG block l: dx_r | df_l
-            tail_a = torch.empty(n_atoms, hid, dtype=cd, device=dev)
-            dn = block_backward(2 * l + 1, False, dn, tail_a, tail_e[:, hid:])
-            de = block_backward(2 * l, True, de, tail_e, None)
+            if side is None:
+                dn = block_backward(2 * l + 1, False, dn, torch.empty(n_atoms, hid, dtype=cd, device=dev), tails[l][:, hid:])
+            else:
+                with torch.cuda.stream(side):
+                    dn = block_backward(2 * l + 1, False, dn, torch.empty(n_atoms, hid, dtype=cd, device=dev),
+                                        tails[l][:, hid:])
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                main.wait_event(ev)
+            de = block_backward(2 * l, True, de, tails[l], None)
+        if side is not None:
+            main.wait_stream(side)
+            dn.record_stream(main)
         dw1, db1 = ops.raw_lg_angle_grad(cfg.a_csr, cfg.w1, cfg.b1, cfg.lg_plan, coefs, qts, gts)
 
         t = ctx.dtypes
