@@ -654,13 +654,13 @@ __global__ void __launch_bounds__(CS_THREADS)
 colsum_kernel(const T *__restrict__ x, int64_t ld, int64_t n_rows, int width, float *__restrict__ partials) {
     __shared__ float red[CS_THREADS * 8];
     const int lanes = width >> 3;                   // threads per row
-    const int groups = CS_THREADS / lanes;          // rows per CTA iteration
+    const int groups = CS_THREADS / lanes;          // rows per CTA iteration (threads beyond lanes * groups idle)
     const int sub = threadIdx.x % lanes, grp = threadIdx.x / lanes;
     const int64_t stride = (int64_t)gridDim.x * groups;
     F8 acc;
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc.v[c] = 0.f;
-    int64_t row = (int64_t)blockIdx.x * groups + grp;
+    int64_t row = grp < groups ? (int64_t)blockIdx.x * groups + grp : n_rows;
     for (; row + 3 * stride < n_rows; row += 4 * stride) {      // 4 independent 16-byte loads in flight per thread
         const F8 a = ld8(x + row * ld + sub * 8), b = ld8(x + (row + stride) * ld + sub * 8);
         const F8 c2 = ld8(x + (row + 2 * stride) * ld + sub * 8), d = ld8(x + (row + 3 * stride) * ld + sub * 8);
@@ -688,7 +688,7 @@ colsum_kernel(const T *__restrict__ x, int64_t ld, int64_t n_rows, int width, fl
 extern "C" int64_t alignn_colsum_partial_floats(int width) { return (int64_t)CS_BLOCKS * width; }
 
 extern "C" int alignn_colsum_supported(int width) {
-    return width >= 8 && width <= 2048 && width % 8 == 0 && CS_THREADS % (width / 8) == 0;
+    return width >= 8 && width <= 2048 && width % 8 == 0;
 }
 
 extern "C" int alignn_colsum(const void *x, int64_t ld, int64_t n_rows, int width, int dtype, float *partials,

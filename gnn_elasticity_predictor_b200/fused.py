@@ -91,7 +91,7 @@ class _LinearCS(torch.autograd.Function):
         x, w, y = ctx.saved_tensors
         dy = dy.contiguous()
         if ctx.relu:
-            dy = dy * (y > 0)
+            dy = torch.ops.aten.threshold_backward(dy, y, 0)
         dx = dy @ w if ctx.needs_input_grad[0] else None
         dw = torch.mm(dy.t(), x, out_dtype=torch.float32) if dy.dtype != torch.float32 else dy.t() @ x
         db = ops.colsum(dy)
@@ -100,7 +100,17 @@ class _LinearCS(torch.autograd.Function):
 
 def mlp2(x: Tensor, w0: Tensor, b0: Tensor, w2: Tensor, b2: Tensor, cd: torch.dtype) -> Tensor:
     """``Linear -> ReLU -> Linear`` encoder in compute dtype ``cd`` (reference ``train.py:350-359``)."""
-    h = _LinearCS.apply(x.to(cd), w0.to(cd), b0.to(cd), True)
+    k = x.size(1)
+    if cd != torch.float32 and k % 8:
+        # pad the input width to a multiple of 8 elements (16 bytes): cuBLAS otherwise falls back to its unaligned
+        # legacy kernels for the [n, 36] / [n, 206] first-layer GEMMs (5x slower); zero columns change nothing
+        kp = (k + 7) // 8 * 8
+        xp = torch.zeros(x.size(0), kp, dtype=cd, device=x.device)
+        xp[:, :k] = x
+        w0p = torch.nn.functional.pad(w0.to(cd), (0, kp - k))
+        h = _LinearCS.apply(xp, w0p, b0.to(cd), True)
+    else:
+        h = _LinearCS.apply(x.to(cd), w0.to(cd), b0.to(cd), True)
     return _LinearCS.apply(h, w2.to(cd), b2.to(cd), False)
 
 

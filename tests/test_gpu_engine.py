@@ -115,7 +115,7 @@ def test_lg_family_matches_stored_feature_family_on_the_model(monkeypatch):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
-@pytest.mark.parametrize("shape", [(98304, 2048), (1000, 1024), (37, 256), (5, 8), (12, 48)])
+@pytest.mark.parametrize("shape", [(98304, 2048), (8544, 1792), (1000, 1024), (37, 256), (5, 8), (12, 48), (333, 24)])
 def test_colsum_matches_fp64(shape, dtype):
     g = torch.Generator().manual_seed(shape[0])
     big = torch.randn(shape[0], shape[1] + 64, generator=g).to(dtype).to(DEV)
