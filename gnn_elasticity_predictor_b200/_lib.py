@@ -59,10 +59,10 @@ SIGNATURES = {
     "alignn_lg_pack_angles": (c_int, [_P, _P, _P, c_int64, c_int, _P]),
     "alignn_lgattn_fwd": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, _P, c_int64, c_int64, _P, _P, _P, c_int,
                                   _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P,
-                                  c_int64, c_int64, c_int, c_int, c_int, c_float, c_uint64, c_uint64, _P, _P]),
+                                  c_int64, c_int64, c_int, c_int, c_int, c_float, c_uint64, c_uint64, _P, _P, _P]),
     "alignn_lgattn_bwd_dst": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, _P, c_int64, c_int64, _P, c_int64,
                                       c_int64, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, c_int64, _P, c_int64, c_int64,
-                                      _P, c_int64, c_int64, c_int, c_int, c_int, c_float, c_uint64, c_uint64, _P, _P]),
+                                      _P, c_int64, c_int64, c_int, c_int, c_int, c_float, c_uint64, c_uint64, _P, _P, _P]),
     "alignn_lg_angle_grad_partial_floats": (c_int64, [c_int64, c_int64]),
     "alignn_lg_angle_grad": (c_int, [_P, _P, _P, c_int, _P, c_int, _P, _P, _P, c_int64, c_int64, c_int64, c_int64,
                                      _P, _P, c_int64, c_int64, _P]),
@@ -88,7 +88,7 @@ SIGNATURES = {
     "alignn_segment_mean_bwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P]),
 }
 
-ABI_VERSION = 12
+ABI_VERSION = 13
 F32, BF16 = 0, 1
 
 

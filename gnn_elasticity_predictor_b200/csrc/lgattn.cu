@@ -41,6 +41,23 @@ __device__ __forceinline__ uint2 lds64(uint32_t smem_addr) {
     return v;
 }
 
+constexpr int LG_UNIT = 128;   // scheduling unit: a row range of about this many (edges + ROW_KAPPA * rows)
+
+// work[0]: next unit, work[1]: CTAs that ran out of units.  The last CTA to finish puts both back to zero, so the same
+// two words serve every launch on the stream without a memset in between (the buffer must be zero before the first one).
+__device__ __forceinline__ void lg_work_done(unsigned int *work) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int d = atomicAdd(work + 1, 1u);
+        if (d == gridDim.x - 1) {
+            work[0] = 0u;
+            work[1] = 0u;
+            __threadfence();
+        }
+    }
+}
+
 // W1ext(ch, r): r < in_dim -> W1[ch, r];  r == in_dim -> b1[ch];  else 0
 __device__ __forceinline__ float w1ext(const float *__restrict__ w1, const float *__restrict__ b1, int in_dim, int ch, int r) {
     return r < in_dim ? __ldg(w1 + ch * in_dim + r) : (r == in_dim ? __ldg(b1 + ch) : 0.f);
@@ -122,6 +139,7 @@ struct LgFwdParams {
     __nv_bfloat16 *abar;                // abar[row * ldab + t * hsab + ch]
     float *stat_m, *stat_z, *stat_s;    // [Nn, 4]
     const uint64_t *rng_step;           // optional device counter added to `offset` (CUDA-graph replays)
+    unsigned int *work;                 // [2] zero on entry, zero again on exit (dynamic unit scheduler)
     int n_nodes, n_edges, in_dim;
     int ldq, ldk, ldv;
     int64_t ldqt, hsqt, ldab, hsab;
@@ -143,13 +161,21 @@ lgattn_fwd_kernel(const LgFwdParams P) {
     for (int off = lane * 16; off < LGF_PER_WARP; off += 512) sts128(wbase_u32 + off, make_uint4(0, 0, 0, 0));
     __syncthreads();
 
-    const int64_t W = (int64_t)gridDim.x * LGF_WARPS, w = (int64_t)blockIdx.x * LGF_WARPS + warp;
     const int64_t total = (int64_t)P.n_edges + (int64_t)ROW_KAPPA * P.n_nodes;
-    const int r0 = (int)row_bound(P.rowptr, P.n_nodes, total * w / W);
-    const int r1 = (int)row_bound(P.rowptr, P.n_nodes, total * (w + 1) / W);
-    if (r0 >= r1) return;
-    const int e_end = __ldg(P.rowptr + r1);
+    const int64_t n_units = (total + LG_UNIT - 1) / LG_UNIT;
     const uint64_t rng_off = P.offset + (P.rng_step ? *P.rng_step : 0ull);
+    // Dynamic scheduling: every warp draws the next unit (a row range of ~LG_UNIT edges) from a global counter, so that
+    // rows of very different length (0 .. thousands of in-edges with PyG-collated batches) balance across the 1 184 warps
+    // of the grid.  A row is always processed by ONE warp in CSR order: the result does not depend on the schedule.
+    for (;;) {
+    int unit = 0;
+    if (lane == 0) unit = (int)atomicAdd(P.work, 1u);
+    unit = __shfl_sync(FULL, unit, 0);
+    if (unit >= n_units) break;
+    const int r0 = (int)row_bound(P.rowptr, P.n_nodes, (int64_t)unit * LG_UNIT);
+    const int r1 = (int)row_bound(P.rowptr, P.n_nodes, min(total, (int64_t)(unit + 1) * LG_UNIT));
+    if (r0 >= r1) continue;
+    const int e_end = __ldg(P.rowptr + r1);
 
     ChunkCursor cur;
     cur.init(P.rowptr, r0, r1);
@@ -167,7 +193,7 @@ lgattn_fwd_kernel(const LgFwdParams P) {
                 P.stat_s[(int64_t)r * LG_HEADS + lane] = 0.f;
             }
         }
-        return;
+        continue;
     }
     int wbase = cur.pos;
     IndexWindow wcol;
@@ -386,6 +412,9 @@ lgattn_fwd_kernel(const LgFwdParams P) {
     }
     cp_async_wait<0>();
     zero_rows(next_unwritten, r1);
+    __syncwarp();
+    }   // unit loop
+    lg_work_done(P.work);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -409,6 +438,7 @@ struct LgBwdParams {
     __nv_bfloat16 *bbar;                  // base[row * ldbb + t * hsbb + ch]
     float *coef;                          // [Ne, 8] in CSR order: (a~_0..3, ds_0..3)
     const uint64_t *rng_step;
+    unsigned int *work;                   // [2] zero on entry / exit
     int n_nodes, n_edges, in_dim;
     int ldq, ldk, ldv, lddq;
     int64_t ldqt, hsqt, ldgt, hsgt, ldbb, hsbb;
@@ -430,13 +460,18 @@ lgattn_bwd_kernel(const LgBwdParams P) {
     for (int off = lane * 16; off < LGB_PER_WARP; off += 512) sts128(wbase_u32 + off, make_uint4(0, 0, 0, 0));
     __syncthreads();
 
-    const int64_t W = (int64_t)gridDim.x * LGB_WARPS, w = (int64_t)blockIdx.x * LGB_WARPS + warp;
     const int64_t total = (int64_t)P.n_edges + (int64_t)ROW_KAPPA * P.n_nodes;
-    const int r0 = (int)row_bound(P.rowptr, P.n_nodes, total * w / W);
-    const int r1 = (int)row_bound(P.rowptr, P.n_nodes, total * (w + 1) / W);
-    if (r0 >= r1) return;
-    const int e_end = __ldg(P.rowptr + r1);
+    const int64_t n_units = (total + LG_UNIT - 1) / LG_UNIT;
     const uint64_t rng_off = P.offset + (P.rng_step ? *P.rng_step : 0ull);
+    for (;;) {   // dynamic units, see lgattn_fwd_kernel
+    int unit = 0;
+    if (lane == 0) unit = (int)atomicAdd(P.work, 1u);
+    unit = __shfl_sync(FULL, unit, 0);
+    if (unit >= n_units) break;
+    const int r0 = (int)row_bound(P.rowptr, P.n_nodes, (int64_t)unit * LG_UNIT);
+    const int r1 = (int)row_bound(P.rowptr, P.n_nodes, min(total, (int64_t)(unit + 1) * LG_UNIT));
+    if (r0 >= r1) continue;
+    const int e_end = __ldg(P.rowptr + r1);
 
     auto zero_rows = [&](int lo, int hi) {
         F8 zf;
@@ -453,7 +488,7 @@ lgattn_bwd_kernel(const LgBwdParams P) {
     cur.init(P.rowptr, r0, r1);
     if (cur.done()) {
         zero_rows(r0, r1);
-        return;
+        continue;
     }
     int wbase = cur.pos;
     IndexWindow wcol;
@@ -675,6 +710,9 @@ lgattn_bwd_kernel(const LgBwdParams P) {
     }
     cp_async_wait<0>();
     zero_rows(next_unwritten, r1);
+    __syncwarp();
+    }   // unit loop
+    lg_work_done(P.work);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -861,6 +899,13 @@ static int lg_grid(int64_t n_nodes, int64_t n_edges, int warps) {
     return (int)blocks;
 }
 
+// persistent grid of the dynamically scheduled kernels: one CTA per SM, fewer when there is little work
+static int lg_persistent_grid(int64_t n_nodes, int64_t n_edges, int warps) {
+    const int64_t units = (n_edges + (int64_t)ROW_KAPPA * n_nodes + LG_UNIT - 1) / LG_UNIT;
+    const int64_t blocks = (units + warps - 1) / warps;
+    return (int)(blocks < 1 ? 1 : (blocks > 148 ? 148 : blocks));
+}
+
 // a_csr[p, :] = (bf16(a[eid[p], 0..in_dim-1]), 1, 0, ...)
 __global__ void lg_pack_angles_kernel(const float *__restrict__ a, const int32_t *__restrict__ eid,
                                       __nv_bfloat16 *__restrict__ a_csr, int64_t n_edges, int in_dim) {
@@ -901,13 +946,14 @@ extern "C" int alignn_lgattn_fwd(const void *q, const void *k, const void *v, in
                                  float *aggv, void *abar, int64_t ldab, int64_t hsab,
                                  float *stat_m, float *stat_z, float *stat_s,
                                  int64_t n_nodes, int64_t n_edges, int hidden, int heads, int dtype,
-                                 float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step, void *stream) {
+                                 float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step, void *work,
+                                 void *stream) {
     if (!alignn_lgattn_supported(hidden, heads, in_dim, dtype)) return ALIGNN_ERR_BAD_SHAPE;
     if (n_nodes < 0 || n_edges < 0 || !(p_drop >= 0.f && p_drop < 1.f)) return ALIGNN_ERR_BAD_ARG;
     if (n_nodes >= ((int64_t)1 << 31) - 1 || n_edges >= ((int64_t)1 << 31) - 64) return ALIGNN_ERR_BAD_SHAPE;
     if (ldq >= ((int64_t)1 << 30) || ldk >= ((int64_t)1 << 30) || ldv >= ((int64_t)1 << 30)) return ALIGNN_ERR_BAD_SHAPE;
     if (n_nodes == 0) return ALIGNN_OK;
-    if (!q || !k || !v || !qt || !w1 || !b1 || !rowptr || !aggv || !abar || !stat_m || !stat_z || !stat_s)
+    if (!q || !k || !v || !qt || !w1 || !b1 || !rowptr || !aggv || !abar || !stat_m || !stat_z || !stat_s || !work)
         return ALIGNN_ERR_BAD_ARG;
     if (n_edges > 0 && (!a_csr || !col)) return ALIGNN_ERR_BAD_ARG;
     if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(qt) || !aligned16(a_csr) || !aligned16(aggv) ||
@@ -917,7 +963,7 @@ extern "C" int alignn_lgattn_fwd(const void *q, const void *k, const void *v, in
     p.q = (const __nv_bfloat16 *)q; p.k = (const __nv_bfloat16 *)k; p.v = (const __nv_bfloat16 *)v;
     p.qt = (const __nv_bfloat16 *)qt; p.a_csr = (const __nv_bfloat16 *)a_csr; p.w1 = w1; p.b1 = b1;
     p.rowptr = rowptr; p.col = col; p.aggv = aggv; p.abar = (__nv_bfloat16 *)abar;
-    p.stat_m = stat_m; p.stat_z = stat_z; p.stat_s = stat_s; p.rng_step = rng_step;
+    p.stat_m = stat_m; p.stat_z = stat_z; p.stat_s = stat_s; p.rng_step = rng_step; p.work = (unsigned int *)work;
     p.n_nodes = (int)n_nodes; p.n_edges = (int)n_edges; p.in_dim = in_dim;
     p.ldq = (int)ldq; p.ldk = (int)ldk; p.ldv = (int)ldv; p.ldqt = ldqt; p.hsqt = hsqt; p.ldab = ldab; p.hsab = hsab;
     p.scale_log2 = LOG2E / sqrtf((float)(hidden / heads));
@@ -926,7 +972,7 @@ extern "C" int alignn_lgattn_fwd(const void *q, const void *k, const void *v, in
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     constexpr int SMEM = LG_IMG + LGF_WARPS * LGF_PER_WARP;
     ALIGNN_CUDA_TRY(cudaFuncSetAttribute(lgattn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    lgattn_fwd_kernel<<<lg_grid(n_nodes, n_edges, LGF_WARPS), LGF_WARPS * 32, SMEM, st>>>(p);
+    lgattn_fwd_kernel<<<lg_persistent_grid(n_nodes, n_edges, LGF_WARPS), LGF_WARPS * 32, SMEM, st>>>(p);
     ALIGNN_LAUNCH_CHECK();
     return ALIGNN_OK;
 }
@@ -938,8 +984,9 @@ extern "C" int alignn_lgattn_bwd_dst(const float *dagg, const void *dagg_lp, con
                                      const float *stat_m, const float *stat_z, const int32_t *rowptr, const int32_t *col,
                                      void *dq, int64_t lddq, void *bbar, int64_t ldbb, int64_t hsbb, float *coef,
                                      int64_t n_nodes, int64_t n_edges, int hidden, int heads, int dtype,
-                                     float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step, void *stream) {
-    if (!alignn_lgattn_supported(hidden, heads, in_dim, dtype)) return ALIGNN_ERR_BAD_SHAPE;
+                                     float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step, void *work,
+                                     void *stream) {
+    if (!alignn_lgattn_supported(hidden, heads, in_dim, dtype) || !work) return ALIGNN_ERR_BAD_SHAPE;
     if (n_nodes < 0 || n_edges < 0 || !(p_drop >= 0.f && p_drop < 1.f)) return ALIGNN_ERR_BAD_ARG;
     if (n_nodes >= ((int64_t)1 << 31) - 1 || n_edges >= ((int64_t)1 << 31) - 64) return ALIGNN_ERR_BAD_SHAPE;
     if (ldq >= ((int64_t)1 << 30) || ldk >= ((int64_t)1 << 30) || ldv >= ((int64_t)1 << 30) || lddq >= ((int64_t)1 << 30))
@@ -960,7 +1007,7 @@ extern "C" int alignn_lgattn_bwd_dst(const float *dagg, const void *dagg_lp, con
     p.qt = (const __nv_bfloat16 *)qt; p.gt = (const __nv_bfloat16 *)gt; p.cvec = cvec;
     p.a_csr = (const __nv_bfloat16 *)a_csr; p.w1 = w1; p.b1 = b1; p.stat_m = stat_m; p.stat_z = stat_z;
     p.rowptr = rowptr; p.col = col; p.dq = (__nv_bfloat16 *)dq; p.bbar = (__nv_bfloat16 *)bbar; p.coef = coef;
-    p.rng_step = rng_step; p.n_nodes = (int)n_nodes; p.n_edges = (int)n_edges; p.in_dim = in_dim;
+    p.rng_step = rng_step; p.work = (unsigned int *)work; p.n_nodes = (int)n_nodes; p.n_edges = (int)n_edges; p.in_dim = in_dim;
     p.ldq = (int)ldq; p.ldk = (int)ldk; p.ldv = (int)ldv; p.lddq = (int)lddq;
     p.ldqt = ldqt; p.hsqt = hsqt; p.ldgt = ldgt; p.hsgt = hsgt; p.ldbb = ldbb; p.hsbb = hsbb;
     p.scale = 1.0f / sqrtf((float)(hidden / heads));
@@ -970,7 +1017,7 @@ extern "C" int alignn_lgattn_bwd_dst(const float *dagg, const void *dagg_lp, con
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     constexpr int SMEM = LG_IMG + LGB_WARPS * LGB_PER_WARP;
     ALIGNN_CUDA_TRY(cudaFuncSetAttribute(lgattn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    lgattn_bwd_kernel<<<lg_grid(n_nodes, n_edges, LGB_WARPS), LGB_WARPS * 32, SMEM, st>>>(p);
+    lgattn_bwd_kernel<<<lg_persistent_grid(n_nodes, n_edges, LGB_WARPS), LGB_WARPS * 32, SMEM, st>>>(p);
     ALIGNN_LAUNCH_CHECK();
     return ALIGNN_OK;
 }

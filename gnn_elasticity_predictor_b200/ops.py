@@ -457,6 +457,14 @@ def raw_attn_bwd_s(dagg: Tensor, dagg_lp: Tensor, agg: Tensor, q: Tensor, k: Ten
         _lib.check(rc, "alignn_edgeattn_bwd_src_lp")
 
 
+def _work(plan: GraphPlan) -> Tensor:
+    """Zeroed scheduler words of the dynamically scheduled line-graph kernels (they leave them zero); one per plan."""
+    w = getattr(plan, "_work", None)
+    if w is None:
+        w = plan._work = torch.zeros(4, dtype=torch.int32, device=plan.rowptr.device)
+    return w
+
+
 def pack_angles(a: Tensor, plan: GraphPlan) -> Tensor:
     """``[L, 16]`` bf16 angle features in the plan's target-sorted order, bias column set to 1 (``csrc/lgattn.cu``)."""
     lib = _lib.load()
@@ -488,7 +496,7 @@ def raw_lgattn_fwd(q: Tensor, k: Tensor, v: Tensor, qt: Tensor, a_csr: Tensor, w
                                    int(qt.stride(0)), _p(a_csr), _p(w1), _p(b1), int(w1.size(1)), _p(plan.rowptr),
                                    _p(plan.col), _p(aggv), _p(abar), int(abar.stride(1)), int(abar.stride(0)),
                                    _p(m), _p(z), _p(s), n_nodes, n_edges, hidden, heads, _dtype_code(q), float(p_drop),
-                                   seed, offset, _p(rng_step), _stream())
+                                   seed, offset, _p(rng_step), _p(_work(plan)), _stream())
     _lib.check(rc, "alignn_lgattn_fwd")
     return aggv, abar, m, z, s
 
@@ -523,7 +531,7 @@ def raw_lgattn_bwd(dagg: Tensor, dagg_lp: Tensor, agg: Tensor, q: Tensor, k: Ten
                 _p(qt), int(qt.stride(1)), int(qt.stride(0)), _p(gt), int(gt.stride(1)), int(gt.stride(0)),
                 _p(cvec), _p(a_csr), _p(w1), _p(b1), int(w1.size(1)), _p(m), _p(z), _p(plan.rowptr), _p(plan.col),
                 _p(dq), _ld(dq), _p(bbar), int(bbar.stride(1)), int(bbar.stride(0)), _p(coef), n_nodes, n_edges, hidden,
-                heads, _dtype_code(q), float(p_drop), seed, offset, _p(rng_step), _stream())
+                heads, _dtype_code(q), float(p_drop), seed, offset, _p(rng_step), _p(_work(plan)), _stream())
         _lib.check(rc, "alignn_lgattn_bwd_dst")
         with _Launch("edgeattn_bwd_src", 1, (n_nodes, n_edges, hidden, heads, q.element_size())):
             rc = lib.alignn_edgeattn_bwd_src_lp(_p(dagg_lp), _p(q), _ld(q), _p(coef), _p(plan.rowptr_t), _p(plan.col_t),

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define ALIGNN_ABI_VERSION 12
+#define ALIGNN_ABI_VERSION 13
 
 #define ALIGNN_F32 0
 #define ALIGNN_BF16 1
@@ -221,7 +221,11 @@ int alignn_edgeattn_mma_bwd_dst_s(const float *dagg, const void *dagg_lp, const 
  * inside the kernel instead of being read as a [L, 256] tensor (see csrc/lgattn.cu).  Same outputs as
  * alignn_edgeattn_fwd; qt / abar are addressed as base[row * ld + head * hs + channel]; `rng_step` (optional device
  * counter) is added to `offset` so that a captured CUDA graph draws fresh dropout masks on every replay.
- *   alignn_lg_pack_angles : a_csr[p] = (bf16(a[eid[p], :]), 1, 0...)  -- [L, 16] bf16 in target-sorted order. */
+ *   alignn_lg_pack_angles : a_csr[p] = (bf16(a[eid[p], :]), 1, 0...)  -- [L, 16] bf16 in target-sorted order.
+ * `work`: 8 bytes of device memory, ZERO on entry; the kernels leave it zero on exit (dynamic row-range scheduler: a
+ * persistent grid of one CTA per SM whose warps draw units of ~128 edges from this counter, so rows of very different
+ * in-degree balance; every row is still reduced by one warp in CSR order, results do not depend on the schedule).
+ * One buffer per stream: launches that may run concurrently must not share it. */
 int alignn_lgattn_supported(int hidden, int heads, int in_dim, int dtype);
 int alignn_lg_pack_angles(const float *a, const int32_t *eid, void *a_csr, int64_t n_edges, int in_dim, void *stream);
 int alignn_lgattn_fwd(const void *q, const void *k, const void *v, int64_t ldq, int64_t ldk, int64_t ldv,
@@ -231,7 +235,7 @@ int alignn_lgattn_fwd(const void *q, const void *k, const void *v, int64_t ldq, 
                       float *aggv, void *abar, int64_t ldab, int64_t hsab,
                       float *stat_m, float *stat_z, float *stat_s,
                       int64_t n_nodes, int64_t n_edges, int hidden, int heads, int dtype,
-                      float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step, void *stream);
+                      float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step, void *work, void *stream);
 
 /* Backward of alignn_lgattn_fwd w.r.t. q (dq), qt (bbar) and -- through coef, consumed by alignn_edgeattn_bwd_src with
  * the plan's CSC->CSR position map in place of eid_t -- k, v.  coef: f32 [L, 8] in target-sorted order, (a~_0..3,
@@ -243,7 +247,7 @@ int alignn_lgattn_bwd_dst(const float *dagg, const void *dagg_lp, const float *a
                           const float *stat_m, const float *stat_z, const int32_t *rowptr, const int32_t *col,
                           void *dq, int64_t lddq, void *bbar, int64_t ldbb, int64_t hsbb, float *coef,
                           int64_t n_nodes, int64_t n_edges, int hidden, int heads, int dtype,
-                          float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step, void *stream);
+                          float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step, void *work, void *stream);
 /* ... the gradient of the first angle-encoder Linear (reference scripts/train.py:360) is formed once per step from the
  * coefficients of all (<= 4 per call) line-graph layers: out[r*256 + c] = dW1[c, r] (r < in_dim), out[in_dim*256 + c] =
  * db1[c].  coef / qt / gt are HOST arrays of n_layers device pointers; partials: f32
