@@ -121,11 +121,11 @@ __device__ __forceinline__ void gather_rows(uint32_t tile, const __nv_bfloat16 *
                                             int lane) {
     const char *base = reinterpret_cast<const char *>(src) + lane * 16;
     const uint32_t dst = tile + lane * 16;
-    const int stride = ld * 2;
+    const uint32_t stride = (uint32_t)ld * 2u;
 #pragma unroll
     for (int u = 0; u < LG_E; ++u) {
-        const int ju = __shfl_sync(FULL, jmine, u);
-        if (u < n) cp_async16(dst + u * LG_ROWB, base + (int64_t)ju * stride);
+        const uint32_t ju = (uint32_t)__shfl_sync(FULL, jmine, u);     // ids are non-negative: one IMAD.WIDE.U32 per row
+        if (u < n) cp_async16(dst + u * LG_ROWB, base + (uint64_t)ju * stride);
     }
 }
 

@@ -1,5 +1,6 @@
 """Time the line-graph kernels of the fused trunk alone at BASELINE config-2 size (also the ncu target).
-usage: python scripts/prof_lgattn.py [pyg|bonds] [iters]"""
+usage: python scripts/prof_lgattn.py [pyg|bonds] [iters] [active]   ("active": run on the active prefix of bond rows only,
+as the trunk program does with PyG-collated batches)"""
 import os, sys, statistics
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -11,8 +12,9 @@ mode = sys.argv[1] if len(sys.argv) > 1 else "pyg"
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 dev, dt = "cuda", torch.bfloat16
 b = pkg.synthetic_batch(256, 32, 12, seed=0, lg_inc=mode)
-n, e, H, h = b.edge_index.size(1), b.lg_edge_index.size(1), 256, 4
-plan = pkg.build_plan(b.lg_edge_index.to(dev), n)
+n_all, e, H, h = b.edge_index.size(1), b.lg_edge_index.size(1), 256, 4
+plan = pkg.build_plan(b.lg_edge_index.to(dev), n_all)
+n = b.lg_active_rows if (len(sys.argv) > 3 and sys.argv[3] == "active") else n_all
 g = torch.Generator(device=dev).manual_seed(0)
 proj = (torch.randn(n, 8 * H, device=dev, generator=g) * 0.5).to(dt)
 dbuf = torch.empty(n, 9 * H, device=dev, dtype=dt)
@@ -60,5 +62,5 @@ by = {"lgattn_fwd": lgattn_bytes("lgattn_fwd", n, e, H, h, 2), "lgattn_bwd_dst":
       "colsum": 2 * 8 * H * n, "lg_angle_grad": 4 * (2 * 2 * h * H * n + 32 * e) + 32 * e}
 for name in ("lgattn_fwd", "lgattn_bwd_dst", "edgeattn_bwd_src", "gate_ln_fwd", "gate_ln_bwd", "colsum", "lg_angle_grad"):
     ms = statistics.median(x[0] for x in d[name])
-    print(f"{mode} {name:18s} {ms * 1e3:8.1f} us   algorithmic {by[name] / 1e6:8.1f} MB  -> {by[name] / ms / 1e6:7.0f} GB/s "
+    print(f"{mode} n={n} {name:18s} {ms * 1e3:8.1f} us   algorithmic {by[name] / 1e6:8.1f} MB  -> {by[name] / ms / 1e6:7.0f} GB/s "
           f"({by[name] / ms / 1e6 / peak:.3f} of measured HBM peak {peak:.0f})")
