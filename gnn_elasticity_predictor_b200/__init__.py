@@ -8,10 +8,12 @@ from .modules import (AlignnRegressor, EdgeUpdateBlock, HeteroAlignnRegressor, N
 from .ops import (GraphPlan, build_plan, build_pool_plan, conv_core, gate_ln_relu_residual,  # noqa: F401
                   segment_mean)
 from .synthetic import GraphBatch, collate, make_crystal, synthetic_batch, zscore_targets  # noqa: F401
+from .batching import bucket_shape, pad_batch, round_up_bucket  # noqa: F401
 
 __all__ = [
     "AlignnRegressor", "EdgeUpdateBlock", "HeteroAlignnRegressor", "NodeUpdateBlock", "TransformerConv",
     "gaussian_nll_loss", "GraphPlan", "build_plan", "build_pool_plan", "conv_core", "gate_ln_relu_residual",
-    "segment_mean", "GraphBatch", "collate", "make_crystal", "synthetic_batch", "zscore_targets",
+    "segment_mean", "GraphBatch", "collate", "make_crystal", "synthetic_batch", "zscore_targets", "bucket_shape", "pad_batch",
+    "round_up_bucket",
 ]
 __version__ = "0.1.0"

@@ -163,8 +163,8 @@ __global__ void plan_finish_kernel(const int32_t *__restrict__ keys, const int32
     if (p >= n_edges) return;
     const int32_t id = vals[p];
     const bool live = keys[p] < n_nodes;
-    eid[p] = live ? id : 0;
-    col[p] = live ? (int32_t)other_row[id] : 0;
+    eid[p] = id;                                       // dropped edges keep their id: eid stays a permutation of [0, Ne)
+    col[p] = live ? (int32_t)other_row[id] : 0;        // ... and get a safe endpoint (never visited: beyond rowptr[Nn])
 }
 
 static inline int num_sort_tiles(int64_t n) { return (int)((n + SORT_TILE - 1) / SORT_TILE); }

@@ -31,6 +31,7 @@ from . import _lib, ops
 from .dp import FlatGradBucket
 from .modules import HeteroAlignnRegressor, gaussian_nll_loss
 from .synthetic import GraphBatch
+from . import batching
 
 _P = ops._p
 
@@ -79,7 +80,7 @@ class FusedAdamW:
 
 
 class _Captured:
-    __slots__ = ("graph", "graph_opt", "batch", "tz", "loss", "mean", "logvar", "kernels")
+    __slots__ = ("graph", "graph_opt", "batch", "tz", "mask", "loss", "mean", "logvar", "kernels")
 
 
 class TrainStep:
@@ -91,7 +92,7 @@ class TrainStep:
     def __init__(self, model: HeteroAlignnRegressor, lr: float = 1e-3, lr_sigma: Optional[float] = None,
                  weight_decay: float = 1e-4, max_norm: float = 5.0, log_sigma_l2: float = 0.1,
                  min_logvar_floor: float = -2.9, loss_scale: float = 1.0, graph: bool = True, graph_warmup: int = 2,
-                 optimizer: bool = True, group=None):
+                 optimizer: bool = True, group=None, pad_to_buckets: bool = False, bucket_align: int = 256):
         self.model = model
         params = [p for p in model.parameters() if p.requires_grad]
         if not params or not params[0].is_cuda:
@@ -117,17 +118,18 @@ class TrainStep:
         self.use_graph, self.graph_warmup, self.group = bool(graph), int(graph_warmup), group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.rng_step = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self.pad_to_buckets, self.bucket_align = bool(pad_to_buckets), int(bucket_align)
         self._captured: Dict[Tuple, _Captured] = {}
         self._seen: Dict[Tuple, int] = {}
         self.replays = 0
         self.eager_steps = 0
 
     # -- the step itself (eager; also what gets captured) ------------------------------------------------------
-    def _fwd_bwd(self, batch, tz: Tensor):
+    def _fwd_bwd(self, batch, tz: Tensor, mask: Optional[Tensor] = None):
         self.bucket.detach_grads()
         self.model.base.build_plans(batch)                 # CSR/CSC sorts of this batch: part of every step
         mean, logvar = self.model(batch)
-        loss = gaussian_nll_loss(mean.float(), logvar.float(), tz, self.log_sigma_l2, self.floor)
+        loss = gaussian_nll_loss(mean.float(), logvar.float(), tz, self.log_sigma_l2, self.floor, mask=mask)
         (loss * self.loss_scale).backward()
         self.bucket.gather()                               # one multi-tensor copy into the flat gradient bucket
         return loss.detach(), mean.detach(), logvar.detach()
@@ -137,10 +139,10 @@ class TrainStep:
             self.opt.step()
         self.rng_step.add_(1)
 
-    def _eager(self, batch, tz):
+    def _eager(self, batch, tz, mask=None):
         prev, ops.RNG_STEP = ops.RNG_STEP, self.rng_step
         try:
-            out = self._fwd_bwd(batch, tz)
+            out = self._fwd_bwd(batch, tz, mask)
             if self.world > 1:
                 self.bucket.all_reduce(self.group)
             self._finish()
@@ -155,20 +157,21 @@ class TrainStep:
         return tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(batch.tensors().items())) + (
             batch.num_graphs, getattr(batch, "lg_active_rows", None))
 
-    def _capture(self, batch: GraphBatch, tz: Tensor) -> _Captured:
+    def _capture(self, batch: GraphBatch, tz: Tensor, mask: Optional[Tensor] = None) -> _Captured:
         cap = _Captured()
         cap.batch = batch._like()
         for k in GraphBatch._TENSORS:
             v = getattr(batch, k)
             setattr(cap.batch, k, v.clone() if isinstance(v, Tensor) else v)
         cap.tz = tz.clone()
+        cap.mask = None if mask is None else mask.clone()
         prev, ops.RNG_STEP = ops.RNG_STEP, self.rng_step
         torch.cuda.synchronize(self.dev)
         k0 = ops.STATS.kernels
         try:
             cap.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(cap.graph):
-                cap.loss, cap.mean, cap.logvar = self._fwd_bwd(cap.batch, cap.tz)
+                cap.loss, cap.mean, cap.logvar = self._fwd_bwd(cap.batch, cap.tz, cap.mask)
                 if self.world == 1:
                     self._finish()
             cap.graph_opt = None
@@ -182,20 +185,31 @@ class TrainStep:
         ops.STATS.kernels = k0
         return cap
 
-    def step(self, batch, target_z: Tensor):
+    def step(self, batch, target_z: Tensor, mask: Optional[Tensor] = None):
+        """``mask`` (``[B]``, 1 = real graph) restricts the loss to real graphs.  With ``pad_to_buckets`` a ``GraphBatch``
+        is padded to its shape bucket first (``batching.pad_batch``), so ragged datasets replay one graph per bucket; the
+        returned ``mean / logvar`` then have the bucket's graph count (real graphs first)."""
+        if self.pad_to_buckets and isinstance(batch, GraphBatch) and not getattr(batch, "padded", False):
+            n_real = batch.num_graphs
+            batch, mask = batching.pad_batch(batch, align=self.bucket_align)
+            tz = torch.zeros(batch.num_graphs, target_z.size(1), dtype=target_z.dtype, device=target_z.device)
+            tz[:n_real] = target_z
+            target_z = tz
         if not self.use_graph or not isinstance(batch, GraphBatch):
-            return self._eager(batch, target_z)
-        sig = self.signature(batch)
+            return self._eager(batch, target_z, mask)
+        sig = self.signature(batch) + (mask is not None,)
         cap = self._captured.get(sig)
         if cap is None:
             seen = self._seen.get(sig, 0)
             self._seen[sig] = seen + 1
             if seen < self.graph_warmup:
-                return self._eager(batch, target_z)
-            cap = self._captured[sig] = self._capture(batch, target_z)
+                return self._eager(batch, target_z, mask)
+            cap = self._captured[sig] = self._capture(batch, target_z, mask)
         for k, v in cap.batch.tensors().items():
             v.copy_(getattr(batch, k), non_blocking=True)
         cap.tz.copy_(target_z, non_blocking=True)
+        if mask is not None:
+            cap.mask.copy_(mask, non_blocking=True)
         cap.graph.replay()
         if cap.graph_opt is not None:
             self.bucket.all_reduce(self.group)

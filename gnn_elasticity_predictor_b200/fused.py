@@ -228,7 +228,7 @@ class _AttnBlock(torch.autograd.Function):
                 lg.coefs, lg.qts, lg.gts = [], [], []
         elif cfg.strided:
             bbar = torch.empty(h, n, hid, dtype=cd, device=agg.device)
-            df_out = torch.empty_like(feat)
+            df_out = torch.zeros_like(feat)       # rows of edges the plan dropped (padding) are never written
             ops.raw_attn_bwd_s(dagg, dagg_lp, agg, q, k, v, qt, gt, cv, feat, m, z, plan, h, dq, dk, dv, bbar, df_out,
                                cfg.p_attn, cfg.seed_attn, cfg.off_attn, rs)
         else:
@@ -238,11 +238,11 @@ class _AttnBlock(torch.autograd.Function):
                 first = acc.visits == 0
                 acc.visits += 1
                 if acc.buf is None:
-                    acc.buf = torch.empty_like(feat)
+                    acc.buf = torch.zeros_like(feat)
                 df_in, df_out = (None if first else acc.buf), acc.buf
                 relu_mask = cfg.is_last_visitor
             else:
-                df_in, df_out = None, torch.empty_like(feat)
+                df_in, df_out = None, torch.zeros_like(feat)
             bbar = ops.raw_edgeattn_bwd(dagg, dagg_lp, agg, q, k, v, qt, gt, cv, feat, m, z, plan, h, dq, dk, dv, df_in,
                                         df_out, relu_mask, cfg.p_attn, cfg.seed_attn, cfg.off_attn)
 
@@ -365,7 +365,7 @@ class _AttnBlock8(torch.autograd.Function):
                 dw1, db1 = ops.raw_lg_angle_grad(lg.a_csr, lg.w1, lg.b1, plan, lg.coefs, lg.qts, lg.gts)
                 lg.coefs, lg.qts, lg.gts = [], [], []
         else:
-            df_out = torch.empty_like(feat)
+            df_out = torch.zeros_like(feat)       # rows of edges the plan dropped (padding) are never written
             ops.raw_attn_bwd_s(dagg, dagg_lp, agg, q, k, v, qt, gt, cv, feat, m, z, plan, h, dq, dk, dv, bbar, df_out,
                                cfg.p_attn, cfg.seed_attn, cfg.off_attn, rs)
 

@@ -378,7 +378,7 @@ class AlignnRegressor(nn.Module):
                 lg_active = getattr(data, "lg_active_rows", None)
                 node32 = self._run_fused_trunk(node32, node_b0, edge32, edge_b0, lg, lg_plan, g_plan, w2, b2,
                                                -1 if lg_active is None or not getattr(self, "elide_isolated", True)
-                                               else int(lg_active))
+                                               else int(lg_active), zero_df=bool(getattr(data, "padded", False)))
                 return self._head_features(node32, data, pool_plan)
             accum = FeatGradAccumulator(n_layers) if run_lg and lg is None else None
 
@@ -414,7 +414,8 @@ class AlignnRegressor(nn.Module):
             return self._head_features(node32, data, pool_plan)
 
     def _run_fused_trunk(self, node32: Tensor, node_b: Tensor, edge32: Tensor, edge_b: Tensor, lg: LgShared,
-                         lg_plan: GraphPlan, g_plan: GraphPlan, w2: Tensor, b2: Tensor, lg_active: int = -1) -> Tensor:
+                         lg_plan: GraphPlan, g_plan: GraphPlan, w2: Tensor, b2: Tensor, lg_active: int = -1,
+                         zero_df: bool = False) -> Tensor:
         """All blocks as one explicit forward / backward program (``trunk.py``).  The weight folds of every block are
         batched here under autograd: ``Wc = W_e W2`` (line graph, second angle-encoder Linear folded into ``lin_edge``),
         ``Wc = W_e W_p`` (atom graph, ``edge_proj`` folded), and the query-side fold ``Wc[t]^T Wq_t`` that turns
@@ -454,7 +455,8 @@ class AlignnRegressor(nn.Module):
             keys.append((sa, oa, so, oo))
         cfg = trunk_mod.TrunkCfg(heads=h, n_layers=nl, eps=[b.norm.eps for b in blocks], p_attn=p_attn, p_out=p_out,
                                  keys=keys, lg_plan=lg_plan, g_plan=g_plan, a_csr=lg.a_csr, w1=lg.w1, b1=lg.b1,
-                                 lg_active=lg_active, overlap=bool(getattr(self, "overlap_streams", True)))
+                                 lg_active=lg_active, overlap=bool(getattr(self, "overlap_streams", True)),
+                                 zero_df=zero_df)
         enc = self.angle_encoder
         return trunk_mod.run_trunk(node32, node_b, edge32, edge_b, w8, b8, wc, cvec, wbeta, gamma, beta_ln,
                                    enc[0].weight, enc[0].bias, cfg)
@@ -513,13 +515,23 @@ class HeteroAlignnRegressor(nn.Module):
 
 
 def gaussian_nll_loss(mean: Tensor, logvar: Tensor, target_z: Tensor, log_sigma_l2: float = 0.1,
-                      min_logvar_floor: float = -2.9) -> Tensor:
+                      min_logvar_floor: float = -2.9, mask: Optional[Tensor] = None) -> Tensor:
     """The training loss of the reference's ``train_epoch_hetero`` without sample weights
-    (``scripts/train.py:655-681``; ``--log-sigma-l2`` default 0.1 at ``:1164``, floor ``:39``)."""
+    (``scripts/train.py:655-681``; ``--log-sigma-l2`` default 0.1 at ``:1164``, floor ``:39``).
+
+    ``mask`` (``[B]``, 1 = real graph): means run over the real graphs only -- the dummy graphs of a padded batch
+    (``batching.pad_batch``) contribute nothing."""
     lv = torch.clamp(logvar, min=min_logvar_floor)
     diff = mean - target_z.to(mean.dtype)
     nll = 0.5 * (lv + diff.pow(2) / torch.exp(lv))
-    loss = nll.mean(dim=1).mean()
+    if mask is None:
+        loss = nll.mean(dim=1).mean()
+        if log_sigma_l2 > 0.0:
+            loss = loss + float(log_sigma_l2) * (0.5 * lv).pow(2).mean()
+        return loss
+    w = mask.to(nll.dtype).unsqueeze(1)
+    n_real = w.sum().clamp(min=1.0)
+    loss = (nll.mean(dim=1, keepdim=True) * w).sum() / n_real
     if log_sigma_l2 > 0.0:
-        loss = loss + float(log_sigma_l2) * (0.5 * lv).pow(2).mean()
+        loss = loss + float(log_sigma_l2) * ((0.5 * lv).pow(2) * w).sum() / (n_real * lv.size(1))
     return loss

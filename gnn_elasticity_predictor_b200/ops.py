@@ -218,7 +218,7 @@ class _ConvCore(torch.autograd.Function):
         n_edges = int(e.size(0))
         dagg = dagg.contiguous().float()
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-        de = torch.empty_like(e)
+        de = torch.zeros_like(e)                 # rows of edges the plan dropped (padding) are never written
         coef = torch.empty(max(n_edges, 1), 2 * ctx.heads, dtype=torch.float32, device=q.device)
         with torch.cuda.device(q.device), _Launch("conv_bwd", 2, (n_nodes, n_edges, hidden, ctx.heads, q.element_size())):
             rc = lib.alignn_conv_bwd(_p(dagg), _p(agg), _p(q), _p(k), _p(v), _p(e), _p(stat_m), _p(stat_z),

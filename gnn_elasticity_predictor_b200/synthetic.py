@@ -69,10 +69,12 @@ class GraphBatch:
         lg = self.lg_edge_index
         self.lg_active_rows = (int(lg.max()) + 1 if lg.numel() > 0 else 0) if isinstance(lg, Tensor) and not lg.is_cuda \
             else None
+        self.padded = False                 # True for batches produced by batching.pad_batch (index -1 = padding)
 
     def _like(self) -> "GraphBatch":
         out = GraphBatch.__new__(GraphBatch)
         out.num_graphs, out.lg_inc, out.lg_active_rows = self.num_graphs, self.lg_inc, self.lg_active_rows
+        out.padded = getattr(self, "padded", False)
         return out
 
     def to(self, device, non_blocking: bool = False) -> "GraphBatch":

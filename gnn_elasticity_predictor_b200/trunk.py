@@ -55,6 +55,7 @@ class TrunkCfg:
     want_node_lp: bool = False
     lg_active: int = -1                  # bond rows >= lg_active are isolated in the line graph (< 0: unknown, all active)
     overlap: bool = True                 # run the atom-graph chain on a second stream (fork/join; capturable)
+    zero_df: bool = False                # padded batches: bond rows that are no atom-graph edge get no df write
 
 
 _SIDE_STREAMS = {}
@@ -220,7 +221,8 @@ class _Trunk(torch.autograd.Function):
 
         main = torch.cuda.current_stream()
         side = _side_stream(dev) if cfg.overlap else None
-        tails = [torch.empty(n_bonds, 2 * hid, dtype=cd, device=dev) for _ in range(nl)]   # LG block l: dx_r | df_l
+        mk = torch.zeros if cfg.zero_df else torch.empty
+        tails = [mk(n_bonds, 2 * hid, dtype=cd, device=dev) for _ in range(nl)]            # LG block l: dx_r | df_l
         if side is not None:
             side.wait_stream(main)
             for t in tails + [dn, d_w8, d_b8, d_wc, d_par, eye]:

@@ -57,7 +57,10 @@ const char *alignn_error_string(int code);
  *
  * edge_index : int64 [2, n_edges] (row 0 = source, row 1 = target), as PyG stores it.
  * status     : int32[1]; set to 1 if any index lies outside [0, n_nodes) (such edges are dropped
- *              from the plan -- the caller decides whether to read the flag).
+ *              from the plan -- the caller decides whether to read the flag).  Dropped edges sort after
+ *              rowptr[n_nodes] in input order; eid / eid_t stay permutations of [0, n_edges) and col / col_t
+ *              hold 0 there.  Shape-bucket padding (batching.py) relies on this: padded edges carry the
+ *              index -1 and are never visited by any kernel.
  */
 size_t alignn_plan_workspace_bytes(int64_t n_edges, int64_t n_nodes);
 int alignn_build_plan(const int64_t *edge_index, int64_t n_edges, int64_t n_nodes,

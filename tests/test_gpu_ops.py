@@ -73,6 +73,9 @@ def test_plan_flags_out_of_range_and_drops_those_edges():
         plan.check()
     assert plan.rowptr.cpu().tolist() == [0, 0, 1, 2]          # only edges 0 and 1 are in range
     assert plan.eid.cpu().tolist()[:2] == [0, 1]
+    # dropped edges stay in the permutation (after the live ones, in input order) with a safe endpoint
+    assert plan.eid.cpu().tolist() == [0, 1, 2, 3, 4] and plan.col.cpu().tolist()[2:] == [0, 0, 0]
+    assert sorted(plan.eid_t.cpu().tolist()) == [0, 1, 2, 3, 4]
 
 
 # ---- conv core ------------------------------------------------------------------------------------------
