@@ -58,6 +58,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-optimizer", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run every step eagerly (no CUDA-graph replay)")
+    ap.add_argument("--placement", choices=["dp", "members"], default="dp",
+                    help="N>1: 'dp' shards graph batches of one member (gradient all-reduce); 'members' trains a different "
+                         "ensemble member on every rank (reference trains members sequentially, train.py:2052), no exchange")
     return ap.parse_args()
 
 
@@ -263,14 +266,20 @@ def main_b200(args):
 
     # members (reference: --ensemble-size 5, seeds seed + 1007*i, train.py:2053)
     members, steppers = [], []
-    for m in range(args.members):
+    member_ids = list(range(args.members))
+    if args.placement == "members" and world > 1:
+        member_ids = dp.member_placement(max(args.members, world), world)[rank]      # this rank's own members
+        args.members = len(member_ids)
+    for m in member_ids:
         torch.manual_seed(42 + 1007 * m)
         model = pkg.HeteroAlignnRegressor(pkg.AlignnRegressor(dropout=args.dropout, **ARCH), ARCH["target_dim"]).to(dev)
         model.base.compute_dtype = cd
         model.train()
         members.append(model)
-        steppers.append(engine.TrainStep(model, lr=1e-3, weight_decay=1e-4, max_norm=5.0, loss_scale=1.0 / world,
-                                         graph=not args.no_graph, optimizer=not args.no_optimizer))
+        dp_mode = args.placement == "dp"
+        steppers.append(engine.TrainStep(model, lr=1e-3, weight_decay=1e-4, max_norm=5.0,
+                                         loss_scale=1.0 / world if dp_mode else 1.0, graph=not args.no_graph,
+                                         optimizer=not args.no_optimizer, data_parallel=dp_mode))
 
     host_batches = [pkg.synthetic_batch(n_graphs, atoms, k, seed=1000 * rank + i, lg_inc=args.lg_inc).pin_memory()
                     for i in range(2)]
@@ -465,8 +474,10 @@ def main_b200(args):
                             f"(N={sizes['N']}, E={sizes['E']}, L={sizes['L']}), one ensemble member per step, "
                             f"{args.members} members cycled",
                 "arch": ARCH, "dropout": args.dropout, "lg_inc": args.lg_inc, "global_batch": n_graphs * world,
-                "parallelism": f"dp{world}" if world > 1 else "single",
-                "step": "plan(CSR/CSC sort) + fwd + Gaussian NLL + bwd" + (" + NCCL allreduce(flat grads)" if world > 1 else "")
+                "parallelism": (f"dp{world}" if args.placement == "dp" else f"member-per-gpu x{world}") if world > 1
+                               else "single",
+                "step": "plan(CSR/CSC sort) + fwd + Gaussian NLL + bwd"
+                        + (" + NCCL allreduce(flat grads)" if world > 1 and args.placement == "dp" else "")
                         + ("" if args.no_optimizer else " + global-norm clip 5.0 + AdamW (one fused kernel pair)")
                         + ("; whole step replayed as one CUDA graph per member" if graphed else "; eager launches"),
                 "l2": "per-step working set (>= 3 GB of edge projections) >> 126 MB L2; no explicit flush",

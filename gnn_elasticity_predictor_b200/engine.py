@@ -92,7 +92,8 @@ class TrainStep:
     def __init__(self, model: HeteroAlignnRegressor, lr: float = 1e-3, lr_sigma: Optional[float] = None,
                  weight_decay: float = 1e-4, max_norm: float = 5.0, log_sigma_l2: float = 0.1,
                  min_logvar_floor: float = -2.9, loss_scale: float = 1.0, graph: bool = True, graph_warmup: int = 2,
-                 optimizer: bool = True, group=None, pad_to_buckets: bool = False, bucket_align: int = 256):
+                 optimizer: bool = True, group=None, pad_to_buckets: bool = False, bucket_align: int = 256,
+                 data_parallel: bool = True):
         self.model = model
         params = [p for p in model.parameters() if p.requires_grad]
         if not params or not params[0].is_cuda:
@@ -116,7 +117,8 @@ class TrainStep:
                               n_active=n_active) if optimizer else None
         self.log_sigma_l2, self.floor, self.loss_scale = float(log_sigma_l2), float(min_logvar_floor), float(loss_scale)
         self.use_graph, self.graph_warmup, self.group = bool(graph), int(graph_warmup), group
-        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        # data_parallel=False: this rank trains its own ensemble member (member-per-GPU placement), no gradient exchange
+        self.world = dist.get_world_size(group) if (data_parallel and dist.is_available() and dist.is_initialized()) else 1
         self.rng_step = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self.pad_to_buckets, self.bucket_align = bool(pad_to_buckets), int(bucket_align)
         self._captured: Dict[Tuple, _Captured] = {}
@@ -217,3 +219,67 @@ class TrainStep:
         self.replays += 1
         ops.STATS.kernels += cap.kernels
         return cap.loss, cap.mean, cap.logvar
+
+
+class EnsemblePredictor:
+    """All ensemble members on one batch + mixture moments as ONE replayed CUDA graph per batch signature -- the member
+    loops of ``ensemble_collect`` (reference ``scripts/train.py:876-894``), ``predict.ensemble_predict``
+    (``scripts/predict.py:604-623``) and ``evaluate.collect_member_predictions`` (``scripts/evaluate.py:244-261``).
+
+    The graph plans are built once per batch and shared by the members.  ``compute_dtype``: ``torch.float32`` is what
+    ``predict.py`` / ``evaluate.py`` run; ``torch.bfloat16`` is what ``eval_epoch_hetero`` runs (``train.py:757``) and is
+    ~6x faster here (tensor-core kernels).  Returns ``(mean_z, var_z, std_z)``, each ``[B, T]`` fp32 (real graphs only
+    when the batch had to be padded)."""
+
+    def __init__(self, models, compute_dtype: torch.dtype = torch.float32, graph: bool = True, graph_warmup: int = 1,
+                 pad_to_buckets: bool = False, bucket_align: int = 256, min_logvar_floor: float = -2.9):
+        from . import ensemble
+        if not models:
+            raise ValueError("no ensemble members")
+        self._ensemble = ensemble
+        self.models = list(models)
+        for m in self.models:
+            m.eval()
+            m.base.compute_dtype = compute_dtype
+        self.dev = next(self.models[0].parameters()).device
+        self.use_graph, self.graph_warmup = bool(graph), int(graph_warmup)
+        self.pad_to_buckets, self.bucket_align, self.floor = bool(pad_to_buckets), int(bucket_align), float(min_logvar_floor)
+        self._captured, self._seen = {}, {}
+        self.replays = self.eager_calls = 0
+
+    @torch.no_grad()
+    def _forward(self, batch):
+        self.models[0].base.build_plans(batch)
+        return self._ensemble.ensemble_forward(self.models, batch, self.floor)
+
+    @torch.no_grad()
+    def predict(self, batch):
+        n_real = batch.num_graphs
+        if self.pad_to_buckets and isinstance(batch, GraphBatch) and not getattr(batch, "padded", False):
+            batch, _ = batching.pad_batch(batch, align=self.bucket_align)
+        if not self.use_graph or not isinstance(batch, GraphBatch):
+            self.eager_calls += 1
+            return tuple(t[:n_real] for t in self._forward(batch))
+        sig = TrainStep.signature(batch)
+        cap = self._captured.get(sig)
+        if cap is None:
+            seen = self._seen.get(sig, 0)
+            self._seen[sig] = seen + 1
+            if seen < self.graph_warmup:
+                self.eager_calls += 1
+                return tuple(t[:n_real] for t in self._forward(batch))
+            static = batch._like()
+            for k in GraphBatch._TENSORS:
+                v = getattr(batch, k)
+                setattr(static, k, v.clone() if isinstance(v, Tensor) else v)
+            torch.cuda.synchronize(self.dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self._forward(static)
+            cap = self._captured[sig] = (g, static, out)
+        g, static, out = cap
+        for k, v in static.tensors().items():
+            v.copy_(getattr(batch, k), non_blocking=True)
+        g.replay()
+        self.replays += 1
+        return tuple(t[:n_real] for t in out)

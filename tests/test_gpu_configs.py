@@ -73,3 +73,30 @@ def test_config5_ensemble_inference_fp32_vs_oracle():
     mean_z, var_z, std_z = ensemble.ensemble_forward(members, host.to(DEV))
     assert rel_err(mean_z, mu) < 1e-5 and rel_err(var_z, var) < 1e-5
     assert rel_err(std_z, var.clamp(min=1e-12).sqrt()) < 1e-5
+
+
+def test_ensemble_predictor_graph_replay_matches_eager_members():
+    from gnn_elasticity_predictor_b200 import engine
+    members = []
+    for i in range(3):
+        torch.manual_seed(7 + i)
+        members.append(pkg.HeteroAlignnRegressor(pkg.AlignnRegressor(dropout=0.15, **{**ARCH, "layers": 2}), 2).to(DEV))
+    pred = engine.EnsemblePredictor(members, compute_dtype=torch.bfloat16, graph=True, graph_warmup=1)
+    batches = [pkg.synthetic_batch(12, 16, 12, seed=s).to(DEV) for s in (0, 1, 2)]
+    for i, b in enumerate(batches + batches):
+        got = pred.predict(b)
+        want = ensemble.ensemble_forward(members, b)
+        for x, y in zip(got, want):
+            assert torch.equal(x, y), i                       # eval mode: no dropout, same kernels -> identical
+    assert pred.replays == 5 and pred.eager_calls == 1
+    # ragged batches through the bucket padding: real graphs' moments unchanged within bf16 tolerance
+    from test_batching import ragged_batch
+    ragged = engine.EnsemblePredictor(members, compute_dtype=torch.bfloat16, graph=True, graph_warmup=0, pad_to_buckets=True)
+    for seed, sizes in ((1, (8, 12, 10, 16, 9)), (2, (9, 11, 10, 16, 9))):
+        b = ragged_batch(seed, sizes=sizes).to(DEV)
+        got = ragged.predict(b)
+        want = ensemble.ensemble_forward(members, b)
+        assert got[0].shape == (5, 2)
+        for x, y in zip(got, want):
+            assert rel_err(x, y) < 2e-2
+    assert ragged.replays == 2 and len(ragged._captured) == 1
