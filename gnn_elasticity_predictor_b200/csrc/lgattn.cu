@@ -320,13 +320,12 @@ lgattn_fwd_kernel(const LgFwdParams P) {
         z0 = z0 * corr0 + (p00 + p10);
         z1 = z1 * corr1 + (p01 + p11);
         if (P.p_drop > 0.f) {
-            float d0[4], d1[4];
-            dropout_scale4(P.seed, rng_off, (uint64_t)(A.pos + g), P.p_drop, P.inv_keep, d0);
-            dropout_scale4(P.seed, rng_off, (uint64_t)(A.pos + g + 8), P.p_drop, P.inv_keep, d1);
-            p00 *= hsel ? d0[2] : d0[0];
-            p01 *= hsel ? d0[3] : d0[1];
-            p10 *= hsel ? d1[2] : d1[0];
-            p11 *= hsel ? d1[3] : d1[1];
+            float k00, k01, k10, k11;
+            dropout_scale_quad(P.seed, rng_off, (uint64_t)A.pos, g, q, P.p_drop, P.inv_keep, k00, k01, k10, k11);
+            p00 *= k00;
+            p01 *= k01;
+            p10 *= k10;
+            p11 *= k11;
         }
         zd0 = zd0 * corr0 + (p00 + p10);
         zd1 = zd1 * corr1 + (p01 + p11);
@@ -625,13 +624,7 @@ lgattn_bwd_kernel(const LgBwdParams P) {
         const float d10 = lo_half ? o[2] : c[2], d11 = lo_half ? o[3] : c[3];
         float dr00 = 1.f, dr01 = 1.f, dr10 = 1.f, dr11 = 1.f;
         if (P.p_drop > 0.f) {
-            float e0[4], e1[4];
-            dropout_scale4(P.seed, rng_off, (uint64_t)(A.pos + g), P.p_drop, P.inv_keep, e0);
-            dropout_scale4(P.seed, rng_off, (uint64_t)(A.pos + g + 8), P.p_drop, P.inv_keep, e1);
-            dr00 = hsel ? e0[2] : e0[0];
-            dr01 = hsel ? e0[3] : e0[1];
-            dr10 = hsel ? e1[2] : e1[0];
-            dr11 = hsel ? e1[3] : e1[1];
+            dropout_scale_quad(P.seed, rng_off, (uint64_t)A.pos, g, q, P.p_drop, P.inv_keep, dr00, dr01, dr10, dr11);
         }
         const bool v0 = g < n, v1 = g + 8 < n;
         const float a00 = v0 ? fast_exp2(sl00 * P.scale_log2 - mh0) * iz0 : 0.f;

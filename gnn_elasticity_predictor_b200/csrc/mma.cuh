@@ -97,4 +97,22 @@ __device__ __forceinline__ void dropout_scale4(uint64_t seed, uint64_t offset, u
     for (int t = 0; t < 4; ++t) out[t] = ((float)(bits[t] >> 8) * (1.0f / 16777216.0f)) < p ? 0.0f : inv_keep;
 }
 
+// Keep-scales of heads (hsel, hsel + 1), hsel = 2 * (q & 1), for the two edges a lane owns in the m16n8 fragment layout
+// (positions pos + g and pos + g + 8).  One Philox block yields the 4 heads of one edge, and the four lanes of a quad need
+// the same two edges: lanes q < 2 evaluate edge g, lanes q >= 2 edge g + 8, and partners (q ^ 2: same head pair) swap.
+// Half the generator work of calling dropout_scale4 twice per lane; identical masks.  Warp-uniform call sites only.
+__device__ __forceinline__ void dropout_scale_quad(uint64_t seed, uint64_t offset, uint64_t pos, int g, int q, float p,
+                                                   float inv_keep, float &lo0, float &lo1, float &hi0, float &hi1) {
+    const bool second = q >= 2;
+    float d[4];
+    dropout_scale4(seed, offset, pos + (uint64_t)(g + (second ? 8 : 0)), p, inv_keep, d);
+    const bool upper = (q & 1) != 0;
+    const float m0 = upper ? d[2] : d[0], m1 = upper ? d[3] : d[1];
+    const float o0 = __shfl_xor_sync(FULL, m0, 2), o1 = __shfl_xor_sync(FULL, m1, 2);
+    lo0 = second ? o0 : m0;
+    lo1 = second ? o1 : m1;
+    hi0 = second ? m0 : o0;
+    hi1 = second ? m1 : o1;
+}
+
 }  // namespace alignn
