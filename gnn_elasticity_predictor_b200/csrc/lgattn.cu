@@ -273,6 +273,10 @@ lgattn_fwd_kernel(const LgFwdParams P) {
             m0 = m1 = -INFINITY;
             z0 = z1 = zd0 = zd1 = 0.f;
         }
+        // dropout keep-scales depend on (seed, position) only: generated here, off the softmax -> phase-2 critical path
+        float k00 = 1.f, k01 = 1.f, k10 = 1.f, k11 = 1.f;
+        if (P.p_drop > 0.f)
+            dropout_scale_quad(P.seed, rng_off, (uint64_t)A.pos, g, q, P.p_drop, P.inv_keep, k00, k01, k10, k11);
         cp_async_wait<2>();   // K of this chunk (V of this chunk and K of the next may still be in flight)
         __syncwarp();
 
@@ -319,14 +323,10 @@ lgattn_fwd_kernel(const LgFwdParams P) {
         float p10 = fast_exp2(s10 - mn0), p11 = fast_exp2(s11 - mn1);
         z0 = z0 * corr0 + (p00 + p10);
         z1 = z1 * corr1 + (p01 + p11);
-        if (P.p_drop > 0.f) {
-            float k00, k01, k10, k11;
-            dropout_scale_quad(P.seed, rng_off, (uint64_t)A.pos, g, q, P.p_drop, P.inv_keep, k00, k01, k10, k11);
-            p00 *= k00;
-            p01 *= k01;
-            p10 *= k10;
-            p11 *= k11;
-        }
+        p00 *= k00;
+        p01 *= k01;
+        p10 *= k10;
+        p11 *= k11;
         zd0 = zd0 * corr0 + (p00 + p10);
         zd1 = zd1 * corr1 + (p01 + p11);
         if (!A.first) {
@@ -573,6 +573,9 @@ lgattn_bwd_kernel(const LgBwdParams P) {
             iz0 = 1.0f / (__ldg(P.stat_z + (int64_t)row * LG_HEADS + hsel) + 1e-16f);
             iz1 = 1.0f / (__ldg(P.stat_z + (int64_t)row * LG_HEADS + hsel + 1) + 1e-16f);
         }
+        float dr00 = 1.f, dr01 = 1.f, dr10 = 1.f, dr11 = 1.f;   // keep-scales: off the critical path (see forward)
+        if (P.p_drop > 0.f)
+            dropout_scale_quad(P.seed, rng_off, (uint64_t)A.pos, g, q, P.p_drop, P.inv_keep, dr00, dr01, dr10, dr11);
         cp_async_wait<1>();
         __syncwarp();
 
@@ -622,10 +625,6 @@ lgattn_bwd_kernel(const LgBwdParams P) {
         const float sl10 = lo_half ? c[2] : o[2], sl11 = lo_half ? c[3] : o[3];
         const float d00 = lo_half ? o[0] : c[0], d01 = lo_half ? o[1] : c[1];
         const float d10 = lo_half ? o[2] : c[2], d11 = lo_half ? o[3] : c[3];
-        float dr00 = 1.f, dr01 = 1.f, dr10 = 1.f, dr11 = 1.f;
-        if (P.p_drop > 0.f) {
-            dropout_scale_quad(P.seed, rng_off, (uint64_t)A.pos, g, q, P.p_drop, P.inv_keep, dr00, dr01, dr10, dr11);
-        }
         const bool v0 = g < n, v1 = g + 8 < n;
         const float a00 = v0 ? fast_exp2(sl00 * P.scale_log2 - mh0) * iz0 : 0.f;
         const float a01 = v0 ? fast_exp2(sl01 * P.scale_log2 - mh1) * iz1 : 0.f;
