@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes
 import os
 import threading
-from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
 from . import build as _build
 
@@ -17,12 +17,28 @@ _LIB = None
 
 _P = c_void_p
 
+
+class GraphStoreStruct(ctypes.Structure):
+    """``alignn_graph_store`` (include/alignn_b200.h)."""
+    _fields_ = ([(n, c_void_p) for n in ("x", "edge_attr", "lg_edge_attr", "global_x", "sg_one_hot", "y", "edge_index",
+                                         "lg_edge_index", "node_ptr", "bond_ptr", "angle_ptr")]
+                + [(n, c_int64) for n in ("n_graphs", "n_nodes", "n_bonds", "n_angles")]
+                + [(n, c_int32) for n in ("node_dim", "edge_dim", "angle_dim", "global_dim", "sg_dim", "target_dim")])
+
+
+class BatchOutStruct(ctypes.Structure):
+    """``alignn_batch_out`` (include/alignn_b200.h)."""
+    _fields_ = ([(n, c_void_p) for n in ("x", "edge_attr", "lg_edge_attr", "global_x", "sg_one_hot", "y", "edge_index",
+                                         "lg_edge_index", "batch", "train_idx")]
+                + [(n, c_int64) for n in ("n_graphs", "n_nodes", "n_bonds", "n_angles")])
+
 # name -> (restype, argtypes); mirrors include/alignn_b200.h one to one
 SIGNATURES = {
     "alignn_abi_version": (c_int, []),
     "alignn_error_string": (c_char_p, [c_int]),
     "alignn_plan_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "alignn_build_plan": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "alignn_build_plan_ex": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, c_int, _P]),
     "alignn_conv_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int,
                                 c_float, c_uint64, c_uint64, _P]),
     "alignn_conv_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
@@ -84,11 +100,16 @@ SIGNATURES = {
     "alignn_angle_h1_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
     "alignn_angle_partial_floats": (c_int64, [c_int]),
     "alignn_angle_h1_bwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
+    "alignn_collate": (c_int, [_P, _P, c_int64, c_int, _P, _P, _P, _P, _P, _P]),
+    "alignn_bond_features": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, _P, c_int, c_double, _P, _P, _P]),
+    "alignn_linegraph_count": (c_int, [_P, _P, _P, _P, c_int64, _P, _P]),
+    "alignn_linegraph_fill": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P, c_int, c_double, _P, c_int64,
+                                      _P, _P]),
     "alignn_segment_mean_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P]),
     "alignn_segment_mean_bwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P]),
 }
 
-ABI_VERSION = 13
+ABI_VERSION = 14
 F32, BF16 = 0, 1
 
 

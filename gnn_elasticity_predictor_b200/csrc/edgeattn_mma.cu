@@ -140,7 +140,6 @@ edgeattn_mma_fwd_kernel(const MmFwdParams P) {
     float m0 = -INFINITY, m1 = -INFINITY, z0 = 0.f, z1 = 0.f, zd0 = 0.f, zd1 = 0.f;
     int64_t next_unwritten = r0;
     const int t_own = g & 3;
-    const int hsel = 2 * (q & 1);   // head of column 2q (columns 4..7 repeat 0..3)
 
     for (int it = 0; !cons.done(); ++it) {
         const int s = it & 1;

@@ -254,7 +254,6 @@ lgattn_fwd_kernel(const LgFwdParams P) {
     float m0 = -INFINITY, m1 = -INFINITY, z0 = 0.f, z1 = 0.f, zd0 = 0.f, zd1 = 0.f;
     int next_unwritten = r0;
     const int t_own = g & 3;
-    const int hsel = 2 * (q & 1);
     B.n = 0; B.row = 0; B.pos = 0; B.first = false; B.last = false;
 
     for (int it = 0;; ++it) {

@@ -21,7 +21,7 @@ constexpr int SORT_PER_WARP = SORT_TILE / SORT_WARPS;
 __global__ void plan_prep_kernel(const int64_t *__restrict__ src_row, const int64_t *__restrict__ dst_row,
                                  int64_t n_edges, int64_t n_nodes, int32_t *__restrict__ key_dst,
                                  int32_t *__restrict__ key_src, int32_t *__restrict__ vals,
-                                 int32_t *__restrict__ status) {
+                                 int32_t *__restrict__ status, int check_src_sorted) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_edges) return;
     const int64_t s = src_row[e], d = dst_row[e];
@@ -29,7 +29,13 @@ __global__ void plan_prep_kernel(const int64_t *__restrict__ src_row, const int6
     key_dst[e] = ok ? (int32_t)d : (int32_t)n_nodes;
     key_src[e] = ok ? (int32_t)s : (int32_t)n_nodes;
     vals[e] = (int32_t)e;
-    if (!ok) *status = 1;  // benign race: every writer stores the same value
+    if (!ok) atomicOr(status, 1);
+    if (check_src_sorted && e > 0) {   // the caller's "already source-sorted" hint, verified on the sort KEYS
+        const int64_t sp = src_row[e - 1], dp = dst_row[e - 1];
+        const bool okp = sp >= 0 && sp < n_nodes && dp >= 0 && dp < n_nodes;
+        const int64_t kp = okp ? sp : n_nodes, kc = ok ? s : n_nodes;
+        if (kc < kp) atomicOr(status, 2);
+    }
 }
 
 __global__ void radix_hist_kernel(const int32_t *__restrict__ keys, int64_t n, int shift,
@@ -233,6 +239,15 @@ extern "C" int alignn_build_plan(const int64_t *edge_index, int64_t n_edges, int
                                  int32_t *rowptr, int32_t *col, int32_t *eid,
                                  int32_t *rowptr_t, int32_t *col_t, int32_t *eid_t,
                                  int32_t *status, void *workspace, size_t workspace_bytes, void *stream) {
+    return alignn_build_plan_ex(edge_index, n_edges, n_nodes, rowptr, col, eid, rowptr_t, col_t, eid_t, status, workspace,
+                                workspace_bytes, 0, stream);
+}
+
+extern "C" int alignn_build_plan_ex(const int64_t *edge_index, int64_t n_edges, int64_t n_nodes,
+                                    int32_t *rowptr, int32_t *col, int32_t *eid,
+                                    int32_t *rowptr_t, int32_t *col_t, int32_t *eid_t,
+                                    int32_t *status, void *workspace, size_t workspace_bytes, int flags, void *stream) {
+    const int src_sorted = flags & ALIGNN_PLAN_SOURCE_SORTED;
     if (n_edges < 0 || n_nodes < 0 || !rowptr || !rowptr_t || !status) return ALIGNN_ERR_BAD_ARG;
     if (n_edges >= ((int64_t)1 << 31) - SORT_TILE || n_nodes >= ((int64_t)1 << 31) - 1) return ALIGNN_ERR_BAD_SHAPE;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -249,7 +264,8 @@ extern "C" int alignn_build_plan(const int64_t *edge_index, int64_t n_edges, int
     const int64_t *src_row = edge_index, *dst_row = edge_index + n_edges;
     const int tb = 256;
     plan_prep_kernel<<<(unsigned)((n_edges + tb - 1) / tb), tb, 0, st>>>(src_row, dst_row, n_edges, n_nodes,
-                                                                          w.key_dst, w.key_src, w.vals0, status);
+                                                                          w.key_dst, w.key_src, w.vals0, status,
+                                                                          src_sorted);
     ALIGNN_LAUNCH_CHECK();
     const unsigned fin_blocks = (unsigned)((n_edges + tb - 1) / tb);
     const unsigned row_blocks = (unsigned)((n_nodes + 1 + tb - 1) / tb);
@@ -259,8 +275,13 @@ extern "C" int alignn_build_plan(const int64_t *edge_index, int64_t n_edges, int
     plan_rowptr_kernel<<<row_blocks, tb, 0, st>>>(sk, n_edges, n_nodes, rowptr);
     plan_finish_kernel<<<fin_blocks, tb, 0, st>>>(sk, sv, src_row, n_edges, n_nodes, col, eid);
     ALIGNN_LAUNCH_CHECK();
-    rc = radix_sort_pairs(w.key_src, w.vals0, w, n_edges, n_nodes, st, &sk, &sv);
-    if (rc != ALIGNN_OK) return rc;
+    if (src_sorted) {   // the stable source sort of a source-sorted list is the identity (verified in plan_prep_kernel)
+        sk = w.key_src;
+        sv = w.vals0;
+    } else {
+        rc = radix_sort_pairs(w.key_src, w.vals0, w, n_edges, n_nodes, st, &sk, &sv);
+        if (rc != ALIGNN_OK) return rc;
+    }
     plan_rowptr_kernel<<<row_blocks, tb, 0, st>>>(sk, n_edges, n_nodes, rowptr_t);
     plan_finish_kernel<<<fin_blocks, tb, 0, st>>>(sk, sv, dst_row, n_edges, n_nodes, col_t, eid_t);
     ALIGNN_LAUNCH_CHECK();

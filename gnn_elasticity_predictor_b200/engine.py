@@ -157,7 +157,7 @@ class TrainStep:
     @staticmethod
     def signature(batch) -> Tuple:
         return tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(batch.tensors().items())) + (
-            batch.num_graphs, getattr(batch, "lg_active_rows", None))
+            batch.num_graphs, getattr(batch, "lg_active_rows", None), getattr(batch, "source_sorted", None))
 
     def _capture(self, batch: GraphBatch, tz: Tensor, mask: Optional[Tensor] = None) -> _Captured:
         cap = _Captured()

@@ -466,8 +466,9 @@ class AlignnRegressor(nn.Module):
         layers and by backward.  Cached on the batch object (``data._alignn_plans``) when possible."""
         n_atoms, n_bonds = data.x.size(0), data.edge_index.size(1)
         v = self.validate_indices
-        lg_plan = ops.build_plan(data.lg_edge_index, n_bonds, validate=v) if n_bonds > 0 else None
-        g_plan = ops.build_plan(data.edge_index, n_atoms, validate=v)
+        g_sorted, lg_sorted = getattr(data, "source_sorted", (False, False))
+        lg_plan = ops.build_plan(data.lg_edge_index, n_bonds, validate=v, source_sorted=lg_sorted) if n_bonds > 0 else None
+        g_plan = ops.build_plan(data.edge_index, n_atoms, validate=v, source_sorted=g_sorted)
         n_graphs = getattr(data, "num_graphs", None)
         if n_graphs is None:
             n_graphs = int(data.batch.max()) + 1 if data.batch.numel() > 0 else 0

@@ -70,10 +70,18 @@ class GraphBatch:
         self.lg_active_rows = (int(lg.max()) + 1 if lg.numel() > 0 else 0) if isinstance(lg, Tensor) and not lg.is_cuda \
             else None
         self.padded = False                 # True for batches produced by batching.pad_batch (index -1 = padding)
+        # second host-side fact: are the source rows (edge_index[0], lg_edge_index[0]) already non-decreasing?  True for
+        # everything fetch.py emits (source-major loops, fetch.py:389-396, 421-444) and preserved by PyG's collate; the
+        # graph plan then skips the source sort (csrc/plan.cu verifies the hint on the device)
+        self.source_sorted = tuple(
+            bool(isinstance(t, Tensor) and not t.is_cuda and t.dim() == 2
+                 and (t.size(1) < 2 or bool((t[0, 1:] >= t[0, :-1]).all())))
+            for t in (self.edge_index, self.lg_edge_index))
 
     def _like(self) -> "GraphBatch":
         out = GraphBatch.__new__(GraphBatch)
         out.num_graphs, out.lg_inc, out.lg_active_rows = self.num_graphs, self.lg_inc, self.lg_active_rows
+        out.source_sorted = getattr(self, "source_sorted", (False, False))
         out.padded = getattr(self, "padded", False)
         return out
 

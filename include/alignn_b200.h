@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define ALIGNN_ABI_VERSION 13
+#define ALIGNN_ABI_VERSION 14
 
 #define ALIGNN_F32 0
 #define ALIGNN_BF16 1
@@ -56,7 +56,7 @@ const char *alignn_error_string(int code);
  * edge_index[1]).  Result is bit-identical to torch.sort(edge_index[k], stable=True).
  *
  * edge_index : int64 [2, n_edges] (row 0 = source, row 1 = target), as PyG stores it.
- * status     : int32[1]; set to 1 if any index lies outside [0, n_nodes) (such edges are dropped
+ * status     : int32[1] bit flags; bit 0 (value 1) is set if any index lies outside [0, n_nodes) (such edges are dropped
  *              from the plan -- the caller decides whether to read the flag).  Dropped edges sort after
  *              rowptr[n_nodes] in input order; eid / eid_t stay permutations of [0, n_edges) and col / col_t
  *              hold 0 there.  Shape-bucket padding (batching.py) relies on this: padded edges carry the
@@ -67,6 +67,17 @@ int alignn_build_plan(const int64_t *edge_index, int64_t n_edges, int64_t n_node
                       int32_t *rowptr, int32_t *col, int32_t *eid,
                       int32_t *rowptr_t, int32_t *col_t, int32_t *eid_t,
                       int32_t *status, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Same plan with hints.  ALIGNN_PLAN_SOURCE_SORTED: the caller states that edge_index[0] is already
+ * non-decreasing -- true for every graph `fetch.py:389-396,421-444` emits (bonds and angles are generated
+ * source-major) and for any PyG collate of such graphs -- so the stable source sort is the identity and the
+ * CSC half of the plan needs no radix passes.  The hint is VERIFIED on the device: if the sort keys are not
+ * non-decreasing, bit 1 (value 2) of `status` is set and the CSC half is invalid. */
+#define ALIGNN_PLAN_SOURCE_SORTED 1
+int alignn_build_plan_ex(const int64_t *edge_index, int64_t n_edges, int64_t n_nodes,
+                         int32_t *rowptr, int32_t *col, int32_t *eid,
+                         int32_t *rowptr_t, int32_t *col_t, int32_t *eid_t,
+                         int32_t *status, void *workspace, size_t workspace_bytes, int flags, void *stream);
 
 /* ---- fused edge-attention conv core, forward ----------------------------------------------------
  * Replaces `TransformerConv.message` + `utils.softmax` + 'add' aggregation (PyG 2.7.0; reference
@@ -334,6 +345,75 @@ int alignn_angle_h1_fwd(const float *a, const float *w1, const float *b1, void *
 int64_t alignn_angle_partial_floats(int in_dim);
 int alignn_angle_h1_bwd(const void *dpre, const float *a, float *partials, float *out, int64_t n_edges,
                         int in_dim, int hidden, int dtype, void *stream);
+
+/* ---- device-resident dataset: collate ---------------------------------------------------
+ * Replaces `PtGraphDataset.__getitem__` (reference scripts/train.py:130-172: one `torch.load` per sample per
+ * epoch) + the host collate of `torch_geometric.loader.DataLoader` (train.py:2037) for batches drawn from a
+ * store of graphs that already lives in HBM: all graphs concatenated field by field (the `Data` fields of
+ * scripts/fetch.py:614-651), indices LOCAL to each graph, `*_ptr` the per-graph row offsets.
+ *
+ * alignn_collate writes the batch PyG's default `Batch.from_data_list` would produce for the graphs
+ * `sel[0..n_sel)`, in that order: feature rows concatenated, `edge_index` shifted by the running ATOM count,
+ * `lg_edge_index` shifted by the running atom count too (`lg_inc_bonds = 0`: PyG's default `__inc__`, what the
+ * reference trains on -- SURVEY.md A9) or by the running BOND count (`lg_inc_bonds = 1`), `batch[n]` = position
+ * of the atom's graph in `sel`, `train_idx[g] = sel[g]`, per-graph rows gathered.  Output sizes in `out` may
+ * exceed the selection's totals (shape buckets): the tail is filled exactly like batching.pad_batch -- zero
+ * feature rows, index -1, padded atoms in graph `n_sel`, `y = 1`, `train_idx = -1`.  Any `out` pointer may be
+ * NULL (field skipped).  Bit-exact (copies and int64 adds only).
+ *
+ * seg_ptr : int64 [3, n_sel + 1] device scratch; on return the running atom / bond / angle counts.
+ * totals  : HOST int64[3]: the selection's atom / bond / angle totals (the caller knows them from its host copy
+ *           of the offsets -- it sized `out` with them); they size the launches and are re-derived on the device.
+ * maxima  : HOST int64[3]: upper bounds of the per-graph atom / bond / angle counts in the selection (grid sizing).
+ * status  : int32[1] bit flags: 1 = an entry of `sel` outside [0, n_graphs), 2 = the device-side totals differ from
+ *           `totals`, 4 = a graph larger than `maxima` (results still correct).  With 1 or 2 nothing is written. */
+typedef struct alignn_graph_store {
+    const float *x, *edge_attr, *lg_edge_attr, *global_x, *sg_one_hot, *y;
+    const int64_t *edge_index;    /* [2, n_bonds]  (row 1 at + n_bonds)  */
+    const int64_t *lg_edge_index; /* [2, n_angles] (row 1 at + n_angles) */
+    const int64_t *node_ptr, *bond_ptr, *angle_ptr; /* [n_graphs + 1] */
+    int64_t n_graphs, n_nodes, n_bonds, n_angles;
+    int32_t node_dim, edge_dim, angle_dim, global_dim, sg_dim, target_dim;
+} alignn_graph_store;
+
+typedef struct alignn_batch_out {
+    float *x, *edge_attr, *lg_edge_attr, *global_x, *sg_one_hot, *y;
+    int64_t *edge_index, *lg_edge_index, *batch, *train_idx;
+    int64_t n_graphs, n_nodes, n_bonds, n_angles; /* allocated sizes (>= the selection's totals) */
+} alignn_batch_out;
+
+int alignn_collate(const alignn_graph_store *store, const int64_t *sel, int64_t n_sel, int lg_inc_bonds,
+                   const alignn_batch_out *out, int64_t *seg_ptr, const int64_t *totals, const int64_t *maxima,
+                   int32_t *status, void *stream);
+
+/* ---- bond features and line graph on the device ---------------------------------------
+ * Replaces the two loops of `build_graph_from_structure` (reference scripts/fetch.py:385-396 bonds,
+ * :417-447 line graph) with their helpers `_edge_geom` (:250-263), `_angle_between_vectors` (:266-273) and
+ * `_rbf_expand` (:311-316).  Arithmetic in float64 in the reference's operation order, stored as float32 /
+ * int64 like `to_pyg_data` (:629-633).  Bonds are the reference's directed `(i, j, jimage)` list, i-major
+ * (:189-207), for one structure or for many concatenated ones (global atom ids; `atom_graph[a]` = structure of
+ * atom a selects its lattice; NULL = one structure).
+ *
+ * alignn_bond_features  : dirv [E,3] f64 (unit i->j, 0 for zero-length bonds), edge_attr [E, n_rbf + 4] f32 =
+ *                         exp(-gamma (dist - c_k)^2) | |EN_i - EN_j| | dirv.
+ * alignn_linegraph_count: counts[e1] = number of bonds (j -> k) leaving j = dst(e1) other than e1's exact reverse
+ *                         image; `out_ptr [A+1]` = first bond leaving each atom.
+ * alignn_linegraph_fill : with angle_ptr = exclusive scan of counts ([E+1]): lg_edge_index [2, L] (e1-major, then
+ *                         bond order -- the reference's emission order; ids minus graph_bond_ptr[structure] when
+ *                         that pointer is given, i.e. LOCAL ids) and lg_edge_attr [L, n_ang + 3] =
+ *                         exp(-gamma (angle - c_k)^2) | angle | cos | sin, angle at j between j->i and j->k. */
+int alignn_bond_features(const double *frac, const double *lattice, const int64_t *atom_graph, const double *en,
+                         const int64_t *bond_src, const int64_t *bond_dst, const int32_t *bond_image, int64_t n_bonds,
+                         const double *rbf_centers, int n_rbf, double rbf_gamma, double *dirv, float *edge_attr,
+                         void *stream);
+int alignn_linegraph_count(const int64_t *bond_src, const int64_t *bond_dst, const int32_t *bond_image,
+                           const int64_t *out_ptr, int64_t n_bonds, int64_t *counts, void *stream);
+int alignn_linegraph_fill(const double *frac, const double *lattice, const int64_t *atom_graph,
+                          const int64_t *graph_bond_ptr, const int64_t *bond_src, const int64_t *bond_dst,
+                          const int32_t *bond_image, const int64_t *out_ptr, const double *dirv,
+                          const int64_t *angle_ptr, int64_t n_bonds, const double *angle_centers, int n_ang,
+                          double angle_gamma, int64_t *lg_edge_index, int64_t n_angles, float *lg_edge_attr,
+                          void *stream);
 
 #ifdef __cplusplus
 }

@@ -65,6 +65,37 @@ def test_plan_source_sorted_input_gives_identity_csc():
     assert torch.equal(plan.eid_t.cpu().long(), torch.arange(b.lg_edge_index.size(1)))
 
 
+@pytest.mark.parametrize("lg_inc", ["pyg", "bonds"])
+def test_plan_source_sorted_hint_gives_the_same_plan(lg_inc):
+    """GraphBatch.source_sorted (host fact, fetch.py emits source-major lists) skips the CSC radix passes: identical plan."""
+    from gnn_elasticity_predictor_b200 import batching
+    b = pkg.synthetic_batch(5, 16, 12, seed=3, lg_inc=lg_inc, dups=True)
+    # under PyG's default collate the line-graph ids of consecutive crystals overlap (SURVEY.md A9): not source-sorted
+    assert b.source_sorted == (True, lg_inc == "bonds")
+    padded, _ = batching.pad_batch(b, align=64)
+    assert padded.source_sorted == b.source_sorted
+    for batch in (b, padded):
+        for index, n, hint in ((batch.edge_index, batch.x.size(0), batch.source_sorted[0]),
+                               (batch.lg_edge_index, batch.edge_index.size(1), batch.source_sorted[1])):
+            if not hint:
+                assert int(pkg.build_plan(index.to(DEV), n, source_sorted=True).status.item()) & 2
+                continue
+            full = pkg.build_plan(index.to(DEV), n)
+            fast = pkg.build_plan(index.to(DEV), n, source_sorted=True)
+            assert int(fast.status.item()) & 2 == 0
+            for name in ("rowptr", "col", "eid", "rowptr_t", "col_t", "eid_t"):
+                assert torch.equal(getattr(full, name), getattr(fast, name)), name
+
+
+def test_plan_wrong_source_sorted_hint_is_flagged():
+    index = torch.tensor([[0, 2, 1], [1, 0, 2]])
+    plan = pkg.build_plan(index.to(DEV), 3, source_sorted=True)
+    assert int(plan.status.item()) == 2
+    with pytest.raises(ValueError):
+        plan.check()
+    assert pkg.GraphBatch(num_graphs=1, edge_index=index, lg_edge_index=index[:, :1]).source_sorted == (False, True)
+
+
 def test_plan_flags_out_of_range_and_drops_those_edges():
     index = torch.tensor([[0, 1, 9, 2, -1], [1, 2, 0, 7, 0]])
     plan = pkg.build_plan(index.to(DEV), 3)
