@@ -76,6 +76,9 @@ SIGNATURES = {
     "alignn_lgattn_fwd": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, _P, c_int64, c_int64, _P, _P, _P, c_int,
                                   _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P,
                                   c_int64, c_int64, c_int, c_int, c_int, c_float, c_uint64, c_uint64, _P, _P, _P]),
+    "alignn_lgattn_fwd_tc": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, _P, c_int64, c_int64, _P, _P, _P, c_int,
+                                     _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P,
+                                     c_int64, c_int64, c_int, c_int, c_int, c_float, c_uint64, c_uint64, _P, _P]),
     "alignn_lgattn_bwd_dst": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, _P, c_int64, c_int64, _P, c_int64,
                                       c_int64, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, c_int64, _P, c_int64, c_int64,
                                       _P, c_int64, c_int64, c_int, c_int, c_int, c_float, c_uint64, c_uint64, _P, _P, _P]),
@@ -109,7 +112,7 @@ SIGNATURES = {
     "alignn_segment_mean_bwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P]),
 }
 
-ABI_VERSION = 14
+ABI_VERSION = 15
 F32, BF16 = 0, 1
 
 

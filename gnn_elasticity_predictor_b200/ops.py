@@ -7,6 +7,7 @@ has a CPU, eager-PyTorch or Triton fallback -- non-CUDA inputs raise ``RuntimeEr
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -484,6 +485,10 @@ def pack_angles(a: Tensor, plan: GraphPlan) -> Tensor:
     return out[:n_edges]
 
 
+# line-graph attention forward on tcgen05 / TMEM (csrc/lgattn_tc.cu) instead of the mma.sync kernel (csrc/lgattn.cu)
+LGATTN_TC = os.environ.get("ALIGNN_LGATTN_TC", "0") == "1"
+
+
 def raw_lgattn_fwd(q: Tensor, k: Tensor, v: Tensor, qt: Tensor, a_csr: Tensor, w1: Tensor, b1: Tensor, plan: GraphPlan,
                    heads: int, p_drop: float, seed: int, offset: int, rng_step: Optional[Tensor] = None,
                    abar: Optional[Tensor] = None):
@@ -498,6 +503,15 @@ def raw_lgattn_fwd(q: Tensor, k: Tensor, v: Tensor, qt: Tensor, a_csr: Tensor, w
     if abar is None:
         abar = torch.empty(heads, n_nodes, hidden, dtype=q.dtype, device=dev)
     m, z, s = (torch.empty(n_nodes, heads, **f32) for _ in range(3))
+    if LGATTN_TC:
+        with torch.cuda.device(dev), _Launch("lgattn_fwd", 1, (n_nodes, n_edges, hidden, heads, q.element_size())):
+            rc = lib.alignn_lgattn_fwd_tc(_p(q), _p(k), _p(v), _ld(q), _ld(k), _ld(v), _p(qt), int(qt.stride(1)),
+                                          int(qt.stride(0)), _p(a_csr), _p(w1), _p(b1), int(w1.size(1)), _p(plan.rowptr),
+                                          _p(plan.col), _p(aggv), _p(abar), int(abar.stride(1)), int(abar.stride(0)),
+                                          _p(m), _p(z), _p(s), n_nodes, n_edges, hidden, heads, _dtype_code(q),
+                                          float(p_drop), seed, offset, _p(rng_step), _stream())
+        _lib.check(rc, "alignn_lgattn_fwd_tc")
+        return aggv, abar, m, z, s
     with torch.cuda.device(dev), _Launch("lgattn_fwd", 1, (n_nodes, n_edges, hidden, heads, q.element_size())):
         rc = lib.alignn_lgattn_fwd(_p(q), _p(k), _p(v), _ld(q), _ld(k), _ld(v), _p(qt), int(qt.stride(1)),
                                    int(qt.stride(0)), _p(a_csr), _p(w1), _p(b1), int(w1.size(1)), _p(plan.rowptr),

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define ALIGNN_ABI_VERSION 14
+#define ALIGNN_ABI_VERSION 15
 
 #define ALIGNN_F32 0
 #define ALIGNN_BF16 1
@@ -250,6 +250,19 @@ int alignn_lgattn_fwd(const void *q, const void *k, const void *v, int64_t ldq, 
                       float *stat_m, float *stat_z, float *stat_s,
                       int64_t n_nodes, int64_t n_edges, int hidden, int heads, int dtype,
                       float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step, void *work, void *stream);
+
+/* The same forward on the 5th-generation tensor cores (csrc/lgattn_tc.cu): 128-angle tiles, every contraction a
+ * tcgen05.mma with M = 128 (H1 = A W1^T; logits = [H1 | K] [QT ; Qbd]^T; [abar | agg]^T = [H1 | V]^T P), accumulators
+ * in TMEM, operands in 128-byte-swizzled shared memory, K / V rows gathered with cp.async.  Same arguments, outputs,
+ * dropout masks and statistics as alignn_lgattn_fwd (no `work` counter: static row-range partition). */
+int alignn_lgattn_fwd_tc(const void *q, const void *k, const void *v, int64_t ldq, int64_t ldk, int64_t ldv,
+                         const void *qt, int64_t ldqt, int64_t hsqt,
+                         const void *a_csr, const float *w1, const float *b1, int in_dim,
+                         const int32_t *rowptr, const int32_t *col,
+                         float *aggv, void *abar, int64_t ldab, int64_t hsab,
+                         float *stat_m, float *stat_z, float *stat_s,
+                         int64_t n_nodes, int64_t n_edges, int hidden, int heads, int dtype,
+                         float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step, void *stream);
 
 /* Backward of alignn_lgattn_fwd w.r.t. q (dq), qt (bbar) and -- through coef, consumed by alignn_edgeattn_bwd_src with
  * the plan's CSC->CSR position map in place of eid_t -- k, v.  coef: f32 [L, 8] in target-sorted order, (a~_0..3,
