@@ -43,8 +43,8 @@ constexpr uint32_t TS_TOTAL = TS_MISC + 2048;
 
 // TMEM columns
 constexpr uint32_t TM_H1 = 0;            // 256 columns
-constexpr uint32_t TM_S = 256;           // 16
-constexpr uint32_t TM_D = 272;           // 4 blocks x 16: (H1 ch 0..127, H1 ch 128..255, V ch 0..127, V ch 128..255)
+constexpr uint32_t TM_S = 256;           // 4 partial blocks x 16 (one per issuing warp, summed on read)
+constexpr uint32_t TM_D = 320;           // 4 blocks x 16: (H1 ch 0..127, H1 ch 128..255, V ch 0..127, V ch 128..255)
 
 struct Misc {
     uint64_t bar[3];                     // completion of MMA1 / MMA2 / MMA3
@@ -186,6 +186,7 @@ struct TcFwdParams {
     int64_t ldqt, hsqt, ldab, hsab;
     float scale_log2, p_drop, inv_keep;
     uint64_t seed, offset;
+    long long *dbg;          // optional [16] cycle counters of CTA 0 (profiling builds of the caller; NULL otherwise)
 };
 
 // gather 128 rows of 512 B (row u from src + col[e0 + u] * ld) into a [4][128][128 B] SW128 image; rows >= ne keep stale data
@@ -229,8 +230,8 @@ lgattn_fwd_tc_kernel(const TcFwdParams P) {
     }
     if (tid == 0) {
         mbar_init(&misc->bar[0], 1);
-        mbar_init(&misc->bar[1], 1);
-        mbar_init(&misc->bar[2], 1);
+        mbar_init(&misc->bar[1], 4);          // four issuing threads each commit their own MMAs
+        mbar_init(&misc->bar[2], 4);
         mbar_fence_init();
     }
     if (warp == 0) {
@@ -308,10 +309,13 @@ lgattn_fwd_tc_kernel(const TcFwdParams P) {
     float m_run[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, z_run[4] = {0.f, 0.f, 0.f, 0.f},
           zd_run[4] = {0.f, 0.f, 0.f, 0.f};
     uint32_t phase = 0;
+    long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#define TC_MARK(i) do { if (P.dbg) { const long long _t = clock64(); tacc[i] += _t - tprev; tprev = _t; } } while (0)
     while (T.valid) {
         int nsk_lo, nsk_hi;
         const Tile Nx = cur.take(P.rowptr, &nsk_lo, &nsk_hi);        // next tile (uniform over the CTA)
 
+        TC_MARK(0);
         // ---- P1: H1acc = A . W1ext^T ---------------------------------------------------------------------------------
         cp_async_wait<2>();                                          // A of this tile
         tc_sync();
@@ -324,6 +328,7 @@ lgattn_fwd_tc_kernel(const TcFwdParams P) {
         if (P.p_drop > 0.f) dropout_scale4(P.seed, rng_off, (uint64_t)(T.e0 + tid), P.p_drop, P.inv_keep, keep);
         mbar_wait(&misc->bar[0], phase);
         tc_fence_after();
+        TC_MARK(1);
 
         // ---- P2: relu, bf16, shared memory (thread = angle row) ---------------------------------------------------------
         {
@@ -345,23 +350,27 @@ lgattn_fwd_tc_kernel(const TcFwdParams P) {
             }
         }
 
+        TC_MARK(2);
         // ---- P3: S = [H1 | K] . [QT ; Qbd]^T -------------------------------------------------------------------------------
         cp_async_wait<1>();                                          // K rows and B2 of this tile
         tc_sync();
-        if (tid == 0) {
-#pragma unroll 1
-            for (int kb = 0; kb < 8; ++kb) {
+        TC_MARK(3);
+        if (lane == 0) {                      // four issuing threads: warp w accumulates k-blocks {w, w + 4} into S block w
+            const uint64_t hi = ((uint64_t)(1024u >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)1 << 16);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int kb = warp + 4 * half;
                 const uint32_t abase = (kb < 4 ? sb + TS_H1 + kb * 16384u : sb + TS_K + (kb - 4) * 16384u);
-                const uint32_t bbase = sb + TS_B2 + kb * 2048u;
+                const uint64_t ad = hi | (uint64_t)((abase & 0x3FFFFu) >> 4), bd = hi | (uint64_t)(((sb + TS_B2 + kb * 2048u) & 0x3FFFFu) >> 4);
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
-                    tc_mma(tmem + TM_S, tc_desc(abase + ks * 32, 16, 1024, 2), tc_desc(bbase + ks * 32, 16, 1024, 2), IDESC2,
-                           (kb | ks) ? 1u : 0u);
+                    tc_mma(tmem + TM_S + warp * TC_N, ad + 2 * ks, bd + 2 * ks, IDESC2, (half | ks) ? 1u : 0u);
             }
             tc_commit(&misc->bar[1]);
         }
         mbar_wait(&misc->bar[1], phase);
         tc_fence_after();
+        TC_MARK(4);
         // K, B2 and A are free: prefetch for the next tile (commit group "A", then "K + B2")
         if (Nx.valid) load_a(Nx);
         cp_async_commit();
@@ -373,13 +382,17 @@ lgattn_fwd_tc_kernel(const TcFwdParams P) {
         const int r_e = (tid >= T.rs[1]) + (tid >= T.rs[2]) + (tid >= T.rs[3]);
         float s[4];
         {
-            uint32_t v[16];
-            TC_LD16(tlane + TM_S, v);
+            uint32_t v[4][16];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) TC_LD16(tlane + TM_S + b * TC_N, v[b]);
             tc_wait_ld();
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                const uint32_t x = r_e == 0 ? v[t] : (r_e == 1 ? v[4 + t] : (r_e == 2 ? v[8 + t] : v[12 + t]));
-                s[t] = valid ? __uint_as_float(x) * P.scale_log2 : -INFINITY;
+                float x = 0.f;
+#pragma unroll
+                for (int b = 0; b < 4; ++b)      // fixed order: k-blocks (0,4) + (1,5) + (2,6) + (3,7)
+                    x += __uint_as_float(r_e == 0 ? v[b][t] : (r_e == 1 ? v[b][4 + t] : (r_e == 2 ? v[b][8 + t] : v[b][12 + t])));
+                s[t] = valid ? x * P.scale_log2 : -INFINITY;
             }
         }
         if (lane < TC_N) { misc->pmax[warp][lane] = -INFINITY; misc->psum[warp][lane] = 0.f; misc->pzd[warp][lane] = 0.f; }
@@ -448,18 +461,19 @@ lgattn_fwd_tc_kernel(const TcFwdParams P) {
             tc_wait_st();
         }
 
+        TC_MARK(5);
         // ---- P5: D += [H1 | V]^T . P -----------------------------------------------------------------------------------------
         cp_async_wait<2>();                                          // V rows of this tile (A and K + B2 of the next may be in flight)
         tc_sync();
-        if (tid == 0) {
+        TC_MARK(6);
+        if (lane == 0) {                      // four issuing threads: warp b owns D block b
             const int ksteps = (T.ne + 15) >> 4;
-#pragma unroll 1
-            for (int b = 0; b < 4; ++b) {
-                const uint32_t abase = (b < 2 ? sb + TS_H1 : sb + TS_V) + (uint32_t)(b & 1) * 32768u;
-                for (int ks = 0; ks < ksteps; ++ks)
-                    tc_mma(tmem + TM_D + b * 16, tc_desc(abase + ks * 2048, 16384, 1024, 2),
-                           tc_desc(sb + TS_P + ks * 512, 256, 128, 0), IDESC3, (ks > 0 || !T.first) ? 1u : 0u);
-            }
+            const int b = warp;
+            const uint32_t abase = (b < 2 ? sb + TS_H1 : sb + TS_V) + (uint32_t)(b & 1) * 32768u;
+            const uint64_t ad = tc_desc(abase, 16384, 1024, 2), bd = tc_desc(sb + TS_P, 256, 128, 0);
+            for (int ks = 0; ks < ksteps; ++ks)
+                tc_mma(tmem + TM_D + b * 16, ad + (uint64_t)(ks * (2048 >> 4)), bd + (uint64_t)(ks * (512 >> 4)), IDESC3,
+                       (ks > 0 || !T.first) ? 1u : 0u);
             tc_commit(&misc->bar[2]);
         }
         // running statistics of the row(s): fixed-order sums over the four warps
@@ -495,6 +509,7 @@ lgattn_fwd_tc_kernel(const TcFwdParams P) {
         }
         mbar_wait(&misc->bar[2], phase);
         tc_fence_after();
+        TC_MARK(7);
         // V is free: gather the next tile's V rows (commit group "V")
         if (Nx.valid) tc_gather(sb + TS_V, P.v, P.ldv, P.col, Nx.e0, Nx.ne, warp, lane);
         cp_async_commit();
@@ -534,7 +549,11 @@ lgattn_fwd_tc_kernel(const TcFwdParams P) {
         zero_rows(nsk_lo, nsk_hi);
         T = Nx;
         phase ^= 1u;
+        TC_MARK(8);
+        tacc[9] += 1;
     }
+    if (P.dbg && blockIdx.x == 0 && tid == 0)
+        for (int i = 0; i < 10; ++i) P.dbg[i] = tacc[i];
     cp_async_wait<0>();
     tc_sync();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
@@ -545,6 +564,10 @@ lgattn_fwd_tc_kernel(const TcFwdParams P) {
 using namespace alignn;
 
 extern "C" int alignn_lgattn_supported(int hidden, int heads, int in_dim, int dtype);
+
+static long long *g_tc_dbg = nullptr;
+// profiling hook (not part of the public header): device buffer of 16 int64 receiving CTA 0's per-phase cycle counts
+extern "C" void alignn_lgattn_tc_debug(long long *buf) { g_tc_dbg = buf; }
 
 extern "C" int alignn_lgattn_fwd_tc(const void *q, const void *k, const void *v, int64_t ldq, int64_t ldk, int64_t ldv,
                                     const void *qt, int64_t ldqt, int64_t hsqt,
@@ -575,6 +598,7 @@ extern "C" int alignn_lgattn_fwd_tc(const void *q, const void *k, const void *v,
     p.scale_log2 = LOG2E / sqrtf((float)(hidden / heads));
     p.p_drop = p_drop; p.inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
     p.seed = seed; p.offset = offset;
+    p.dbg = g_tc_dbg;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     ALIGNN_CUDA_TRY(cudaFuncSetAttribute(lgattn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS_TOTAL));
     int dev = 0, sms = 148;

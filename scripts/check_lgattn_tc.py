@@ -75,6 +75,17 @@ if mode == "full":
                 t0.record(); ops.raw_lgattn_fwd(q, k, v, qt, a_csr, w1, b1, plan_a, HEADS, 0.15, 7, 3); t1.record()
                 torch.cuda.synchronize(); ts.append(t0.elapsed_time(t1))
             ts.sort(); res[tc] = (ts[len(ts) // 2], outs)
+        import ctypes
+        from gnn_elasticity_predictor_b200 import _lib
+        dbg = torch.zeros(16, dtype=torch.int64, device=DEV)
+        lib = _lib.load()
+        lib.alignn_lgattn_tc_debug.argtypes = [ctypes.c_void_p]
+        lib.alignn_lgattn_tc_debug(ctypes.c_void_p(dbg.data_ptr()))
+        run(True, q, k, v, qt, a_csr, w1, b1, plan_a, HEADS, 0.15, 7, 3)
+        lib.alignn_lgattn_tc_debug(None)
+        d = dbg.cpu().tolist()
+        names = ["take", "P1 mma1+wait", "P2 cvt", "P3 wait K+sync", "MMA2+wait", "P4 softmax", "P5 wait V+sync", "MMA3+wait", "epilogue"]
+        print("  CTA0 cycles per tile over", d[9], "tiles:", {nm: round(c / max(d[9], 1)) for nm, c in zip(names, d[:9])}, flush=True)
         errs = {name: rel(x, y) for name, x, y in zip(("aggv", "abar", "m", "z", "s"), res[True][1], res[False][1])}
         print(f"config2 {lg_inc}: rows {na}, angles {plan.n_edges}: mma.sync {res[False][0] * 1e3:.1f} us, tcgen05 {res[True][0] * 1e3:.1f} us; "
               f"rel err {({k_: f'{v_:.1e}' for k_, v_ in errs.items()})}", flush=True)

@@ -192,6 +192,31 @@ def test_lgattn_forward_matches_stored_feature_kernel(p):
         assert abs(float(s.mean()) - 1.0) < 0.05
 
 
+@pytest.mark.parametrize("n,e,hub,p", [(9, 40, 4, 0.0), (301, 7000, 500, 0.0), (301, 7000, 500, 0.2), (64, 9000, 3000, 0.0),
+                                       (2000, 22000, 10, 0.15)])
+def test_lgattn_tcgen05_forward_matches_mma_sync_kernel(n, e, hub, p, monkeypatch):
+    """csrc/lgattn_tc.cu (tcgen05.mma + TMEM, 128-angle tiles) against csrc/lgattn.cu (mma.sync, 16-angle chunks): same
+    statistics to fp32 rounding, same dropout masks, outputs within bf16 rounding of the probabilities; multi-row tiles,
+    rows split over several tiles (online rescale in TMEM), rows without in-edges."""
+    index, q, k, v, qt, feat, dagg, gt, cvec, wc, a, w1, b1 = lg_case(n, e, 31, hub)
+    plan = pkg.build_plan(index.to(DEV), n)
+    a_csr = ops.pack_angles(a, plan)
+    monkeypatch.setattr(ops, "LGATTN_TC", False)
+    want = ops.raw_lgattn_fwd(q, k, v, qt, a_csr, w1, b1, plan, HEADS, p, 7, 3)
+    monkeypatch.setattr(ops, "LGATTN_TC", True)
+    got = ops.raw_lgattn_fwd(q, k, v, qt, a_csr, w1, b1, plan, HEADS, p, 7, 3)
+    again = ops.raw_lgattn_fwd(q, k, v, qt, a_csr, w1, b1, plan, HEADS, p, 7, 3)
+    for name, x, y, z in zip(("aggv", "abar", "m", "z", "s"), got, want, again):
+        assert not torch.isnan(x).any(), name
+        assert rel_err(x, y) < (2e-2 if name in ("aggv", "abar") else 1e-5), name
+        assert torch.equal(x, z), name                                   # deterministic
+    # against the stored-feature reference path too (independent of both in-kernel-feature kernels)
+    ref = ops.raw_edgeattn_fwd(q, k, v, qt, feat, plan, HEADS, 0.0, 7, 3) if p == 0.0 else None
+    if ref is not None:
+        for name, x, y in zip(("aggv", "abar"), got, ref):
+            assert rel_err(x, y) < 2e-2, name
+
+
 def test_lgattn_backward_and_angle_gradient_match_stored_feature_kernels():
     """dq / bbar / dk / dv of the in-kernel-feature backward == the stored-feature tensor-core backward fed with the
     same h1; the fused angle-encoder gradient == (sum_l df_l * [h1 > 0])^T a from the stored-feature kernels' df."""
