@@ -309,7 +309,7 @@ lgattn_fwd_tc_kernel(const TcFwdParams P) {
     float m_run[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, z_run[4] = {0.f, 0.f, 0.f, 0.f},
           zd_run[4] = {0.f, 0.f, 0.f, 0.f};
     uint32_t phase = 0;
-    long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+    long long tacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
 #define TC_MARK(i) do { if (P.dbg) { const long long _t = clock64(); tacc[i] += _t - tprev; tprev = _t; } } while (0)
     while (T.valid) {
         int nsk_lo, nsk_hi;
@@ -377,6 +377,7 @@ lgattn_fwd_tc_kernel(const TcFwdParams P) {
         if (Nx.valid) { tc_gather(sb + TS_K, P.k, P.ldk, P.col, Nx.e0, Nx.ne, warp, lane); load_b2(Nx); }
         cp_async_commit();
 
+        TC_MARK(10);
         // ---- P4: segmented softmax over the tile (thread = angle) ---------------------------------------------------------
         const bool valid = tid < T.ne;
         const int r_e = (tid >= T.rs[1]) + (tid >= T.rs[2]) + (tid >= T.rs[3]);
@@ -395,6 +396,7 @@ lgattn_fwd_tc_kernel(const TcFwdParams P) {
                 s[t] = valid ? x * P.scale_log2 : -INFINITY;
             }
         }
+        TC_MARK(11);
         if (lane < TC_N) { misc->pmax[warp][lane] = -INFINITY; misc->psum[warp][lane] = 0.f; misc->pzd[warp][lane] = 0.f; }
         __syncwarp();
         const unsigned seg = __match_any_sync(FULL, valid ? r_e : TC_R);
@@ -405,6 +407,7 @@ lgattn_fwd_tc_kernel(const TcFwdParams P) {
             if (valid && lane == seg_lo) misc->pmax[warp][4 * r_e + t] = mx;
         }
         __syncthreads();
+        TC_MARK(12);
         float m_new[4], corr[4], p[4], pd[4];
         {
             const int cbase = valid ? 4 * r_e : 0;
@@ -514,6 +517,7 @@ lgattn_fwd_tc_kernel(const TcFwdParams P) {
         if (Nx.valid) tc_gather(sb + TS_V, P.v, P.ldv, P.col, Nx.e0, Nx.ne, warp, lane);
         cp_async_commit();
 
+        TC_MARK(13);
         // ---- P6: epilogue (thread = channel) ---------------------------------------------------------------------------------
         if (T.last) {
             __syncthreads();                                         // misc->inv
@@ -553,7 +557,7 @@ lgattn_fwd_tc_kernel(const TcFwdParams P) {
         tacc[9] += 1;
     }
     if (P.dbg && blockIdx.x == 0 && tid == 0)
-        for (int i = 0; i < 10; ++i) P.dbg[i] = tacc[i];
+        for (int i = 0; i < 16; ++i) P.dbg[i] = tacc[i];
     cp_async_wait<0>();
     tc_sync();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");

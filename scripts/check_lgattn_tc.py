@@ -86,6 +86,9 @@ if mode == "full":
         d = dbg.cpu().tolist()
         names = ["take", "P1 mma1+wait", "P2 cvt", "P3 wait K+sync", "MMA2+wait", "P4 softmax", "P5 wait V+sync", "MMA3+wait", "epilogue"]
         print("  CTA0 cycles per tile over", d[9], "tiles:", {nm: round(c / max(d[9], 1)) for nm, c in zip(names, d[:9])}, flush=True)
+        print("    inside: prefetch issue (A, K gather, B2)", round(d[10] / d[9]), "| S load + select", round(d[11] / d[9]),
+              "| max: match/redux/sync", round(d[12] / d[9]), "| (P4 value = the rest: exp, sums, P store) | V gather issue",
+              round(d[13] / d[9]), flush=True)
         errs = {name: rel(x, y) for name, x, y in zip(("aggv", "abar", "m", "z", "s"), res[True][1], res[False][1])}
         print(f"config2 {lg_inc}: rows {na}, angles {plan.n_edges}: mma.sync {res[False][0] * 1e3:.1f} us, tcgen05 {res[True][0] * 1e3:.1f} us; "
               f"rel err {({k_: f'{v_:.1e}' for k_, v_ in errs.items()})}", flush=True)
