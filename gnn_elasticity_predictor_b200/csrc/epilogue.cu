@@ -46,6 +46,7 @@ struct GateExtra {
     int heads;
     int64_t ldxr, lddxr;   // row strides (elements) of xr and dxr
     const uint64_t *rng_step;   // optional device counter added to the dropout offset (CUDA-graph replays)
+    const void *x_lp;           // forward: residual input in the STORAGE dtype, read when the fp32 `x` is null
 };
 
 template <typename T, int LANES>
@@ -71,7 +72,7 @@ gate_ln_fwd_kernel(const float *__restrict__ agg, const T *__restrict__ xr, cons
     if (ok) {
         if (has_agg) af = ld8(agg + row * hidden + ch);
         sf = ld8(xr + row * X.ldxr + ch);
-        xf = ld8(x + row * hidden + ch);
+        xf = x ? ld8(x + row * hidden + ch) : ld8(reinterpret_cast<const T *>(X.x_lp) + row * hidden + ch);
         if (X.agge && has_agg) {   // agg = aggv + (Wc[t] abar_t)  [HEADS, agg_rows, C]  + c_t * S_t
             const int C = hidden / X.heads, t = ch / C;
             const F8 ef = ld8(reinterpret_cast<const T *>(X.agge) + ((int64_t)t * agg_rows + row) * C + (ch - t * C));
@@ -509,7 +510,7 @@ extern "C" int64_t alignn_gate_ln_bwd_partial_rows(void) { return EPI_PARTIAL_BL
 static GateExtra plain_extra(int hidden) {
     GateExtra X;
     X.agge = nullptr; X.cvec = nullptr; X.stat_s = nullptr; X.agg_out = nullptr; X.dagg_lp = nullptr; X.dcvec = false; X.dy2 = nullptr; X.lddy2 = hidden; X.agg_rows = -1;
-    X.heads = 1; X.ldxr = hidden; X.lddxr = hidden; X.rng_step = nullptr;
+    X.heads = 1; X.ldxr = hidden; X.lddxr = hidden; X.rng_step = nullptr; X.x_lp = nullptr;
     return X;
 }
 
@@ -521,8 +522,8 @@ static int gate_ln_fwd_impl(const float *agg, const void *xr, const float *x,
     if (n_rows < 0 || hidden <= 0 || hidden > 2048) return ALIGNN_ERR_BAD_SHAPE;
     if (!(p_drop >= 0.f && p_drop < 1.f)) return ALIGNN_ERR_BAD_ARG;
     if (n_rows == 0) return ALIGNN_OK;
-    if (!agg || !xr || !x || !wbeta || !gamma || !bias || !y || !beta || !mean || !rstd) return ALIGNN_ERR_BAD_ARG;
-    if (!aligned16(agg) || !aligned16(xr) || !aligned16(x) || !aligned16(wbeta) || !aligned16(gamma) ||
+    if (!agg || !xr || (!x && !X.x_lp) || !wbeta || !gamma || !bias || !y || !beta || !mean || !rstd) return ALIGNN_ERR_BAD_ARG;
+    if (!aligned16(agg) || !aligned16(xr) || !aligned16(x) || !aligned16(X.x_lp) || !aligned16(wbeta) || !aligned16(gamma) ||
         !aligned16(bias) || !aligned16(y) || !aligned16(y_lp) || !aligned16(X.agge) || !aligned16(X.cvec) ||
         !aligned16(X.agg_out) || (X.ldxr % 8))
         return ALIGNN_ERR_BAD_ARG;
@@ -603,6 +604,21 @@ extern "C" int alignn_gate_ln_fwd3(const float *aggv, const void *agge, const fl
     GateExtra X = plain_extra(hidden);
     X.agge = agge; X.cvec = cvec; X.stat_s = stat_s; X.agg_out = agg_out; X.heads = heads; X.ldxr = ldxr;
     X.rng_step = rng_step;
+    X.agg_rows = (agg_rows < 0 || agg_rows > n_rows) ? -1 : agg_rows;
+    if (hidden % 8 || hidden > 256 || (256 % hidden)) return ALIGNN_ERR_BAD_SHAPE;   // fast mapping only
+    return gate_ln_fwd_impl(aggv, xr, x, wbeta, gamma, bias, y, y_lp, beta, mean, rstd, n_rows, hidden, dtype, eps,
+                            p_drop, seed, offset, X, true, stream);
+}
+
+extern "C" int alignn_gate_ln_fwd4(const float *aggv, const void *agge, const float *cvec, const float *stat_s,
+                                   int heads, int64_t agg_rows, const void *xr, int64_t ldxr, const float *x, const void *x_lp,
+                                   const float *wbeta, const float *gamma, const float *bias,
+                                   float *agg_out, float *y, void *y_lp, float *beta, float *mean, float *rstd,
+                                   int64_t n_rows, int hidden, int dtype, float eps,
+                                   float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step, void *stream) {
+    GateExtra X = plain_extra(hidden);
+    X.agge = agge; X.cvec = cvec; X.stat_s = stat_s; X.agg_out = agg_out; X.heads = heads; X.ldxr = ldxr;
+    X.rng_step = rng_step; X.x_lp = x ? nullptr : x_lp;
     X.agg_rows = (agg_rows < 0 || agg_rows > n_rows) ? -1 : agg_rows;
     if (hidden % 8 || hidden > 256 || (256 % hidden)) return ALIGNN_ERR_BAD_SHAPE;   // fast mapping only
     return gate_ln_fwd_impl(aggv, xr, x, wbeta, gamma, bias, y, y_lp, beta, mean, rstd, n_rows, hidden, dtype, eps,

@@ -173,6 +173,17 @@ __global__ void plan_finish_kernel(const int32_t *__restrict__ keys, const int32
     col[p] = live ? (int32_t)other_row[id] : 0;        // ... and get a safe endpoint (never visited: beyond rowptr[Nn])
 }
 
+// inv[eid[q]] = q, then pos_t[p] = inv[eid_t[p]]: CSR position of the p-th edge of the CSC order
+__global__ void plan_invert_kernel(const int32_t *__restrict__ eid, int64_t n, int32_t *__restrict__ inv) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n) inv[eid[q]] = (int32_t)q;
+}
+__global__ void plan_compose_kernel(const int32_t *__restrict__ inv, const int32_t *__restrict__ eid_t, int64_t n,
+                                    int32_t *__restrict__ pos_t) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) pos_t[p] = inv[eid_t[p]];
+}
+
 static inline int num_sort_tiles(int64_t n) { return (int)((n + SORT_TILE - 1) / SORT_TILE); }
 
 struct PlanWorkspace {
@@ -284,6 +295,20 @@ extern "C" int alignn_build_plan_ex(const int64_t *edge_index, int64_t n_edges, 
     }
     plan_rowptr_kernel<<<row_blocks, tb, 0, st>>>(sk, n_edges, n_nodes, rowptr_t);
     plan_finish_kernel<<<fin_blocks, tb, 0, st>>>(sk, sv, dst_row, n_edges, n_nodes, col_t, eid_t);
+    ALIGNN_LAUNCH_CHECK();
+    return ALIGNN_OK;
+}
+
+extern "C" int alignn_plan_csc_positions(const int32_t *eid, const int32_t *eid_t, int64_t n_edges, int32_t *scratch,
+                                         int32_t *pos_t, void *stream) {
+    if (n_edges < 0) return ALIGNN_ERR_BAD_ARG;
+    if (n_edges == 0) return ALIGNN_OK;
+    if (!eid || !eid_t || !scratch || !pos_t) return ALIGNN_ERR_BAD_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int tb = 256;
+    const unsigned blocks = (unsigned)((n_edges + tb - 1) / tb);
+    plan_invert_kernel<<<blocks, tb, 0, st>>>(eid, n_edges, scratch);
+    plan_compose_kernel<<<blocks, tb, 0, st>>>(scratch, eid_t, n_edges, pos_t);
     ALIGNN_LAUNCH_CHECK();
     return ALIGNN_OK;
 }

@@ -336,10 +336,9 @@ class AlignnRegressor(nn.Module):
         with torch.autocast("cuda", enabled=False):
             enc_n, enc_e = self.node_encoder, self.edge_encoder
             node_b0 = fused.mlp2(data.x, enc_n[0].weight, enc_n[0].bias, enc_n[2].weight, enc_n[2].bias, cd)
-            node32 = node_b0.float()
+            node32 = edge32 = None        # fp32 copies of the encoder outputs: only the per-block path needs them
             if data.edge_attr.numel() > 0:
                 edge_b0 = fused.mlp2(data.edge_attr, enc_e[0].weight, enc_e[0].bias, enc_e[2].weight, enc_e[2].bias, cd)
-                edge32 = edge_b0.float()
             else:
                 edge32 = torch.zeros(n_bonds, self.hidden, device=dev)
                 edge_b0 = edge32.to(cd)
@@ -376,10 +375,16 @@ class AlignnRegressor(nn.Module):
             if lg is not None and run_atoms and getattr(self, "fused_trunk", True) and \
                     len(self.edge_blocks) == len(self.node_blocks):
                 lg_active = getattr(data, "lg_active_rows", None)
-                node32 = self._run_fused_trunk(node32, node_b0, edge32, edge_b0, lg, lg_plan, g_plan, w2, b2,
+                lp_in = cd != torch.float32     # the first blocks read the bf16 encoder outputs directly (no fp32 copy)
+                node32 = self._run_fused_trunk(None if lp_in else node_b0.float(), node_b0,
+                                               None if lp_in and edge32 is None else (edge32 if edge32 is not None else edge_b0.float()),
+                                               edge_b0, lg, lg_plan, g_plan, w2, b2,
                                                -1 if lg_active is None or not getattr(self, "elide_isolated", True)
                                                else int(lg_active), zero_df=bool(getattr(data, "padded", False)))
                 return self._head_features(node32, data, pool_plan)
+            node32 = node_b0.float()
+            if edge32 is None:
+                edge32 = edge_b0.float()
             accum = FeatGradAccumulator(n_layers) if run_lg and lg is None else None
 
             edge_b = node_b = None
@@ -433,7 +438,7 @@ class AlignnRegressor(nn.Module):
         wc = torch.stack([wc_lg, wc_at], dim=1).reshape(2 * nl, hid, hid)
         cvec = torch.stack([cv_lg, cv_at], dim=1).reshape(2 * nl, hid)
         wq, bq = f([cv.lin_query.weight for cv in convs]), f([cv.lin_query.bias for cv in convs])
-        zeros = torch.zeros(hid, device=node32.device)
+        zeros = torch.zeros(hid, device=node_b.device)
         w4 = [wq, f([cv.lin_key.weight for cv in convs]), f([cv.lin_value.weight for cv in convs]),
               f([cv.lin_skip.weight for cv in convs])]
         b4 = [bq, f([cv.lin_key.bias for cv in convs]), f([cv.lin_value.bias for cv in convs]),

@@ -526,9 +526,14 @@ def csc_positions(plan: GraphPlan) -> Tensor:
     """int32 [Ne]: CSR (target-sorted) position of the p-th edge of the CSC (source-sorted) order; cached on the plan."""
     pos_t = getattr(plan, "_pos_t", None)
     if pos_t is None:
-        inv = torch.empty(max(plan.n_edges, 1), dtype=torch.int32, device=plan.eid.device)
-        inv[plan.eid.long()] = torch.arange(plan.n_edges, dtype=torch.int32, device=plan.eid.device)
-        pos_t = inv[plan.eid_t.long()].contiguous()
+        lib = _lib.load()
+        dev = plan.eid.device
+        scratch = torch.empty(max(plan.n_edges, 1), dtype=torch.int32, device=dev)
+        pos_t = torch.empty(max(plan.n_edges, 1), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev), _Launch("build_plan", 2, (plan.n_nodes, plan.n_edges)):
+            rc = lib.alignn_plan_csc_positions(_p(plan.eid), _p(plan.eid_t), plan.n_edges, _p(scratch), _p(pos_t), _stream())
+        _lib.check(rc, "alignn_plan_csc_positions")
+        pos_t = pos_t[:plan.n_edges]
         plan._pos_t = pos_t
     return pos_t
 
@@ -627,10 +632,15 @@ def raw_edgeattn_bwd(dagg: Tensor, dagg_lp: Optional[Tensor], agg: Tensor, q: Te
 def raw_gate_ln_fwd2(aggv: Tensor, agge: Optional[Tensor], cvec: Optional[Tensor], stat_s: Optional[Tensor],
                      heads: int, xr: Tensor, x: Tensor, wbeta: Tensor, gamma: Tensor, bias: Tensor, eps: float,
                      p_drop: float, seed: int, offset: int, want_lp: bool, rng_step: Optional[Tensor] = None,
-                     agg_rows: int = -1):
-    """``agg_rows >= 0``: only the first ``agg_rows`` rows have an aggregate (``agge`` is ``[heads, agg_rows, C]``)."""
+                     agg_rows: int = -1, x_lp: Optional[Tensor] = None):
+    """``agg_rows >= 0``: only the first ``agg_rows`` rows have an aggregate (``agge`` is ``[heads, agg_rows, C]``).
+    ``x = None`` + ``x_lp``: the residual input is read in the storage dtype (first block of a chain)."""
     lib = _lib.load()
-    n_rows, hidden = x.shape
+    n_rows, hidden = (x if x is not None else x_lp).shape
+    if x is None:
+        if agg_rows < 0:
+            agg_rows = n_rows
+        x_lp = x_lp.contiguous()
     dev = aggv.device
     f32 = dict(dtype=torch.float32, device=dev)
     agg = torch.empty(n_rows, hidden, **f32)
@@ -639,8 +649,9 @@ def raw_gate_ln_fwd2(aggv: Tensor, agge: Optional[Tensor], cvec: Optional[Tensor
     beta, mean, rstd = (torch.empty(n_rows, **f32) for _ in range(3))
     with torch.cuda.device(dev), _Launch("gate_ln_fwd", 1, (n_rows, hidden, xr.element_size())):
         if agg_rows >= 0:
-            rc = lib.alignn_gate_ln_fwd3(_p(aggv), _p(agge), _p(cvec), _p(stat_s), heads, int(agg_rows), _p(xr), _ld(xr),
-                                         _p(x), _p(wbeta), _p(gamma), _p(bias), _p(agg), _p(y), _p(y_lp), _p(beta),
+            rc = lib.alignn_gate_ln_fwd4(_p(aggv), _p(agge), _p(cvec), _p(stat_s), heads, int(agg_rows), _p(xr), _ld(xr),
+                                         _p(x), _p(x_lp) if x is None else None, _p(wbeta), _p(gamma), _p(bias), _p(agg),
+                                         _p(y), _p(y_lp), _p(beta),
                                          _p(mean), _p(rstd), n_rows, hidden, _dtype_code(xr), float(eps), float(p_drop),
                                          seed, offset, _p(rng_step), _stream())
         else:

@@ -76,7 +76,7 @@ def _block_forward(idx: int, is_lg: bool, x32: Tensor, xb: Tensor, feat: Optiona
                    wc3: Tensor, cv: Tensor, wb: Tensor, gm: Tensor, bl: Tensor, cfg: TrunkCfg, want_lp: bool, rs):
     """One conv block forward on raw kernels.  Returns (y32, y_lp, saved-state dict)."""
     h = cfg.heads
-    n, hid = x32.shape
+    n, hid = xb.shape                    # x32 is None for the first block of a chain: the residual input is read as xb
     sa, oa, so, oo = cfg.keys[idx]
     na = cfg.lg_active if (is_lg and 0 <= cfg.lg_active < n) else n            # active prefix
     # q | k | v | qt_0..3 over the ACTIVE prefix ([na, 7H]) and x_r over all rows ([n, H]): two contiguous GEMM outputs
@@ -95,7 +95,8 @@ def _block_forward(idx: int, is_lg: bool, x32: Tensor, xb: Tensor, feat: Optiona
         aggv, _, m, z, s = ops.raw_attn_fwd_s(q, k, v, qt, feat, cfg.g_plan, h, cfg.p_attn[idx], sa, oa, rs, abar=abar)
     agge = torch.bmm(abar, wc3.transpose(1, 2))                               # [h, na, C]
     y, y_lp, agg, beta, mean, rstd = ops.raw_gate_ln_fwd2(aggv, agge, cv, s, h, xr, x32, wb, gm, bl, cfg.eps[idx],
-                                                          cfg.p_out[idx], so, oo, want_lp, rs, agg_rows=na)
+                                                          cfg.p_out[idx], so, oo, want_lp, rs, agg_rows=na,
+                                                          x_lp=xb if x32 is None else None)
     st = dict(xb=xb, feat=feat, proj=proj, xr=xr, abar_rows=abar_rows, agg=agg, m=m, z=z, s=s, beta=beta, mean=mean,
               rstd=rstd, na=na)
     return y, y_lp, st
@@ -107,7 +108,7 @@ class _Trunk(torch.autograd.Function):
                 cvec: Tensor, wbeta: Tensor, gamma: Tensor, beta_ln: Tensor, w1: Tensor, b1: Tensor, cfg: TrunkCfg):
         cd = torch.bfloat16
         h, nl = cfg.heads, cfg.n_layers
-        hid = node32.size(1)
+        hid = node_b.size(1)
         c = hid // h
         rs = ops.RNG_STEP
         w8c, b8c = w8.detach().to(cd), b8.detach().to(cd)                      # [2L, 8H, H], [2L, 8H]
@@ -115,19 +116,22 @@ class _Trunk(torch.autograd.Function):
         cvf = cvec.detach().float().contiguous()
         wbf = wbeta.detach().float().contiguous()
         gmf, blf = gamma.detach().float().contiguous(), beta_ln.detach().float().contiguous()
-        n32, nb = node32.contiguous().float(), node_b.contiguous()
-        e32, eb = edge32.contiguous().float(), edge_b.contiguous()
+        # node32 / edge32 may be None: the encoder outputs then enter the first blocks in the storage dtype (no fp32 copy)
+        n32 = node32.contiguous().float() if node32 is not None else None
+        e32 = edge32.contiguous().float() if edge32 is not None else None
+        nb, eb = node_b.contiguous(), edge_b.contiguous()
         if nb.dtype != cd:
             nb = nb.to(cd)
         if eb.dtype != cd:
             eb = eb.to(cd)
         saved = [None] * (2 * nl)
         main = torch.cuda.current_stream()
-        side = _side_stream(node32.device) if cfg.overlap else None
+        side = _side_stream(node_b.device) if cfg.overlap else None
         if side is not None:
             side.wait_stream(main)
             for t in (n32, nb):
-                t.record_stream(side)
+                if t is not None:
+                    t.record_stream(side)
         for l in range(nl):
             i = 2 * l
             e32, eb, saved[i] = _block_forward(i, True, e32, eb, None, w8c[i], b8c[i], wc3[i], cvf[i], wbf[i], gmf[i],
@@ -151,7 +155,8 @@ class _Trunk(torch.autograd.Function):
         ctx.saved, ctx.cfg, ctx.rs = saved, cfg, rs
         ctx.weights = (w8c, wc3, cvf, wbf, gmf, blf)
         ctx.dtypes = (w8.dtype, b8.dtype, wc.dtype, cvec.dtype, wbeta.dtype, gamma.dtype, beta_ln.dtype, w1.dtype, b1.dtype)
-        ctx.sizes = (int(node32.size(0)), int(edge32.size(0)), hid)
+        ctx.sizes = (int(node_b.size(0)), int(edge_b.size(0)), hid)
+        ctx.lp_inputs = (node32 is None, edge32 is None)
         return n32
 
     @staticmethod
@@ -244,7 +249,8 @@ class _Trunk(torch.autograd.Function):
         dw1, db1 = ops.raw_lg_angle_grad(cfg.a_csr, cfg.w1, cfg.b1, cfg.lg_plan, coefs, qts, gts)
 
         t = ctx.dtypes
-        return (dn, None, de, None, d_w8.to(t[0]), d_b8.to(t[1]), d_wc.to(t[2]), d_par[:, 5 * hid:].to(t[3]),
+        lp_n, lp_e = ctx.lp_inputs            # gradients go to whichever copy of the encoder output was the input
+        return (None if lp_n else dn, dn if lp_n else None, None if lp_e else de, de if lp_e else None, d_w8.to(t[0]), d_b8.to(t[1]), d_wc.to(t[2]), d_par[:, 5 * hid:].to(t[3]),
                 d_par[:, :3 * hid].to(t[4]), d_par[:, 3 * hid:4 * hid].to(t[5]), d_par[:, 4 * hid:5 * hid].to(t[6]),
                 dw1.to(t[7]), db1.to(t[8]), None)
 

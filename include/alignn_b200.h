@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define ALIGNN_ABI_VERSION 15
+#define ALIGNN_ABI_VERSION 16
 
 #define ALIGNN_F32 0
 #define ALIGNN_BF16 1
@@ -78,6 +78,12 @@ int alignn_build_plan_ex(const int64_t *edge_index, int64_t n_edges, int64_t n_n
                          int32_t *rowptr, int32_t *col, int32_t *eid,
                          int32_t *rowptr_t, int32_t *col_t, int32_t *eid_t,
                          int32_t *status, void *workspace, size_t workspace_bytes, int flags, void *stream);
+
+/* pos_t[p] = position in the target-sorted (CSR) order of the p-th edge of the source-sorted (CSC) order: lets the
+ * source-sorted backward pass read per-edge records the target-sorted pass wrote in CSR order (`coef`) without an edge-id
+ * indirection.  eid / eid_t: the plan's permutations; scratch: int32 [n_edges]. */
+int alignn_plan_csc_positions(const int32_t *eid, const int32_t *eid_t, int64_t n_edges, int32_t *scratch,
+                              int32_t *pos_t, void *stream);
 
 /* ---- fused edge-attention conv core, forward ----------------------------------------------------
  * Replaces `TransformerConv.message` + `utils.softmax` + 'add' aggregation (PyG 2.7.0; reference
@@ -322,6 +328,15 @@ int alignn_gate_ln_bwd2(const float *dy, const float *agg, const void *xr, int64
  * are written for rows < agg_rows only). */
 int alignn_gate_ln_fwd3(const float *aggv, const void *agge, const float *cvec, const float *stat_s,
                         int heads, int64_t agg_rows, const void *xr, int64_t ldxr, const float *x,
+                        const float *wbeta, const float *gamma, const float *bias,
+                        float *agg_out, float *y, void *y_lp, float *beta, float *mean, float *rstd,
+                        int64_t n_rows, int hidden, int dtype, float eps,
+                        float p_drop, uint64_t seed, uint64_t offset, const uint64_t *rng_step, void *stream);
+/* alignn_gate_ln_fwd3 with the residual input optionally in the STORAGE dtype: when `x` is NULL the kernel reads `x_lp`
+ * ([n_rows, hidden], same dtype as xr) instead -- the first block of each chain, whose input is the bf16 encoder output
+ * (reference: `edge_state + Dropout(...)` promotes bf16 + fp32 -> fp32, train.py:317), needs no fp32 copy of it. */
+int alignn_gate_ln_fwd4(const float *aggv, const void *agge, const float *cvec, const float *stat_s,
+                        int heads, int64_t agg_rows, const void *xr, int64_t ldxr, const float *x, const void *x_lp,
                         const float *wbeta, const float *gamma, const float *bias,
                         float *agg_out, float *y, void *y_lp, float *beta, float *mean, float *rstd,
                         int64_t n_rows, int hidden, int dtype, float eps,
