@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define ALIGNN_ABI_VERSION 16
+#define ALIGNN_ABI_VERSION 17
 
 #define ALIGNN_F32 0
 #define ALIGNN_BF16 1
@@ -442,6 +442,19 @@ int alignn_linegraph_fill(const double *frac, const double *lattice, const int64
                           const int64_t *angle_ptr, int64_t n_bonds, const double *angle_centers, int n_ang,
                           double angle_gamma, int64_t *lg_edge_index, int64_t n_angles, float *lg_edge_attr,
                           void *stream);
+
+/* ---- ensemble post-processing ------------------------------------------------------------------
+ * Replaces the tail of the member loop of `ensemble_collect` (reference scripts/train.py:876-894, 903; same arithmetic at
+ * scripts/predict.py:604-623 and scripts/evaluate.py:244-261), `apply_conformal_intervals` (train.py:1053-1076) and
+ * `LogTransformer.inverse_transform_tensor` (train.py:281-296) by one kernel over the stacked member outputs.
+ * member_means / member_logvars : f32 [n_members, n_graphs, n_targets] (logvars NULL = homoscedastic members, var_z =
+ *     mean mu^2 - mean_z^2).  q : f32 [n_targets] conformal quantile (NULL = no interval), scaled = 1 for the "scaled"
+ *     method (interval = q * std_z), 0 for "absolute".  log_means / log_stds : f32 [n_targets] of the fitted LogTransformer
+ *     (both NULL = outputs stay in z-space).  var_z, std_z, mean_orig, lower_orig, upper_orig may be NULL. */
+int alignn_ensemble_post(const float *member_means, const float *member_logvars, int n_members, int64_t n_graphs,
+                         int n_targets, float min_logvar_floor, const float *q, int scaled,
+                         const float *log_means, const float *log_stds, float *mean_z, float *var_z, float *std_z,
+                         float *mean_orig, float *lower_orig, float *upper_orig, void *stream);
 
 #ifdef __cplusplus
 }

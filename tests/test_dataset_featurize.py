@@ -246,3 +246,52 @@ def test_train_step_on_device_collated_bucket_matches_host_batch():
             tz = pkg.zscore_targets(b.y, b.num_graphs)
             losses.append(float(ts.step(b, tz)[0]))
     assert abs(losses[0] - losses[1]) <= 1e-5 * max(1.0, abs(losses[1]))
+
+
+# ---- N4: ensemble post-processing ---------------------------------------------------------------------------------------------
+def test_oracle_ensemble_post_matches_reference_golden():
+    """oracle/ensemble_ref.py against outputs of the reference's own ensemble_collect / conformal_calibration /
+    apply_conformal_intervals / LogTransformer (oracle/gen_golden_ensemble.py)."""
+    from oracle import ensemble_ref
+    g = load_golden("ensemble_post.pt")
+    mz, sz = ensemble_ref.moments_batched(g["member_means"], g["member_logvars"], g["batch_sizes"])
+    assert torch.equal(mz, g["mean_z"]) and torch.equal(sz, g["std_z"])
+    tz = ensemble_ref.to_z(g["targets"], g["log_means"], g["log_stds"])
+    for method in ("scaled", "absolute"):
+        conf = ensemble_ref.calibration(mz, sz, tz, 0.1, method)
+        assert torch.equal(conf["q"], g[method]["q"]) and conf["method"] == g[method]["method"]
+        mo, lo, hi = ensemble_ref.intervals(mz, sz, conf["q"], method, g["log_means"], g["log_stds"])
+        assert torch.equal(mo, g[method]["mean"]) and torch.equal(lo, g[method]["lower"]) and torch.equal(hi, g[method]["upper"])
+        _, lo_z, hi_z = ensemble_ref.intervals(mz, sz, conf["q"], method)
+        assert torch.equal(lo_z, g[method]["lower_z"]) and torch.equal(hi_z, g[method]["upper_z"])
+    assert bool((g["member_logvars"] < -2.9).any())                      # the floor is exercised
+
+
+def test_ensemble_post_refuses_cpu():
+    from gnn_elasticity_predictor_b200 import ensemble
+    with pytest.raises(RuntimeError, match="no CPU"):
+        ensemble.ensemble_post(torch.zeros(2, 3, 2), torch.zeros(2, 3, 2))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", ["scaled", "absolute"])
+def test_gpu_ensemble_post_matches_reference_golden(method):
+    from gnn_elasticity_predictor_b200 import ensemble
+    g = load_golden("ensemble_post.pt")
+    mu, lv = g["member_means"].to(DEV), g["member_logvars"].to(DEV)
+    out = ensemble.ensemble_post(mu, lv, q=g[method]["q"], method=method, log_means=g["log_means"], log_stds=g["log_stds"])
+    close = lambda a, b: torch.allclose(a.cpu(), b, rtol=2e-6, atol=2e-6)     # noqa: E731
+    assert close(out["mean_z"], g["mean_z"]) and close(out["std_z"], g["std_z"])
+    assert close(out["mean"], g[method]["mean"]) and close(out["lower"], g[method]["lower"]) and close(out["upper"], g[method]["upper"])
+    z = ensemble.ensemble_post(mu, lv, q=g[method]["q"], method=method)                       # z-space intervals
+    assert close(z["lower"], g[method]["lower_z"]) and close(z["upper"], g[method]["upper_z"])
+    # same moments as the torch composition used by EnsemblePredictor, and the calibration quantile on the device
+    mz, vz, sz = ensemble.ensemble_moments(mu, lv)
+    assert close(out["mean_z"], mz.cpu()) and close(out["var_z"], vz.cpu())
+    tz = ((torch.log(g["targets"]) - g["log_means"]) / g["log_stds"]).to(DEV)
+    conf = ensemble.conformal_calibration(out["mean_z"], out["std_z"], tz, 0.1, method)
+    assert torch.allclose(conf["q"].cpu(), g[method]["q"], rtol=1e-5, atol=1e-6)
+    # homoscedastic members: var = spread of the means only, intervals fall back to "absolute"
+    h = ensemble.ensemble_post(mu, None, q=g[method]["q"], method=method)
+    want_var = mu.pow(2).mean(0) - mu.mean(0).pow(2)
+    assert close(h["var_z"], want_var.cpu()) and close(h["upper"], (mu.mean(0).cpu() + g[method]["q"]))
