@@ -30,7 +30,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
-NCU_TRAFFIC = {"lgattn_fwd": 706576128}
+NCU_TRAFFIC = {   # profiles/r01_v14_ncu_lg_{pyg,bonds}.txt, config 2, per launch
+    "pyg": {"lgattn_fwd": 75_901_952, "lgattn_bwd_dst": 140_308_480, "conv_bwd_src": 53_103_104},
+    "bonds": {"lgattn_fwd": 662_797_568, "lgattn_bwd_dst": 1_117_352_192, "conv_bwd_src": 217_685_248},
+}
 METRIC = "ALIGNN train graphs/sec (fwd+bwd)"
 UNIT = "graphs/s"
 ARCH = dict(node_dim=206, edge_dim=36, angle_dim=11, global_dim=289, target_dim=2, hidden=256, layers=4, heads=4)
@@ -386,12 +389,15 @@ def main_b200(args):
             "achieved": gbs_bwd, "peak": peak, "unit": "GB/s", "frac": gbs_bwd / peak, "peak_source": peak_src,
             "algorithmic_bytes": b_bwd, "avg_launch_ms": t_bwd, "launch_ms_parts": {k2: round(v, 4) for k2, v in parts.items()},
             "launches_timed": kern[dom]["launches_timed"],
-            "traffic": NCU_TRAFFIC.get(dom),
+            "traffic": (sum(NCU_TRAFFIC[args.lg_inc].get(k2, 0) for k2 in ("lgattn_bwd_dst", "conv_bwd_src"))
+                        if args.workload == "config2" else None),
+            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of alignn_lgattn_bwd_dst + alignn_conv_bwd_src from the "
+                            "committed ncu --set full capture (profiles/r01_v14_ncu_lg_*.txt); lg_angle_grad not in that capture",
             "formula": "SURVEY.md 8(d) B_b with Nn = active rows, Ne = angles: s*H*(3Nn+Ne) re-read + 4*H*Nn dagg + "
                        "s*H*(3Nn+Ne) gradients + 8*h*Nn stats + 4*(4Ne+2Nn) plan",
             "conv_forward": {"kernel": "alignn_lgattn_fwd", "algorithmic_bytes": b_fwd, "avg_launch_ms": round(t_fwd, 4),
                              "achieved": round(gbs_fwd, 1), "frac": round(gbs_fwd / peak, 4),
-                             "traffic": NCU_TRAFFIC.get("lgattn_fwd")},
+                             "traffic": NCU_TRAFFIC[args.lg_inc]["lgattn_fwd"] if args.workload == "config2" else None},
             "note": "algorithmic bytes are the reference formulation's compulsory traffic (one [Ne,H] edge-projection row "
                     "per angle); the kernels here rebuild that row from 32 B per angle, so what they really touch is the "
                     "`touched` view below -- by that stricter count they sit far below the HBM roofline and are bound "
