@@ -295,3 +295,43 @@ def test_gpu_ensemble_post_matches_reference_golden(method):
     h = ensemble.ensemble_post(mu, None, q=g[method]["q"], method=method)
     want_var = mu.pow(2).mean(0) - mu.mean(0).pow(2)
     assert close(h["var_z"], want_var.cpu()) and close(h["upper"], (mu.mean(0).cpu() + g[method]["q"]))
+
+
+@pytest.mark.gpu
+def test_device_collate_and_featuriser_degenerate_inputs():
+    """Graphs without angles / without bonds, an empty selection, and a structure whose atoms have no bonds at all."""
+    from gnn_elasticity_predictor_b200.synthetic import CrystalGraph
+    gen = torch.Generator().manual_seed(0)
+    full = pkg.make_crystal(8, 6, gen)
+    lone = CrystalGraph(x=torch.randn(2, 206, generator=gen), edge_index=torch.tensor([[0], [1]]),
+                        edge_attr=torch.rand(1, 36, generator=gen), lg_edge_index=torch.zeros(2, 0, dtype=torch.long),
+                        lg_edge_attr=torch.zeros(0, 11), global_x=torch.randn(59, 1, generator=gen),
+                        sg_one_hot=torch.zeros(230, 1), y=torch.tensor([10.0, 20.0]))
+    bare = CrystalGraph(x=torch.randn(1, 206, generator=gen), edge_index=torch.zeros(2, 0, dtype=torch.long),
+                        edge_attr=torch.zeros(0, 36), lg_edge_index=torch.zeros(2, 0, dtype=torch.long),
+                        lg_edge_attr=torch.zeros(0, 11), global_x=torch.randn(59, 1, generator=gen),
+                        sg_one_hot=torch.zeros(230, 1), y=torch.tensor([1.0, 2.0]))
+    graphs = [full, lone, bare, full]
+    for lg_inc in ("pyg", "bonds"):
+        store = dataset.DeviceGraphStore(graphs, DEV, lg_inc=lg_inc)
+        for ids in ([1, 2], [2], [0, 2, 1, 3], [2, 2]):
+            _assert_same_batch(store.collate(ids, validate=True), pkg.collate([graphs[i] for i in ids], lg_inc=lg_inc), ids)
+        got = store.collate([2, 1], pad_to_bucket=True, align=32, validate=True)
+        want, _ = batching.pad_batch(pkg.collate([graphs[2], graphs[1]], lg_inc=lg_inc), align=32)
+        _assert_same_batch(got, want)
+        empty = store.collate([], validate=True)
+        assert empty.sizes == {"B": 0, "N": 0, "E": 0, "L": 0}
+    # featuriser: no bonds at all; and atoms whose bonds have no continuation (a single directed bond)
+    z3 = torch.zeros(2, 3, dtype=torch.float64)
+    lat = torch.eye(3, dtype=torch.float64)[None] * 3.0
+    none = _gpu_featurise(z3, lat, torch.ones(2, dtype=torch.float64), torch.zeros(0).long(), torch.zeros(0).long(),
+                          torch.zeros(0, 3).int())
+    assert none["lg_edge_index"].shape == (2, 0) and none["edge_attr"].shape == (0, 36)
+    frac = torch.tensor([[0.0, 0, 0], [0.5, 0, 0]], dtype=torch.float64)
+    one = _gpu_featurise(frac, lat, torch.ones(2, dtype=torch.float64), torch.tensor([0]), torch.tensor([1]),
+                         torch.zeros(1, 3).int())
+    assert one["lg_edge_index"].shape == (2, 0) and int(one["angle_ptr"][-1]) == 0
+    assert torch.allclose(one["edge_attr"][0, 33:].cpu(), torch.tensor([1.0, 0.0, 0.0]))
+    pair = _gpu_featurise(frac, lat, torch.ones(2, dtype=torch.float64), torch.tensor([0, 1]), torch.tensor([1, 0]),
+                          torch.zeros(2, 3).int())                       # i->j and its exact reverse: both continuations skipped
+    assert pair["lg_edge_index"].shape == (2, 0)
