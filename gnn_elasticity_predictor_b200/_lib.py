@@ -111,12 +111,13 @@ SIGNATURES = {
     "alignn_linegraph_count": (c_int, [_P, _P, _P, _P, c_int64, _P, _P]),
     "alignn_linegraph_fill": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P, c_int, c_double, _P, c_int64,
                                       _P, _P]),
+    "alignn_gaussian_nll": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_float, c_float, _P, _P, _P, _P]),
     "alignn_ensemble_post": (c_int, [_P, _P, c_int, c_int64, c_int, c_float, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "alignn_segment_mean_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P]),
     "alignn_segment_mean_bwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P]),
 }
 
-ABI_VERSION = 17
+ABI_VERSION = 18
 F32, BF16 = 0, 1
 
 

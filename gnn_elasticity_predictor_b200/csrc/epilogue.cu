@@ -19,16 +19,18 @@ constexpr int EPI_WARPS = EPI_THREADS / 32;
 constexpr int EPI_PARTIAL_BLOCKS = 296;  // 2 x 148 SMs: persistent grid of the backward
 constexpr int EPI_GEN_WARPS = 4;
 
-// dropout keep-scales of 8 consecutive elements starting at a multiple of 8
+// dropout keep-scales of 8 consecutive elements starting at a multiple of 8: ONE Philox4x32-10 block per 8 elements, 16
+// random bits each (drop iff u16 < p * 65536: the drop probability is p rounded down to a multiple of 2^-16).  Forward
+// and backward of the fast kernels call this with the same (seed, offset, first), so they see the same mask.
 __device__ __forceinline__ void dropout8(uint64_t seed, uint64_t offset, uint64_t first, float p,
                                          float inv_keep, float *out) {
-    const Philox4 r0 = philox4x32_10(seed, offset, first >> 2);
-    const Philox4 r1 = philox4x32_10(seed, offset, (first >> 2) + 1);
-    const uint32_t bits[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+    const Philox4 r = philox4x32_10(seed, offset, first >> 3);
+    const uint32_t thr = (uint32_t)(p * 65536.0f);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        const float u = (float)(bits[c] >> 8) * (1.0f / 16777216.0f);
-        out[c] = u < p ? 0.0f : inv_keep;
+        const uint32_t u = (w[c >> 1] >> (16 * (c & 1))) & 0xffffu;
+        out[c] = u < thr ? 0.0f : inv_keep;
     }
 }
 

@@ -29,7 +29,7 @@ from torch import Tensor
 
 from . import _lib, ops
 from .dp import FlatGradBucket
-from .modules import HeteroAlignnRegressor, gaussian_nll_loss
+from .modules import HeteroAlignnRegressor, fused_gaussian_nll, gaussian_nll_loss  # noqa: F401
 from .synthetic import GraphBatch
 from . import batching
 
@@ -131,7 +131,7 @@ class TrainStep:
         self.bucket.detach_grads()
         self.model.base.build_plans(batch)                 # CSR/CSC sorts of this batch: part of every step
         mean, logvar = self.model(batch)
-        loss = gaussian_nll_loss(mean.float(), logvar.float(), tz, self.log_sigma_l2, self.floor, mask=mask)
+        loss = fused_gaussian_nll(mean, logvar, tz, self.log_sigma_l2, self.floor, mask=mask)
         (loss * self.loss_scale).backward()
         self.bucket.gather()                               # one multi-tensor copy into the flat gradient bucket
         return loss.detach(), mean.detach(), logvar.detach()

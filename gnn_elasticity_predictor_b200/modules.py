@@ -472,12 +472,28 @@ class AlignnRegressor(nn.Module):
         n_atoms, n_bonds = data.x.size(0), data.edge_index.size(1)
         v = self.validate_indices
         g_sorted, lg_sorted = getattr(data, "source_sorted", (False, False))
-        lg_plan = ops.build_plan(data.lg_edge_index, n_bonds, validate=v, source_sorted=lg_sorted) if n_bonds > 0 else None
-        g_plan = ops.build_plan(data.edge_index, n_atoms, validate=v, source_sorted=g_sorted)
         n_graphs = getattr(data, "num_graphs", None)
         if n_graphs is None:
             n_graphs = int(data.batch.max()) + 1 if data.batch.numel() > 0 else 0
-        pool_plan = ops.build_pool_plan(data.batch, int(n_graphs))
+        # the three plans are independent chains of small, latency-bound kernels: the atom-graph and pooling plans are
+        # built on the side stream beside the (10x larger) line-graph plan; fork / join are capturable graph edges
+        side = trunk_mod._side_stream(data.x.device) if (getattr(self, "overlap_streams", True) and data.x.is_cuda
+                                                         and n_bonds > 0 and not v) else None
+        if side is not None:
+            main = torch.cuda.current_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                g_plan = ops.build_plan(data.edge_index, n_atoms, source_sorted=g_sorted)
+                pool_plan = ops.build_pool_plan(data.batch, int(n_graphs))
+            lg_plan = ops.build_plan(data.lg_edge_index, n_bonds, source_sorted=lg_sorted)
+            main.wait_stream(side)
+            for pl in (g_plan, pool_plan):
+                for t in (pl.rowptr, pl.col, pl.eid, pl.rowptr_t, pl.col_t, pl.eid_t, pl.status):
+                    t.record_stream(main)
+        else:
+            lg_plan = ops.build_plan(data.lg_edge_index, n_bonds, validate=v, source_sorted=lg_sorted) if n_bonds > 0 else None
+            g_plan = ops.build_plan(data.edge_index, n_atoms, validate=v, source_sorted=g_sorted)
+            pool_plan = ops.build_pool_plan(data.batch, int(n_graphs))
         plans = (lg_plan, g_plan, pool_plan)
         try:
             object.__setattr__(data, "_alignn_plans", plans)
@@ -541,3 +557,41 @@ def gaussian_nll_loss(mean: Tensor, logvar: Tensor, target_z: Tensor, log_sigma_
     if log_sigma_l2 > 0.0:
         loss = loss + float(log_sigma_l2) * ((0.5 * lv).pow(2) * w).sum() / (n_real * lv.size(1))
     return loss
+
+
+class _FusedGaussianNLL(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mean: Tensor, logvar: Tensor, target_z: Tensor, mask: Optional[Tensor], weight: Optional[Tensor],
+                log_sigma_l2: float, floor: float):
+        from . import _lib
+        lib = _lib.load()
+        dev = mean.device
+        f = lambda t: None if t is None else t.detach().to(dev, torch.float32).contiguous()      # noqa: E731
+        mu, lv, tz, mk, w = f(mean), f(logvar), f(target_z), f(mask), f(weight)
+        b, t = mu.shape
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        dmean, dlogvar = torch.empty_like(mu), torch.empty_like(lv)
+        with torch.cuda.device(dev), ops._Launch("gaussian_nll", 1, (b, t)):
+            rc = lib.alignn_gaussian_nll(ops._p(mu), ops._p(lv), ops._p(tz), ops._p(mk), ops._p(w), b, t, float(floor),
+                                         float(log_sigma_l2), ops._p(loss), ops._p(dmean), ops._p(dlogvar), ops._stream())
+        _lib.check(rc, "alignn_gaussian_nll")
+        ctx.save_for_backward(dmean, dlogvar)
+        ctx.dtypes = (mean.dtype, logvar.dtype)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        dmean, dlogvar = ctx.saved_tensors
+        return (g * dmean).to(ctx.dtypes[0]), (g * dlogvar).to(ctx.dtypes[1]), None, None, None, None, None
+
+
+def fused_gaussian_nll(mean: Tensor, logvar: Tensor, target_z: Tensor, log_sigma_l2: float = 0.1,
+                       min_logvar_floor: float = -2.9, mask: Optional[Tensor] = None,
+                       sample_weight: Optional[Tensor] = None) -> Tensor:
+    """:func:`gaussian_nll_loss` (reference ``train.py:655-681``, incl. the optional per-sample weights of ``:661-675``) as
+    ONE kernel for the value and the gradient (``alignn_gaussian_nll``, ``csrc/loss.cu``).  CUDA tensors only."""
+    if not mean.is_cuda:
+        raise RuntimeError("fused_gaussian_nll: tensors must live on a CUDA device (no CPU fallback path)")
+    if mean.dim() != 2 or mean.shape != logvar.shape or target_z.shape != mean.shape:
+        raise ValueError("mean, logvar, target_z must share one [graphs, targets] shape")
+    return _FusedGaussianNLL.apply(mean, logvar, target_z, mask, sample_weight, float(log_sigma_l2), float(min_logvar_floor))

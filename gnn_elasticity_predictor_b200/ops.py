@@ -349,7 +349,7 @@ def build_pool_plan(batch: Tensor, num_graphs: int) -> GraphPlan:
     n = int(batch.numel())
     idx = torch.stack([torch.arange(n, device=batch.device, dtype=torch.int64), batch.to(torch.int64)])
     # keys (row 1) live in [0, num_graphs); the "source" row holds node ids in [0, n): plan over max(n, B)
-    plan = build_plan(idx, max(n, int(num_graphs)))
+    plan = build_plan(idx, max(n, int(num_graphs)), source_sorted=True)      # row 0 is arange: its sort is the identity
     plan.n_nodes = int(num_graphs)
     return plan
 

