@@ -424,18 +424,24 @@ def main_b200(args):
         # two device staging batches, allocated once: per-step device allocations on the copy stream make the caching
         # allocator wait on cross-stream events (or fall back to cudaMalloc) and serialise the pipeline
         staging = [host_batches[j].to(dev) for j in range(2)]
-        consumed = [None, None]                    # event: the step that read staging[j] has been enqueued and finished
+
+        # With >= 2 members cycling, the H2D copy of step i+1 goes straight into the input buffers of the CUDA graph that
+        # will run it (another member's graph than the one executing): no staging copy on the device.
+        direct = graphed and args.members >= 2
+        consumed = {}                              # buffer key -> event: the step that read it has finished
 
         def upload(i):
-            j = i % 2
+            st_in = steppers[i % args.members].static_inputs(host_batches[i % 2]) if direct else None
+            key = ("m", i % args.members) if st_in is not None else ("s", i % 2)
+            dst = st_in[0] if st_in is not None else staging[i % 2]
             with torch.cuda.stream(copy_stream):
-                if consumed[j] is not None:
-                    copy_stream.wait_event(consumed[j])
-                for k2, dst in staging[j].tensors().items():
-                    dst.copy_(getattr(host_batches[j], k2), non_blocking=True)
+                if consumed.get(key) is not None:
+                    copy_stream.wait_event(consumed[key])
+                for k2, t_dst in dst.tensors().items():
+                    t_dst.copy_(getattr(host_batches[i % 2], k2), non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
-            return staging[j], ev, j
+            return dst, ev, key, (st_in[1] if st_in is not None else None)
 
         def e2e_loop(n_steps):
             """Software pipeline, one step deep: while step i runs on the GPU the host uploads batch i+1 (copy stream)
@@ -444,14 +450,17 @@ def main_b200(args):
             pending = None
             seen = 0.0
             for i in range(n_steps):
-                b, ev, j = nxt
+                b, ev, key, tz_buf = nxt
                 main_stream.wait_event(ev)
                 if i + 1 < n_steps:
                     nxt = upload(i + 1)            # next batch's H2D overlaps this step's compute
                 tz = pkg.zscore_targets(b.y, b.num_graphs)
+                if tz_buf is not None:
+                    tz_buf.copy_(tz)
+                    tz = tz_buf
                 loss, mean, logvar = step(i, b, tz)
-                consumed[j] = torch.cuda.Event()
-                consumed[j].record(main_stream)
+                consumed[key] = torch.cuda.Event()
+                consumed[key].record(main_stream)
                 packed = torch.cat([loss.detach().float().reshape(1), mean.detach().float().reshape(-1),
                                     logvar.detach().float().reshape(-1)])
                 out_host[i % 2].copy_(packed, non_blocking=True)
@@ -477,7 +486,9 @@ def main_b200(args):
         e2e = {"value": n_graphs * world * args.steps / float(tw.item()), "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_host[0].numel() * 4,
                "ms_per_step": float(tw.item()) / args.steps * 1e3,
-               "how": "pinned host batch -> H2D (copy stream, next batch overlapped) -> plan + fwd + loss + bwd"
+               "how": "pinned host batch -> H2D (copy stream, next batch overlapped"
+                      + (", written straight into the input buffers of the next member's CUDA graph" if direct else "")
+                      + ") -> plan + fwd + loss + bwd"
                       + ("" if args.no_optimizer else " + clip + AdamW") + " -> D2H loss/mean/logvar every step, read on "
                       "the host one step later (one-step-deep software pipeline); wall clock over all steps incl. the drain"}
 
@@ -494,13 +505,19 @@ def main_b200(args):
         perms_np = [p_.numpy() for p_ in perms]
         ids_dev = [torch.empty(n_graphs, dtype=torch.int64, device=dev) for _ in range(2)]
         out_host2 = [torch.empty(1 + 4 * n_graphs, dtype=torch.float32).pin_memory() for _ in range(2)]
+        store_probe = store.collate(perms_np[0])          # a batch with this workload's signature
 
         def store_loop(n_steps):
             pending, seen = None, 0.0
             for i in range(n_steps):
                 ids_dev[i % 2].copy_(perms[i % 4], non_blocking=True)               # the step's only H2D traffic
-                b = store.collate(perms_np[i % 4], ids_device=ids_dev[i % 2])
+                st_in = steppers[i % args.members].static_inputs(store_probe) if graphed else None
+                # once the member's graph is captured, the batch is collated straight into its input buffers
+                b = store.collate(perms_np[i % 4], ids_device=ids_dev[i % 2], out=None if st_in is None else st_in[0])
                 tz = pkg.zscore_targets(b.y, b.num_graphs)
+                if st_in is not None:
+                    st_in[1].copy_(tz)
+                    tz = st_in[1]
                 loss, mean, logvar = step(i, b, tz)
                 packed = torch.cat([loss.detach().float().reshape(1), mean.detach().float().reshape(-1),
                                     logvar.detach().float().reshape(-1)])

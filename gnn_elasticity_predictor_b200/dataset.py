@@ -119,15 +119,18 @@ class DeviceGraphStore:
                 "max_L": int(l.max()) if ids.size else 0}
 
     def collate(self, ids, pad_to_bucket: bool = False, align: int = 256, shape: Optional[Dict[str, int]] = None,
-                ids_device: Optional[Tensor] = None, validate: bool = False) -> GraphBatch:
+                ids_device: Optional[Tensor] = None, validate: bool = False, out: Optional[GraphBatch] = None) -> GraphBatch:
         """The batch PyG's ``Batch.from_data_list([dataset[i] for i in ids])`` would build, on the device.
 
         ``pad_to_bucket`` / ``shape``: write into a shape bucket (``batching.bucket_shape`` semantics; the returned batch has
         ``padded = True`` and ``mask`` attached as ``batch.loss_mask``).  ``ids_device``: the same ids already on the device
-        (int64) -- otherwise they are uploaded here (``B`` x 8 bytes)."""
+        (int64) -- otherwise they are uploaded here (``B`` x 8 bytes).  ``out``: an existing batch of exactly the target shape
+        (e.g. ``TrainStep.static_inputs(...)[0]``, the input buffers of a captured CUDA graph) to write into."""
         ids_h = np.asarray(ids, dtype=np.int64).reshape(-1)
         s = self.sizes_of(ids_h)
         b = s["B"]
+        if out is not None:                          # the destination fixes the shape (a bucket if it is larger)
+            shape = dict(out.sizes)
         if shape is None and pad_to_bucket:
             shape = {"N": batching.round_up_bucket(s["N"] + 1, align), "E": batching.round_up_bucket(s["E"], align),
                      "L": batching.round_up_bucket(s["L"], align), "B": batching.round_up_bucket(b + 1, 8)}
@@ -141,6 +144,8 @@ class DeviceGraphStore:
         dev, d = self.device, self.dims
         sel = ids_device if ids_device is not None else torch.from_numpy(ids_h).to(dev, non_blocking=True)
         f32, i64 = dict(dtype=torch.float32, device=dev), dict(dtype=torch.int64, device=dev)
+        if out is not None:
+            return self._collate_into(out, ids_h, s, shape, padded, sel, align, validate, check_facts=True)
         out = GraphBatch.__new__(GraphBatch)
         out.num_graphs, out.lg_inc, out.padded = shape["B"], self.lg_inc, padded
         out.x = torch.empty(shape["N"], d["node"], **f32)
@@ -153,6 +158,27 @@ class DeviceGraphStore:
         out.lg_edge_index = torch.empty(2, shape["L"], **i64)
         out.batch = torch.empty(shape["N"], **i64)
         out.train_idx = torch.empty(shape["B"], **i64)
+        return self._collate_into(out, ids_h, s, shape, padded, sel, align, validate)
+
+    def _collate_into(self, out: GraphBatch, ids_h, s, shape, padded: bool, sel: Tensor, align: int, validate: bool,
+                      check_facts: bool = False) -> GraphBatch:
+        dev, b = self.device, s["B"]
+        # host-side facts of the batch (what GraphBatch.__init__ derives from host tensors), from per-graph host metadata
+        if b:
+            ptr = self.bond_ptr_h if self.lg_inc == "bonds" else self.node_ptr_h
+            inc = np.concatenate([[0], np.cumsum(ptr[ids_h + 1] - ptr[ids_h])])[:-1]
+            has = self._lg_max_h[ids_h] > 0
+            active = int((inc[has] + self._lg_max_h[ids_h][has]).max()) if has.any() else 0
+        else:
+            active = 0
+        active = min(shape["E"], batching.round_up_bucket(active, align)) if padded else active
+        sorted_ = self._batch_sorted(ids_h)
+        if check_facts and (getattr(out, "lg_active_rows", None) != active or getattr(out, "source_sorted", None) != sorted_
+                            or bool(getattr(out, "padded", False)) != padded):
+            # a captured CUDA graph was specialised on these facts: refuse rather than replay it on a batch it does not fit
+            raise ValueError("collate(out=...): the selection's lg_active_rows / source_sorted / padding differ from the "
+                             "destination batch's")
+        f32, i64 = dict(dtype=torch.float32, device=dev), dict(dtype=torch.int64, device=dev)
         seg = torch.empty(3, b + 1, **i64)
         bo = _lib.BatchOutStruct()
         for name in ("x", "edge_attr", "lg_edge_attr", "global_x", "sg_one_hot", "y", "edge_index", "lg_edge_index",
@@ -169,16 +195,7 @@ class DeviceGraphStore:
         _lib.check(rc, "alignn_collate")
         if validate and int(self.status.item()) & 3:
             raise RuntimeError(f"alignn_collate status {int(self.status.item())}")
-        # host-side facts of the batch (what GraphBatch.__init__ derives from host tensors), from per-graph host metadata
-        if b:
-            inc = np.concatenate([[0], np.cumsum((self.bond_ptr_h if self.lg_inc == "bonds" else self.node_ptr_h)[ids_h + 1]
-                                                 - (self.bond_ptr_h if self.lg_inc == "bonds" else self.node_ptr_h)[ids_h])])[:-1]
-            has = self._lg_max_h[ids_h] > 0
-            active = int((inc[has] + self._lg_max_h[ids_h][has]).max()) if has.any() else 0
-        else:
-            active = 0
-        out.lg_active_rows = min(shape["E"], batching.round_up_bucket(active, align)) if padded else active
-        out.source_sorted = self._batch_sorted(ids_h)
+        out.lg_active_rows, out.source_sorted = active, sorted_
         out.seg_ptr = seg
         if padded:
             mask = torch.zeros(shape["B"], **f32)

@@ -187,6 +187,13 @@ class TrainStep:
         ops.STATS.kernels = k0
         return cap
 
+    def static_inputs(self, batch_like, masked: bool = False):
+        """``(batch, target_z)`` input buffers of the CUDA graph captured for ``batch_like``'s signature, or ``None`` before
+        capture.  A loader may write the next batch straight into them (e.g. the H2D copy on a side stream, once the
+        previous replay of this graph has finished) and pass them to :meth:`step`, which then copies nothing."""
+        cap = self._captured.get(self.signature(batch_like) + (bool(masked),)) if isinstance(batch_like, GraphBatch) else None
+        return None if cap is None else (cap.batch, cap.tz)
+
     def step(self, batch, target_z: Tensor, mask: Optional[Tensor] = None):
         """``mask`` (``[B]``, 1 = real graph) restricts the loss to real graphs.  With ``pad_to_buckets`` a ``GraphBatch``
         is padded to its shape bucket first (``batching.pad_batch``), so ragged datasets replay one graph per bucket; the
@@ -207,9 +214,11 @@ class TrainStep:
             if seen < self.graph_warmup:
                 return self._eager(batch, target_z, mask)
             cap = self._captured[sig] = self._capture(batch, target_z, mask)
-        for k, v in cap.batch.tensors().items():
-            v.copy_(getattr(batch, k), non_blocking=True)
-        cap.tz.copy_(target_z, non_blocking=True)
+        if batch is not cap.batch:                      # callers may fill the graph's own input buffers (static_inputs)
+            for k, v in cap.batch.tensors().items():
+                v.copy_(getattr(batch, k), non_blocking=True)
+        if target_z is not cap.tz:
+            cap.tz.copy_(target_z, non_blocking=True)
         if mask is not None:
             cap.mask.copy_(mask, non_blocking=True)
         cap.graph.replay()

@@ -335,3 +335,20 @@ def test_device_collate_and_featuriser_degenerate_inputs():
     pair = _gpu_featurise(frac, lat, torch.ones(2, dtype=torch.float64), torch.tensor([0, 1]), torch.tensor([1, 0]),
                           torch.zeros(2, 3).int())                       # i->j and its exact reverse: both continuations skipped
     assert pair["lg_edge_index"].shape == (2, 0)
+
+
+@pytest.mark.gpu
+def test_device_collate_into_existing_buffers():
+    """collate(out=...) writes into a given batch (e.g. the input buffers of a captured CUDA graph) and refuses selections
+    whose plan hints differ from what those buffers were captured with."""
+    graphs = _graphs([8, 8, 8, 8, 9], k=6, seed=4)
+    store = dataset.DeviceGraphStore(graphs, DEV)
+    first = store.collate([0, 1, 2])
+    ptrs = {k: v.data_ptr() for k, v in first.tensors().items()}
+    again = store.collate([3, 1, 0], out=first)
+    assert again is first and {k: v.data_ptr() for k, v in first.tensors().items()} == ptrs
+    _assert_same_batch(first, pkg.collate([graphs[i] for i in (3, 1, 0)]), [3, 1, 0])
+    with pytest.raises(ValueError):
+        store.collate([0, 1, 4], out=first)            # 9-atom graph: other sizes
+    with pytest.raises(ValueError):
+        store.collate([0, 1], out=first)               # smaller selection would need padding the destination was not made with
