@@ -111,13 +111,16 @@ SIGNATURES = {
     "alignn_linegraph_count": (c_int, [_P, _P, _P, _P, c_int64, _P, _P]),
     "alignn_linegraph_fill": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P, c_int, c_double, _P, c_int64,
                                       _P, _P]),
+    "alignn_wgrad_supported": (c_int, [c_int, c_int]),
+    "alignn_wgrad_partial_floats": (c_int64, [c_int64, c_int]),
+    "alignn_wgrad": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int, c_int, c_int, _P, _P, _P, _P]),
     "alignn_gaussian_nll": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_float, c_float, _P, _P, _P, _P]),
     "alignn_ensemble_post": (c_int, [_P, _P, c_int, c_int64, c_int, c_float, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "alignn_segment_mean_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P]),
     "alignn_segment_mean_bwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P]),
 }
 
-ABI_VERSION = 18
+ABI_VERSION = 19
 F32, BF16 = 0, 1
 
 

@@ -486,6 +486,7 @@ def pack_angles(a: Tensor, plan: GraphPlan) -> Tensor:
 
 
 # line-graph attention forward on tcgen05 / TMEM (csrc/lgattn_tc.cu) instead of the mma.sync kernel (csrc/lgattn.cu)
+BF16_CODE = 1
 LGATTN_TC = os.environ.get("ALIGNN_LGATTN_TC", "0") == "1"
 
 
@@ -707,6 +708,36 @@ def raw_gate_ln_bwd3(dy: Optional[Tensor], agg: Tensor, xr: Tensor, wbeta: Tenso
                                      offset, _p(rng_step), _stream())
     _lib.check(rc, "alignn_gate_ln_bwd3")
     return dagg, dagg_lp, dparams
+
+
+WGRAD_TC = os.environ.get("ALIGNN_WGRAD_TC", "1") == "1"     # tcgen05 weight + bias gradient (csrc/wgrad_tc.cu) vs cuBLAS + colsum
+# the UMMA kernel wins where the reduction is long and the output small (one 256-channel group: dW_s, K = all bond rows);
+# for the wide stacked projection (M = 7H over the active rows only) its per-split partials outweigh the operands
+WGRAD_TC_MAX_M = int(os.environ.get("ALIGNN_WGRAD_TC_MAX_M", "256"))
+WGRAD_TC_MIN_K = 32768            # below this the launch + reduction overhead of the split kernel eats the gain
+
+
+def wgrad(a: Tensor, b: Tensor, w_out: Tensor, b_out: Optional[Tensor] = None) -> None:
+    """``w_out[M, N] = a^T b`` and ``b_out[M] = a.sum(0)`` (fp32) for ``a [K, M]``, ``b [K, N]`` bf16 with unit column
+    stride: the weight and bias gradient of a node projection in one pass (``alignn_wgrad``); falls back to cuBLAS + the
+    column-sum kernel for shapes the tcgen05 kernel does not take."""
+    lib = _lib.load()
+    k, m = a.shape
+    n = int(b.size(1))
+    ok = (WGRAD_TC and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and bool(lib.alignn_wgrad_supported(n, BF16_CODE))
+          and m % 8 == 0 and a.stride(1) == 1 and b.stride(1) == 1 and _ld(a) % 8 == 0 and _ld(b) % 8 == 0
+          and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0 and w_out.is_contiguous() and w_out.dtype == torch.float32
+          and (b_out is None or (b_out.is_contiguous() and b_out.dtype == torch.float32)) and k > 0
+          and (m <= WGRAD_TC_MAX_M or WGRAD_TC_MAX_M < 0) and (k >= WGRAD_TC_MIN_K or WGRAD_TC_MAX_M < 0))
+    if not ok:
+        torch.mm(a.t(), b, out_dtype=torch.float32, out=w_out)
+        if b_out is not None:
+            colsum(a, out=b_out)
+        return
+    partials = torch.empty(int(lib.alignn_wgrad_partial_floats(k, m)), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device), _Launch("wgrad", 2, (k, m, n)):
+        rc = lib.alignn_wgrad(_p(a), _ld(a), _p(b), _ld(b), k, m, n, BF16_CODE, _p(partials), _p(w_out), _p(b_out), _stream())
+    _lib.check(rc, "alignn_wgrad")
 
 
 def colsum(x: Tensor, out: Optional[Tensor] = None) -> Tensor:

@@ -217,10 +217,9 @@ class _Trunk(torch.autograd.Function):
             else:
                 dx = torch.mm(dtail, wtail, out_dtype=torch.float32)
             torch.addmm(dx[:na], dbuf, w7, out_dtype=torch.float32, out=dx[:na])
-            torch.mm(dbuf.t(), xb[:na], out_dtype=torch.float32, out=d_w8[idx, :7 * hid])
-            torch.mm(dxr.t(), xb, out_dtype=torch.float32, out=d_w8[idx, 7 * hid:])
-            ops.colsum(dbuf, out=d_b8[idx, :7 * hid])
-            ops.colsum(dxr, out=d_b8[idx, 7 * hid:])
+            # weight + bias gradients of the stacked projection: one streaming pass per operand pair (tcgen05, wgrad_tc.cu)
+            ops.wgrad(dbuf, xb[:na], d_w8[idx, :7 * hid], d_b8[idx, :7 * hid])
+            ops.wgrad(dxr, xb, d_w8[idx, 7 * hid:], d_b8[idx, 7 * hid:])
             st.clear()
             return dx
 

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define ALIGNN_ABI_VERSION 18
+#define ALIGNN_ABI_VERSION 19
 
 #define ALIGNN_F32 0
 #define ALIGNN_BF16 1
@@ -465,6 +465,18 @@ int alignn_ensemble_post(const float *member_means, const float *member_logvars,
 int alignn_gaussian_nll(const float *mean, const float *logvar, const float *target, const float *mask,
                         const float *weight, int64_t n_graphs, int n_targets, float min_logvar_floor,
                         float log_sigma_l2, float *loss, float *dmean, float *dlogvar, void *stream);
+
+/* ---- weight + bias gradient of a node projection in one pass (tcgen05 / TMEM) ---------------------------------------
+ * Replaces autograd's AddmmBackward of PyG TransformerConv's lin_query / lin_key / lin_value / lin_skip (reference
+ * scripts/train.py:691): C[M, N] = A^T B and colsum[M] = sum_k A[k, :], for A [K, M] (row stride lda) = gradient of the
+ * projection output and B [K, N] (row stride ldb) = the block input, both bf16, N = 256 (alignn_wgrad_supported).  One
+ * streaming pass over A and B (csrc/wgrad_tc.cu: split over K and over 256-channel groups of M, UMMA 128x256x16 with
+ * both operands MN-major, accumulators in TMEM), per-CTA partials reduced in a fixed order.
+ * partials : f32 [alignn_wgrad_partial_floats(K, M)] scratch.  colsum may be NULL. */
+int alignn_wgrad_supported(int n, int dtype);
+int64_t alignn_wgrad_partial_floats(int64_t K, int M);
+int alignn_wgrad(const void *a, int64_t lda, const void *b, int64_t ldb, int64_t K, int M, int N, int dtype,
+                 float *partials, float *c, float *colsum, void *stream);
 
 #ifdef __cplusplus
 }

@@ -14,6 +14,7 @@ oracle.install_shim()
 from torch_geometric.utils import scatter, softmax  # noqa: E402  (oracle leaf ops)
 
 import gnn_elasticity_predictor_b200 as pkg  # noqa: E402
+from gnn_elasticity_predictor_b200 import ops  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -322,3 +323,33 @@ def test_fused_gaussian_nll_value_and_gradients(b, t, l2, use_mask, use_w):
         assert abs(float(got) - float(ref)) <= 2e-6 * max(1.0, abs(float(ref)))
     with pytest.raises(RuntimeError, match="no CPU"):
         pkg.fused_gaussian_nll(mean, logvar, tz)
+
+
+# ---- tcgen05 weight + bias gradient (csrc/wgrad_tc.cu) ------------------------------------------------------------------
+@pytest.mark.parametrize("k,m,strided", [(98304, 256, True), (8544, 1792, False), (8192, 256, False), (1000, 1792, False),
+                                         (63, 256, False), (1, 8, False), (12345, 136, True)])
+def test_wgrad_tcgen05_matches_fp64(k, m, strided, monkeypatch):
+    """alignn_wgrad (UMMA with both operands MN-major, TMEM accumulators, split over K) against the fp64 product and
+    column sums of the same bf16 operands; also bit-identical across two runs (fixed-order reduction)."""
+    g = torch.Generator().manual_seed(k + m)
+    a_full = (torch.randn(k, 2 * m if strided else m, generator=g) * 0.5).to(torch.bfloat16).to(DEV)
+    a = a_full[:, :m]                                         # row stride 2m when strided (the trunk's [dx_r | df] buffer)
+    b = torch.randn(k, 256, generator=g).to(torch.bfloat16).to(DEV)
+    monkeypatch.setattr(ops, "WGRAD_TC", True)
+    monkeypatch.setattr(ops, "WGRAD_TC_MAX_M", -1)            # exercise the kernel for every M (the default gates it to M <= 256)
+    w1, s1 = torch.empty(m, 256, device=DEV), torch.empty(m, device=DEV)
+    ops.STATS.reset(); ops.STATS.events = True
+    ops.wgrad(a, b, w1, s1)
+    torch.cuda.synchronize()
+    assert "wgrad" in ops.STATS.durations_ms(), "the tcgen05 kernel must have been taken for this shape"
+    ops.STATS.events = False
+    w2, s2 = torch.empty_like(w1), torch.empty_like(s1)
+    ops.wgrad(a, b, w2, s2)
+    assert torch.equal(w1, w2) and torch.equal(s1, s2)
+    want_w = a.double().t() @ b.double()
+    want_s = a.double().sum(0)
+    assert rel_err(w1, want_w) < 2e-6 and rel_err(s1, want_s) < 2e-6
+    monkeypatch.setattr(ops, "WGRAD_TC", False)               # the library path computes the same thing
+    w3, s3 = torch.empty_like(w1), torch.empty_like(s1)
+    ops.wgrad(a, b, w3, s3)
+    assert rel_err(w3, want_w) < 5e-5 and rel_err(s3, want_s) < 2e-5          # cuBLAS split-K: looser than the UMMA kernel
