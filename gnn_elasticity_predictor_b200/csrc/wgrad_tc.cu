@@ -45,6 +45,7 @@ struct WgParams {
     float *partials;                             // [k_splits][256 columns][M] (+ [M] column sums): column-major per split
     int64_t K;
     int M;
+    int ch_per_cta;                              // 256 (two accumulators per CTA) or 128 (one; twice the CTAs stream)
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c_inner, int c_outer, uint64_t *bar) {
@@ -80,8 +81,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int64_t chunks_total = (P.K + WG_ROWS - 1) / WG_ROWS;
     const int64_t c_lo = chunks_total * blockIdx.x / splits, c_hi = chunks_total * (blockIdx.x + 1) / splits;
     const int64_t n_chunks = c_hi - c_lo;
-    const int m0 = blockIdx.y * 256;                              // first gradient channel of this CTA
-    const int m_end = min(P.M, m0 + 256);
+    const int m0 = blockIdx.y * P.ch_per_cta;                     // first gradient channel of this CTA
+    const int m_end = min(P.M, m0 + P.ch_per_cta);
     const int n_tiles = (m_end - m0 + 127) / 128;                 // 1 or 2 accumulators
 
     if (warp == 0) {
@@ -91,12 +92,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 const int stage = (int)(c % WG_STAGES);
                 if (c >= WG_STAGES) mbar_wait(&misc->empty[stage], (uint32_t)((c / WG_STAGES - 1) & 1));
                 uint64_t *bar = &misc->full[stage];
-                mbar_expect_tx(bar, WG_STAGE);
+                mbar_expect_tx(bar, WG_TILE + (uint32_t)n_tiles * 16384u);
                 const int row = (int)((c_lo + c) * WG_ROWS);
                 const uint32_t base = sb + (uint32_t)stage * WG_STAGE;
 #pragma unroll
                 for (int blk = 0; blk < 4; ++blk) {
-                    tma_load_2d(base + (uint32_t)blk * 8192u, &map_a, m0 + 64 * blk, row, bar);
+                    if (blk < 2 * n_tiles) tma_load_2d(base + (uint32_t)blk * 8192u, &map_a, m0 + 64 * blk, row, bar);
                     tma_load_2d(base + WG_TILE + (uint32_t)blk * 8192u, &map_b, 64 * blk, row, bar);
                 }
             }
@@ -132,6 +133,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             mbar_wait(&misc->full[stage], (uint32_t)((c / WG_STAGES) & 1));
             const uint32_t blk = sb + (uint32_t)stage * WG_STAGE + (uint32_t)(c2 >> 6) * 8192u;
             float a0 = 0.f, a1 = 0.f;
+            if (c2 < 128 * n_tiles)
 #pragma unroll 8
             for (int r = 0; r < WG_ROWS; ++r) {
                 uint32_t w;
@@ -207,14 +209,17 @@ wgrad_reduce_kernel(const float *__restrict__ partials, int splits, int64_t widt
     }
 }
 
+static int wg_ch_per_cta(int M) { return M <= 256 ? 128 : 256; }
+
 static int wg_splits(int64_t K, int M) {
-    const int groups = (M + 255) / 256;
+    const int groups = (M + wg_ch_per_cta(M) - 1) / wg_ch_per_cta(M);
     if (const char *e = getenv("ALIGNN_WG_SPLITS")) {            // tuning knob (profiling only)
         const int v = atoi(e);
         if (v > 0) return v;
     }
     int64_t chunks = (K + WG_ROWS - 1) / WG_ROWS;
-    int s = 74 / groups;                         // half the SMs per channel group: the partials stay small, HBM still saturates
+    int s = (M <= 256 ? 148 : 74) / groups;      // M <= 256: every SM streams, one 128-channel accumulator each (partials as small
+                                                 // as with 74 two-accumulator CTAs; the second reader of a B row hits L2)
     if (s < 1) s = 1;
     if (s > chunks) s = (int)(chunks > 0 ? chunks : 1);
     return s;
@@ -275,9 +280,9 @@ extern "C" int alignn_wgrad(const void *a, int64_t lda, const void *b, int64_t l
     rc = wg_make_map(&map_b, b, K, N, ldb);
     if (rc != ALIGNN_OK) return rc;
     WgParams p;
-    p.partials = partials; p.K = K; p.M = M;
+    p.partials = partials; p.K = K; p.M = M; p.ch_per_cta = wg_ch_per_cta(M);
     ALIGNN_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM));
-    wgrad_tc_kernel<<<dim3((unsigned)splits, (unsigned)((M + 255) / 256)), WG_THREADS, WG_SMEM, st>>>(map_a, map_b, p);
+    wgrad_tc_kernel<<<dim3((unsigned)splits, (unsigned)((M + p.ch_per_cta - 1) / p.ch_per_cta)), WG_THREADS, WG_SMEM, st>>>(map_a, map_b, p);
     ALIGNN_LAUNCH_CHECK();
     const int64_t w_mat = (int64_t)M * WG_N, width = w_mat + M;
     wgrad_reduce_kernel<<<(unsigned)((width / 4 + WR_COLS - 1) / WR_COLS), WR_COLS * WR_ROWS, 0, st>>>(partials, splits, width,
