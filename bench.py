@@ -587,7 +587,9 @@ def main_b200(args):
                         + ("; whole step replayed as one CUDA graph per member" if graphed else "; eager launches"),
                 "l2": "inputs larger than L2: every step streams > 1 GB of per-block activations / gradients (98 304 x 256 bond states x 8 blocks, fwd + bwd) through HBM, far above the 126 MB L2; no explicit flush",
                 "projections": "per-NODE projections only (the per-edge E x H x H GEMMs are eliminated algebraically); "
-                               + ("cuBLAS via torch (bf16)" if cd == torch.bfloat16 else "cuBLAS via torch (fp32, TF32 off)"),
+                               + ("cuBLAS via torch (bf16), except the K = n_bonds weight + bias gradient of the skip projection: "
+                                  "hand-written tcgen05 + TMA kernel (csrc/wgrad_tc.cu)" if cd == torch.bfloat16
+                                  else "cuBLAS via torch (fp32, TF32 off)"),
             },
             "clocks": clocks, "e2e": e2e, "e2e_device_store": e2e_store, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "kernel_ms_per_step": {k2: round(v, 4) for k2, v in sorted(totals.items())},
