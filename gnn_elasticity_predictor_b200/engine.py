@@ -12,7 +12,7 @@ B200 specifics:
   fused kernel pair (``csrc/optim.cu``: deterministic norm -> clip -> decoupled-weight-decay Adam), the DP exchange ONE
   NCCL all-reduce;
 * nothing in the step synchronises with the host, so the whole step is captured once per batch signature
-  ``(B, N, E, L)`` into a CUDA graph and replayed: ~1 200 kernel launches collapse into one ``cudaGraphLaunch``.  Dropout
+  ``(B, N, E, L)`` into a CUDA graph and replayed: ~400 kernel launches collapse into one ``cudaGraphLaunch``.  Dropout
   masks stay fresh across replays through a device-side step counter added to every Philox offset (``ops.RNG_STEP``);
   the learning rates and the Adam step count also live on the device;
 * batches whose signature has not been captured (ragged datasets) run the same code eagerly.
