@@ -5,11 +5,14 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
 product (``gnn_elasticity_predictor_b200``) never does and fails loudly when
 its CUDA library is missing.
 
-PARITY UNPINNED: the reference ships no golden vectors / numeric assertions
-for this path and its arithmetic lives in ``torch-geometric==2.7.0``
-(``/root/reference/requirements.txt:9``), absent from the mount and from this
-image.  See ``oracle/pyg_shim/torch_geometric/__init__.py`` for how the
-restatement is self-pinned.
+PARITY UNPINNED for the third-party part: the reference ships no golden
+vectors / numeric assertions for this path and the conv arithmetic lives in
+``torch-geometric==2.7.0`` (``/root/reference/requirements.txt:9``), absent
+from the mount and from this image.  See
+``oracle/pyg_shim/torch_geometric/__init__.py`` for how that restatement is
+self-pinned.  Everything the reference's OWN code computes (model classes,
+loss, featuriser loops, ensemble post-processing) is pinned by fixtures made by
+running that code here (``gen_golden*.py`` -> ``tests/golden/``).
 
 Contents
 --------
@@ -20,6 +23,12 @@ Contents
 ``gen_golden.py`` imports the reference's OWN classes (``/root/reference``)
                   under the shim and writes ``tests/golden/*.pt``
 ``Makefile``      builds ``oracle/_ref/libconv_ref.so`` from ``conv_ref.c``
+``linegraph_ref.py`` / ``gen_golden_linegraph.py``   featuriser loops of
+                  ``scripts/fetch.py`` restated / golden vectors from the
+                  reference's own ``build_graph_from_structure``
+``ensemble_ref.py`` / ``gen_golden_ensemble.py``     ensemble post-processing
+                  restated / golden vectors from the reference's own
+                  ``ensemble_collect``, ``conformal_*``, ``LogTransformer``
 """
 from __future__ import annotations
 
