@@ -39,6 +39,7 @@ SIGNATURES = {
     "alignn_plan_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "alignn_build_plan": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "alignn_build_plan_ex": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, c_int, _P]),
+    "alignn_build_plan_bounded": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, c_int, _P]),
     "alignn_plan_csc_positions": (c_int, [_P, _P, c_int64, _P, _P, _P]),
     "alignn_conv_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int,
                                 c_float, c_uint64, c_uint64, _P]),
@@ -120,7 +121,7 @@ SIGNATURES = {
     "alignn_segment_mean_bwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P]),
 }
 
-ABI_VERSION = 19
+ABI_VERSION = 20
 F32, BF16 = 0, 1
 
 

@@ -21,7 +21,8 @@ constexpr int SORT_PER_WARP = SORT_TILE / SORT_WARPS;
 __global__ void plan_prep_kernel(const int64_t *__restrict__ src_row, const int64_t *__restrict__ dst_row,
                                  int64_t n_edges, int64_t n_nodes, int32_t *__restrict__ key_dst,
                                  int32_t *__restrict__ key_src, int32_t *__restrict__ vals,
-                                 int32_t *__restrict__ status, int check_src_sorted) {
+                                 int32_t *__restrict__ status, int check_src_sorted, int64_t n_valid) {
+    // n_nodes here is the KEY BOUND (sentinel); indices in [bound, n_valid) are legal node ids the caller's bound excluded
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_edges) return;
     const int64_t s = src_row[e], d = dst_row[e];
@@ -29,7 +30,7 @@ __global__ void plan_prep_kernel(const int64_t *__restrict__ src_row, const int6
     key_dst[e] = ok ? (int32_t)d : (int32_t)n_nodes;
     key_src[e] = ok ? (int32_t)s : (int32_t)n_nodes;
     vals[e] = (int32_t)e;
-    if (!ok) atomicOr(status, 1);
+    if (!ok) atomicOr(status, (s >= 0 && s < n_valid && d >= 0 && d < n_valid) ? 4 : 1);
     if (check_src_sorted && e > 0) {   // the caller's "already source-sorted" hint, verified on the sort KEYS
         const int64_t sp = src_row[e - 1], dp = dst_row[e - 1];
         const bool okp = sp >= 0 && sp < n_nodes && dp >= 0 && dp < n_nodes;
@@ -150,13 +151,14 @@ radix_scatter_kernel(const int32_t *__restrict__ keys_in, const int32_t *__restr
 // rowptr[i] = first sorted position whose key is >= i (binary search: empty-row runs of any length
 // cost the same).  One thread per row 0..n_nodes.
 __global__ void plan_rowptr_kernel(const int32_t *__restrict__ keys, int64_t n_edges, int64_t n_nodes,
-                                   int32_t *__restrict__ rowptr) {
+                                   int32_t *__restrict__ rowptr, int64_t bound) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i > n_nodes) return;
+    const int64_t target = i < bound ? i : bound;      // rows at / beyond the key bound are empty: all point at the first sentinel
     int64_t lo = 0, hi = n_edges;
     while (lo < hi) {
         const int64_t mid = (lo + hi) >> 1;
-        if ((int64_t)keys[mid] < i) lo = mid + 1; else hi = mid;
+        if ((int64_t)keys[mid] < target) lo = mid + 1; else hi = mid;
     }
     rowptr[i] = (int32_t)lo;
 }
@@ -254,11 +256,25 @@ extern "C" int alignn_build_plan(const int64_t *edge_index, int64_t n_edges, int
                                 workspace_bytes, 0, stream);
 }
 
+extern "C" int alignn_build_plan_bounded(const int64_t *edge_index, int64_t n_edges, int64_t n_nodes, int64_t key_bound,
+                                         int32_t *rowptr, int32_t *col, int32_t *eid,
+                                         int32_t *rowptr_t, int32_t *col_t, int32_t *eid_t,
+                                         int32_t *status, void *workspace, size_t workspace_bytes, int flags, void *stream);
+
 extern "C" int alignn_build_plan_ex(const int64_t *edge_index, int64_t n_edges, int64_t n_nodes,
                                     int32_t *rowptr, int32_t *col, int32_t *eid,
                                     int32_t *rowptr_t, int32_t *col_t, int32_t *eid_t,
                                     int32_t *status, void *workspace, size_t workspace_bytes, int flags, void *stream) {
+    return alignn_build_plan_bounded(edge_index, n_edges, n_nodes, n_nodes, rowptr, col, eid, rowptr_t, col_t, eid_t, status,
+                                     workspace, workspace_bytes, flags, stream);
+}
+
+extern "C" int alignn_build_plan_bounded(const int64_t *edge_index, int64_t n_edges, int64_t n_nodes, int64_t key_bound,
+                                         int32_t *rowptr, int32_t *col, int32_t *eid,
+                                         int32_t *rowptr_t, int32_t *col_t, int32_t *eid_t,
+                                         int32_t *status, void *workspace, size_t workspace_bytes, int flags, void *stream) {
     const int src_sorted = flags & ALIGNN_PLAN_SOURCE_SORTED;
+    const int64_t kb = (key_bound < 0 || key_bound > n_nodes) ? n_nodes : key_bound;
     if (n_edges < 0 || n_nodes < 0 || !rowptr || !rowptr_t || !status) return ALIGNN_ERR_BAD_ARG;
     if (n_edges >= ((int64_t)1 << 31) - SORT_TILE || n_nodes >= ((int64_t)1 << 31) - 1) return ALIGNN_ERR_BAD_SHAPE;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -274,27 +290,27 @@ extern "C" int alignn_build_plan_ex(const int64_t *edge_index, int64_t n_edges, 
     carve(workspace, n_edges, &w);
     const int64_t *src_row = edge_index, *dst_row = edge_index + n_edges;
     const int tb = 256;
-    plan_prep_kernel<<<(unsigned)((n_edges + tb - 1) / tb), tb, 0, st>>>(src_row, dst_row, n_edges, n_nodes,
+    plan_prep_kernel<<<(unsigned)((n_edges + tb - 1) / tb), tb, 0, st>>>(src_row, dst_row, n_edges, kb,
                                                                           w.key_dst, w.key_src, w.vals0, status,
-                                                                          src_sorted);
+                                                                          src_sorted, n_nodes);
     ALIGNN_LAUNCH_CHECK();
     const unsigned fin_blocks = (unsigned)((n_edges + tb - 1) / tb);
     const unsigned row_blocks = (unsigned)((n_nodes + 1 + tb - 1) / tb);
     int32_t *sk = nullptr, *sv = nullptr;
-    int rc = radix_sort_pairs(w.key_dst, w.vals0, w, n_edges, n_nodes, st, &sk, &sv);
+    int rc = radix_sort_pairs(w.key_dst, w.vals0, w, n_edges, kb, st, &sk, &sv);
     if (rc != ALIGNN_OK) return rc;
-    plan_rowptr_kernel<<<row_blocks, tb, 0, st>>>(sk, n_edges, n_nodes, rowptr);
-    plan_finish_kernel<<<fin_blocks, tb, 0, st>>>(sk, sv, src_row, n_edges, n_nodes, col, eid);
+    plan_rowptr_kernel<<<row_blocks, tb, 0, st>>>(sk, n_edges, n_nodes, rowptr, kb);
+    plan_finish_kernel<<<fin_blocks, tb, 0, st>>>(sk, sv, src_row, n_edges, kb, col, eid);
     ALIGNN_LAUNCH_CHECK();
     if (src_sorted) {   // the stable source sort of a source-sorted list is the identity (verified in plan_prep_kernel)
         sk = w.key_src;
         sv = w.vals0;
     } else {
-        rc = radix_sort_pairs(w.key_src, w.vals0, w, n_edges, n_nodes, st, &sk, &sv);
+        rc = radix_sort_pairs(w.key_src, w.vals0, w, n_edges, kb, st, &sk, &sv);
         if (rc != ALIGNN_OK) return rc;
     }
-    plan_rowptr_kernel<<<row_blocks, tb, 0, st>>>(sk, n_edges, n_nodes, rowptr_t);
-    plan_finish_kernel<<<fin_blocks, tb, 0, st>>>(sk, sv, dst_row, n_edges, n_nodes, col_t, eid_t);
+    plan_rowptr_kernel<<<row_blocks, tb, 0, st>>>(sk, n_edges, n_nodes, rowptr_t, kb);
+    plan_finish_kernel<<<fin_blocks, tb, 0, st>>>(sk, sv, dst_row, n_edges, kb, col_t, eid_t);
     ALIGNN_LAUNCH_CHECK();
     return ALIGNN_OK;
 }

@@ -472,6 +472,8 @@ class AlignnRegressor(nn.Module):
         n_atoms, n_bonds = data.x.size(0), data.edge_index.size(1)
         v = self.validate_indices
         g_sorted, lg_sorted = getattr(data, "source_sorted", (False, False))
+        lg_bound = getattr(data, "lg_active_rows", None)          # host fact: every line-graph index is below it
+        lg_bound = -1 if lg_bound is None else int(lg_bound)
         n_graphs = getattr(data, "num_graphs", None)
         if n_graphs is None:
             n_graphs = int(data.batch.max()) + 1 if data.batch.numel() > 0 else 0
@@ -485,13 +487,14 @@ class AlignnRegressor(nn.Module):
             with torch.cuda.stream(side):
                 g_plan = ops.build_plan(data.edge_index, n_atoms, source_sorted=g_sorted)
                 pool_plan = ops.build_pool_plan(data.batch, int(n_graphs))
-            lg_plan = ops.build_plan(data.lg_edge_index, n_bonds, source_sorted=lg_sorted)
+            lg_plan = ops.build_plan(data.lg_edge_index, n_bonds, source_sorted=lg_sorted, key_bound=lg_bound)
             main.wait_stream(side)
             for pl in (g_plan, pool_plan):
                 for t in (pl.rowptr, pl.col, pl.eid, pl.rowptr_t, pl.col_t, pl.eid_t, pl.status):
                     t.record_stream(main)
         else:
-            lg_plan = ops.build_plan(data.lg_edge_index, n_bonds, validate=v, source_sorted=lg_sorted) if n_bonds > 0 else None
+            lg_plan = ops.build_plan(data.lg_edge_index, n_bonds, validate=v, source_sorted=lg_sorted,
+                                     key_bound=lg_bound) if n_bonds > 0 else None
             g_plan = ops.build_plan(data.edge_index, n_atoms, validate=v, source_sorted=g_sorted)
             pool_plan = ops.build_pool_plan(data.batch, int(n_graphs))
         plans = (lg_plan, g_plan, pool_plan)

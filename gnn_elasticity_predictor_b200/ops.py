@@ -116,10 +116,11 @@ class _Launch:
         return False
 
 
-def _plan_kernels(n_edges: int, n_nodes: int, source_sorted: bool = False) -> int:
+def _plan_kernels(n_edges: int, n_nodes: int, source_sorted: bool = False, key_bound: int = -1) -> int:
     if n_edges == 0:
         return 0
-    passes = (max(int(n_nodes), 1).bit_length() + 7) // 8
+    top = n_nodes if key_bound < 0 or key_bound > n_nodes else key_bound
+    passes = (max(int(top), 1).bit_length() + 7) // 8
     return 1 + (1 if source_sorted else 2) * 4 * passes + 4
 
 
@@ -150,16 +151,20 @@ class GraphPlan:
         """Synchronising validation: raises if any edge referenced a node outside ``[0, n_nodes)`` or a
         ``source_sorted`` hint was wrong."""
         st = int(self.status.item())
+        if st & 4:
+            raise ValueError("build_plan(key_bound=...): an index at or beyond the stated bound")
         if st & 2:
             raise ValueError("build_plan(source_sorted=True): edge_index[0] is not non-decreasing")
         if st & 1:
             raise IndexError(f"edge_index contains indices outside [0, {self.n_nodes})")
 
 
-def build_plan(edge_index: Tensor, n_nodes: int, validate: bool = False, source_sorted: bool = False) -> GraphPlan:
+def build_plan(edge_index: Tensor, n_nodes: int, validate: bool = False, source_sorted: bool = False,
+               key_bound: int = -1) -> GraphPlan:
     """Stable target-sort / source-sort of ``edge_index`` (int64 ``[2, E]``) on the device.  ``source_sorted``: the
     caller knows ``edge_index[0]`` is non-decreasing (``GraphBatch.source_sorted``), so the source sort is skipped; the
-    device verifies it (``plan.check()``)."""
+    device verifies it (``plan.check()``).  ``key_bound``: the caller knows every index is below it (e.g.
+    ``GraphBatch.lg_active_rows``): fewer radix passes; verified on the device as well."""
     _require_cuda(edge_index)
     if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.size(0) != 2:
         raise RuntimeError("edge_index must be an int64 tensor of shape [2, E]")
@@ -175,11 +180,11 @@ def build_plan(edge_index: Tensor, n_nodes: int, validate: bool = False, source_
     status = torch.empty(1, **i32)
     ws_bytes = int(lib.alignn_plan_workspace_bytes(n_edges, n_nodes))
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev), _Launch("build_plan", _plan_kernels(n_edges, n_nodes, source_sorted), (n_nodes, n_edges)):
-        rc = lib.alignn_build_plan_ex(_p(ei), n_edges, n_nodes, _p(rowptr), _p(col), _p(eid), _p(rowptr_t),
-                                      _p(col_t), _p(eid_t), _p(status), _p(ws), ws_bytes, 1 if source_sorted else 0,
-                                      _stream())
-    _lib.check(rc, "alignn_build_plan_ex")
+    with torch.cuda.device(dev), _Launch("build_plan", _plan_kernels(n_edges, n_nodes, source_sorted, key_bound), (n_nodes, n_edges)):
+        rc = lib.alignn_build_plan_bounded(_p(ei), n_edges, n_nodes, int(key_bound), _p(rowptr), _p(col), _p(eid),
+                                           _p(rowptr_t), _p(col_t), _p(eid_t), _p(status), _p(ws), ws_bytes,
+                                           1 if source_sorted else 0, _stream())
+    _lib.check(rc, "alignn_build_plan_bounded")
     plan = GraphPlan(rowptr, col[:n_edges], eid[:n_edges], rowptr_t, col_t[:n_edges], eid_t[:n_edges], status,
                      n_nodes, n_edges)
     if validate:

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define ALIGNN_ABI_VERSION 19
+#define ALIGNN_ABI_VERSION 20
 
 #define ALIGNN_F32 0
 #define ALIGNN_BF16 1
@@ -78,6 +78,16 @@ int alignn_build_plan_ex(const int64_t *edge_index, int64_t n_edges, int64_t n_n
                          int32_t *rowptr, int32_t *col, int32_t *eid,
                          int32_t *rowptr_t, int32_t *col_t, int32_t *eid_t,
                          int32_t *status, void *workspace, size_t workspace_bytes, int flags, void *stream);
+
+/* The same with a KEY BOUND: the caller states that every index is < key_bound (<= n_nodes) -- e.g. the batch's
+ * `lg_active_rows`: with PyG's default collate every line-graph index is below N_atoms + E_last -- so the
+ * radix sorts run over log2(key_bound) bits instead of log2(n_nodes) (2 passes instead of 3 at BASELINE config 2).  Rows at
+ * or beyond the bound come out empty.  Verified on the device: a legal index >= key_bound sets bit 2 (value 4) of `status`
+ * and the edge is dropped like an out-of-range one.  key_bound < 0 or > n_nodes means n_nodes. */
+int alignn_build_plan_bounded(const int64_t *edge_index, int64_t n_edges, int64_t n_nodes, int64_t key_bound,
+                              int32_t *rowptr, int32_t *col, int32_t *eid,
+                              int32_t *rowptr_t, int32_t *col_t, int32_t *eid_t,
+                              int32_t *status, void *workspace, size_t workspace_bytes, int flags, void *stream);
 
 /* pos_t[p] = position in the target-sorted (CSR) order of the p-th edge of the source-sorted (CSC) order: lets the
  * source-sorted backward pass read per-edge records the target-sorted pass wrote in CSR order (`coef`) without an edge-id

@@ -88,6 +88,29 @@ def test_plan_source_sorted_hint_gives_the_same_plan(lg_inc):
                 assert torch.equal(getattr(full, name), getattr(fast, name)), name
 
 
+@pytest.mark.parametrize("n_graphs,atoms,k", [(6, 16, 12), (256, 32, 12)])
+def test_plan_key_bound_gives_the_same_plan_with_fewer_passes(n_graphs, atoms, k):
+    """GraphBatch.lg_active_rows bounds every line-graph index under PyG's collate: the bounded plan is the
+    same plan (rows at / beyond the bound are empty either way) built with fewer radix passes."""
+    from gnn_elasticity_predictor_b200 import batching
+    b = pkg.synthetic_batch(n_graphs, atoms, k, seed=2, lg_inc="pyg")
+    n = b.edge_index.size(1)
+    assert 0 < b.lg_active_rows < n
+    for batch in (b, batching.pad_batch(b, align=64)[0]):
+        n = batch.edge_index.size(1)
+        idx = batch.lg_edge_index.to(DEV)
+        full = pkg.build_plan(idx, n)
+        fast = pkg.build_plan(idx, n, key_bound=batch.lg_active_rows)
+        assert int(fast.status.item()) & 4 == 0
+        for name in ("rowptr", "col", "eid", "rowptr_t", "col_t", "eid_t"):
+            assert torch.equal(getattr(full, name), getattr(fast, name)), name
+        assert ops._plan_kernels(idx.size(1), n, False, batch.lg_active_rows) <= ops._plan_kernels(idx.size(1), n)
+    wrong = pkg.build_plan(b.lg_edge_index.to(DEV), n, key_bound=b.lg_active_rows - 1)      # one index is at the bound
+    assert int(wrong.status.item()) & 4
+    with pytest.raises(ValueError):
+        wrong.check()
+
+
 def test_plan_wrong_source_sorted_hint_is_flagged():
     index = torch.tensor([[0, 2, 1], [1, 0, 2]])
     plan = pkg.build_plan(index.to(DEV), 3, source_sorted=True)
