@@ -80,7 +80,7 @@ class FusedAdamW:
 
 
 class _Captured:
-    __slots__ = ("graph", "graph_opt", "batch", "tz", "mask", "loss", "mean", "logvar", "kernels")
+    __slots__ = ("graph", "graph_opt", "batch", "tz", "mask", "weight", "loss", "mean", "logvar", "kernels")
 
 
 class TrainStep:
@@ -127,11 +127,11 @@ class TrainStep:
         self.eager_steps = 0
 
     # -- the step itself (eager; also what gets captured) ------------------------------------------------------
-    def _fwd_bwd(self, batch, tz: Tensor, mask: Optional[Tensor] = None):
+    def _fwd_bwd(self, batch, tz: Tensor, mask: Optional[Tensor] = None, weight: Optional[Tensor] = None):
         self.bucket.detach_grads()
         self.model.base.build_plans(batch)                 # CSR/CSC sorts of this batch: part of every step
         mean, logvar = self.model(batch)
-        loss = fused_gaussian_nll(mean, logvar, tz, self.log_sigma_l2, self.floor, mask=mask)
+        loss = fused_gaussian_nll(mean, logvar, tz, self.log_sigma_l2, self.floor, mask=mask, sample_weight=weight)
         (loss * self.loss_scale).backward()
         self.bucket.gather()                               # one multi-tensor copy into the flat gradient bucket
         return loss.detach(), mean.detach(), logvar.detach()
@@ -141,10 +141,10 @@ class TrainStep:
             self.opt.step()
         self.rng_step.add_(1)
 
-    def _eager(self, batch, tz, mask=None):
+    def _eager(self, batch, tz, mask=None, weight=None):
         prev, ops.RNG_STEP = ops.RNG_STEP, self.rng_step
         try:
-            out = self._fwd_bwd(batch, tz, mask)
+            out = self._fwd_bwd(batch, tz, mask, weight)
             if self.world > 1:
                 self.bucket.all_reduce(self.group)
             self._finish()
@@ -159,7 +159,8 @@ class TrainStep:
         return tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(batch.tensors().items())) + (
             batch.num_graphs, getattr(batch, "lg_active_rows", None), getattr(batch, "source_sorted", None))
 
-    def _capture(self, batch: GraphBatch, tz: Tensor, mask: Optional[Tensor] = None) -> _Captured:
+    def _capture(self, batch: GraphBatch, tz: Tensor, mask: Optional[Tensor] = None,
+                 weight: Optional[Tensor] = None) -> _Captured:
         cap = _Captured()
         cap.batch = batch._like()
         for k in GraphBatch._TENSORS:
@@ -167,13 +168,14 @@ class TrainStep:
             setattr(cap.batch, k, v.clone() if isinstance(v, Tensor) else v)
         cap.tz = tz.clone()
         cap.mask = None if mask is None else mask.clone()
+        cap.weight = None if weight is None else weight.clone()
         prev, ops.RNG_STEP = ops.RNG_STEP, self.rng_step
         torch.cuda.synchronize(self.dev)
         k0 = ops.STATS.kernels
         try:
             cap.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(cap.graph):
-                cap.loss, cap.mean, cap.logvar = self._fwd_bwd(cap.batch, cap.tz, cap.mask)
+                cap.loss, cap.mean, cap.logvar = self._fwd_bwd(cap.batch, cap.tz, cap.mask, cap.weight)
                 if self.world == 1:
                     self._finish()
             cap.graph_opt = None
@@ -194,8 +196,9 @@ class TrainStep:
         cap = self._captured.get(self.signature(batch_like) + (bool(masked),)) if isinstance(batch_like, GraphBatch) else None
         return None if cap is None else (cap.batch, cap.tz)
 
-    def step(self, batch, target_z: Tensor, mask: Optional[Tensor] = None):
-        """``mask`` (``[B]``, 1 = real graph) restricts the loss to real graphs.  With ``pad_to_buckets`` a ``GraphBatch``
+    def step(self, batch, target_z: Tensor, mask: Optional[Tensor] = None, sample_weight: Optional[Tensor] = None):
+        """``sample_weight`` (``[B]``): the per-sample loss weights of the reference's KNN weighting (``train.py:661-675``).
+        ``mask`` (``[B]``, 1 = real graph) restricts the loss to real graphs.  With ``pad_to_buckets`` a ``GraphBatch``
         is padded to its shape bucket first (``batching.pad_batch``), so ragged datasets replay one graph per bucket; the
         returned ``mean / logvar`` then have the bucket's graph count (real graphs first)."""
         if self.pad_to_buckets and isinstance(batch, GraphBatch) and not getattr(batch, "padded", False):
@@ -204,16 +207,20 @@ class TrainStep:
             tz = torch.zeros(batch.num_graphs, target_z.size(1), dtype=target_z.dtype, device=target_z.device)
             tz[:n_real] = target_z
             target_z = tz
+            if sample_weight is not None:
+                w = torch.ones(batch.num_graphs, dtype=sample_weight.dtype, device=sample_weight.device)
+                w[:n_real] = sample_weight
+                sample_weight = w
         if not self.use_graph or not isinstance(batch, GraphBatch):
-            return self._eager(batch, target_z, mask)
-        sig = self.signature(batch) + (mask is not None,)
+            return self._eager(batch, target_z, mask, sample_weight)
+        sig = self.signature(batch) + (mask is not None,) + ((True,) if sample_weight is not None else ())
         cap = self._captured.get(sig)
         if cap is None:
             seen = self._seen.get(sig, 0)
             self._seen[sig] = seen + 1
             if seen < self.graph_warmup:
-                return self._eager(batch, target_z, mask)
-            cap = self._captured[sig] = self._capture(batch, target_z, mask)
+                return self._eager(batch, target_z, mask, sample_weight)
+            cap = self._captured[sig] = self._capture(batch, target_z, mask, sample_weight)
         if batch is not cap.batch:                      # callers may fill the graph's own input buffers (static_inputs)
             for k, v in cap.batch.tensors().items():
                 v.copy_(getattr(batch, k), non_blocking=True)
@@ -221,6 +228,8 @@ class TrainStep:
             cap.tz.copy_(target_z, non_blocking=True)
         if mask is not None:
             cap.mask.copy_(mask, non_blocking=True)
+        if sample_weight is not None:
+            cap.weight.copy_(sample_weight, non_blocking=True)
         cap.graph.replay()
         if cap.graph_opt is not None:
             self.bucket.all_reduce(self.group)

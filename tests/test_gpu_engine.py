@@ -198,3 +198,23 @@ def test_isolated_row_elision_changes_nothing():
         assert float((a[2][k] - g).abs().max()) < 1e-4 * max(float(g.abs().max()), 1e-2 * gmax), k
     # a "bonds"-collated batch has no isolated prefix: the bound equals the number of bonds
     assert pkg.synthetic_batch(4, 16, 12, seed=1, lg_inc="bonds").lg_active_rows == 4 * 16 * 12
+
+
+def test_train_step_sample_weights_match_reference_weighting():
+    """Per-sample loss weights (the reference's KNN weighting, train.py:661-675: nll * w before the means) through the fused
+    loss, eager and replayed: same loss as the torch composition with the weights applied."""
+    m = _model(seed=4)
+    batch = pkg.synthetic_batch(6, 8, 4, seed=5).to(DEV)
+    tz = pkg.zscore_targets(batch.y, batch.num_graphs)
+    w = torch.tensor([0.5, 2.0, 1.0, 1.5, 0.25, 3.0], device=DEV)
+    with torch.no_grad():
+        mean, logvar = copy.deepcopy(m)(batch)
+    lv = torch.clamp(logvar.float(), min=-2.9)
+    want = ((0.5 * (lv + (mean.float() - tz) ** 2 / torch.exp(lv))) * w[:, None]).mean(1).mean() + 0.1 * (0.5 * lv).pow(2).mean()
+    ts = engine.TrainStep(m, lr=0.0, weight_decay=0.0, graph=True, graph_warmup=1)
+    got = [float(ts.step(batch, tz, sample_weight=w)[0]) for _ in range(3)]          # eager, then captured + replayed
+    assert ts.replays >= 1
+    for g in got:
+        assert abs(g - float(want)) <= 1e-5 * max(1.0, abs(float(want)))
+    plain = float(engine.TrainStep(copy.deepcopy(m), lr=0.0, weight_decay=0.0, graph=False).step(batch, tz)[0])
+    assert abs(plain - got[0]) > 1e-4                                               # the weights do change the loss
