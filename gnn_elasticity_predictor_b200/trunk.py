@@ -174,7 +174,8 @@ class _Trunk(torch.autograd.Function):
         d_b8 = torch.empty(nb2, 8 * hid, **f32)
         d_wc = torch.empty(nb2, hid, hid, **f32)
         d_par = torch.empty(nb2, 6 * hid, **f32)       # per block: dw_beta x3 | dgamma | dbias | dcvec
-        eye = torch.eye(hid, dtype=cd, device=dev)
+        # [Ws ; I] of every block at once (the identity block adds the atom-graph feature gradient inside the dx GEMM)
+        wtail_all = torch.cat([w8c[:, 7 * hid:], torch.eye(hid, dtype=cd, device=dev).expand(nb2, hid, hid)], dim=1)
         dn = dn.contiguous().float()
         de: Optional[Tensor] = None                    # fp32 gradient of the bond residual stream (None above the top)
         coefs, qts, gts = [], [], []
@@ -206,12 +207,12 @@ class _Trunk(torch.autograd.Function):
             else:
                 ops.raw_attn_bwd_s(dagg, dagg_lp, agg, q, k, v, qt, gt, cvf[idx], st["feat"], st["m"], st["z"],
                                    cfg.g_plan, h, dq, dk, dv, bbar, df_out, cfg.p_attn[idx], sa, oa, rs)
-            # dWc[t] = dagg_t^T abar_t: diagonal blocks of one dense [H, na] x [na, 4H] product (K = na is what costs)
-            gfull = torch.mm(dagg_lp.t(), st["abar_rows"].view(-1, h * hid), out_dtype=torch.float32)   # [H, 4H]
-            d_wc[idx].copy_(torch.stack([gfull[t * c:(t + 1) * c, t * hid:(t + 1) * hid] for t in range(h)]).view(hid, hid))
+            # dWc[t] = dagg_t^T abar_t: one batched [C, na] x [na, H] product per head, written straight into its slot
+            torch.bmm(dagg_lp.view(na, h, c).permute(1, 2, 0), st["abar_rows"].transpose(0, 1), out_dtype=torch.float32,
+                      out=d_wc[idx].view(h, c, hid))
             # dx = dy + [dx_r | df] [Ws ; I]  (all rows; the identity block adds df)  +  dbuf [Wq; Wk; Wv; WQT]  (active rows)
             w7, ws = w8c[idx, :7 * hid], w8c[idx, 7 * hid:]
-            wtail = torch.cat([ws, eye], dim=0) if dy2 is not None else ws
+            wtail = wtail_all[idx] if dy2 is not None else ws
             if dy is not None:
                 dx = torch.addmm(dy, dtail, wtail, out_dtype=torch.float32)
             else:
@@ -229,7 +230,7 @@ class _Trunk(torch.autograd.Function):
         tails = [mk(n_bonds, 2 * hid, dtype=cd, device=dev) for _ in range(nl)]            # LG block l: dx_r | df_l
         if side is not None:
             side.wait_stream(main)
-            for t in tails + [dn, d_w8, d_b8, d_wc, d_par, eye]:
+            for t in tails + [dn, d_w8, d_b8, d_wc, d_par, wtail_all]:
                 t.record_stream(side)
         for l in reversed(range(nl)):
             if side is None:
