@@ -51,88 +51,177 @@ struct GateExtra {
     const void *x_lp;           // forward: residual input in the STORAGE dtype, read when the fp32 `x` is null
 };
 
+// ---- per-lane cp.async ring --------------------------------------------------------------------------
+// The fast forward kernel is persistent (2 CTAs per SM) and streams its operand rows through shared memory: every lane copies
+// the 16-byte pieces of ITS OWN 8 channels of a row EPI_STAGES - 1 iterations ahead with cp.async and reads back only
+// what it copied itself, so the ring needs no barrier -- cp.async.wait_group is the only synchronisation -- and the
+// bytes in flight per SM (2 CTAs x 8 warps x 3 rows ahead) no longer depend on the register budget.
+template <typename T> struct EpiRing {
+    static constexpr int CT = (int)sizeof(T) * 8 / 16;          // 16-byte chunks per lane for 8 elements of T
+    static constexpr int STAGES = sizeof(T) == 2 ? 4 : 3;
+    static constexpr int NCH = 4 + 2 * CT;                      // f32 row (2) | T row (CT) | f32-or-T row (2) | T row (CT)
+    static constexpr int BYTES = EPI_WARPS * STAGES * NCH * 512;
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// this lane's 8 elements starting at g -> chunk slots `chunk`, `chunk + 1` (512 B apart: conflict-free across the warp)
+__device__ __forceinline__ void cp_row8(uint32_t lane_base, int chunk, const float *g) {
+    cp_async16(lane_base + chunk * 512, g);
+    cp_async16(lane_base + (chunk + 1) * 512, g + 4);
+}
+__device__ __forceinline__ void cp_row8(uint32_t lane_base, int chunk, const __nv_bfloat16 *g) {
+    cp_async16(lane_base + chunk * 512, g);
+}
+__device__ __forceinline__ F8 lds8(const uint4 *lane_ptr, int chunk, float) {
+    const uint4 a = lane_ptr[chunk * 32], b = lane_ptr[(chunk + 1) * 32];
+    F8 r;
+    r.v[0] = __uint_as_float(a.x); r.v[1] = __uint_as_float(a.y); r.v[2] = __uint_as_float(a.z); r.v[3] = __uint_as_float(a.w);
+    r.v[4] = __uint_as_float(b.x); r.v[5] = __uint_as_float(b.y); r.v[6] = __uint_as_float(b.z); r.v[7] = __uint_as_float(b.w);
+    return r;
+}
+__device__ __forceinline__ F8 lds8(const uint4 *lane_ptr, int chunk, __nv_bfloat16) {
+    const uint4 u = lane_ptr[chunk * 32];
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    F8 r;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        r.v[2 * i] = __uint_as_float(w[i] << 16);
+        r.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+    return r;
+}
+
 template <typename T, int LANES>
-__global__ void __launch_bounds__(EPI_THREADS)
+__global__ void __launch_bounds__(EPI_THREADS, 2)
 gate_ln_fwd_kernel(const float *__restrict__ agg, const T *__restrict__ xr, const float *__restrict__ x,
                    const float *__restrict__ wbeta, const float *__restrict__ gamma,
                    const float *__restrict__ bias, float *__restrict__ y, T *__restrict__ y_lp,
                    float *__restrict__ beta_out, float *__restrict__ mean_out, float *__restrict__ rstd_out,
                    int64_t n_rows, int hidden, float eps, float p_drop, float inv_keep, uint64_t seed,
                    uint64_t offset, const GateExtra X) {
-    constexpr int RPW = 32 / LANES;
-    const int lane = threadIdx.x & 31;
+    using R = EpiRing<T>;
+    constexpr int RPW = 32 / LANES, CT = R::CT, S = R::STAGES;
+    constexpr int C_AGG = 0, C_XR = 2, C_X = 2 + CT, C_AGGE = 4 + CT;
+    extern __shared__ uint4 epi_ring[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane % LANES;
-    const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t row = warp_id * RPW + lane / LANES;
-    const bool ok = row < n_rows;
     const int ch = sub * 8;
-    F8 af, sf, xf;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) af.v[c] = sf.v[c] = xf.v[c] = 0.f;
+    const int64_t slots = (int64_t)gridDim.x * EPI_WARPS * RPW;
+    const int64_t slot = ((int64_t)blockIdx.x * EPI_WARPS + warp) * RPW + lane / LANES;
+    const int64_t iters = (n_rows + slots - 1) / slots;
     const int64_t agg_rows = X.agg_rows < 0 ? n_rows : X.agg_rows;
-    const bool has_agg = row < agg_rows;
-    if (ok) {
-        if (has_agg) af = ld8(agg + row * hidden + ch);
-        sf = ld8(xr + row * X.ldxr + ch);
-        xf = x ? ld8(x + row * hidden + ch) : ld8(reinterpret_cast<const T *>(X.x_lp) + row * hidden + ch);
-        if (X.agge && has_agg) {   // agg = aggv + (Wc[t] abar_t)  [HEADS, agg_rows, C]  + c_t * S_t
-            const int C = hidden / X.heads, t = ch / C;
-            const F8 ef = ld8(reinterpret_cast<const T *>(X.agge) + ((int64_t)t * agg_rows + row) * C + (ch - t * C));
-            float sv = 0.f;
-            F8 cf;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) cf.v[c] = 0.f;
-            if (X.cvec) {
-                cf = ld8(X.cvec + ch);
-                sv = __ldg(X.stat_s + row * X.heads + t);
+    const int C = hidden / X.heads, t = ch / C;
+    const T *x_lp = reinterpret_cast<const T *>(X.x_lp);
+    const T *agge = reinterpret_cast<const T *>(X.agge);
+    const uint4 *my_ring = epi_ring + (size_t)warp * S * R::NCH * 32 + lane;
+    const uint32_t my_ring_s = (uint32_t)__cvta_generic_to_shared(my_ring);
+
+    auto issue = [&](int64_t it) {
+        const int64_t row = slot + it * slots;
+        if (it < iters && row < n_rows) {
+            const uint32_t base = my_ring_s + (uint32_t)(it % S) * (R::NCH * 512);
+            if (row < agg_rows) {
+                cp_row8(base, C_AGG, agg + row * hidden + ch);
+                if (agge) cp_row8(base, C_AGGE, agge + ((int64_t)t * agg_rows + row) * C + (ch - t * C));
             }
-#pragma unroll
-            for (int c = 0; c < 8; ++c) af.v[c] += ef.v[c] + cf.v[c] * sv;
+            cp_row8(base, C_XR, xr + row * X.ldxr + ch);
+            if (x) cp_row8(base, C_X, x + row * hidden + ch);
+            else cp_row8(base, C_X, x_lp + row * hidden + ch);
         }
-        if (X.agg_out && has_agg) st8(X.agg_out + row * hidden + ch, af);
-    }
-    const F8 w1 = ld8(wbeta + ch), w2 = ld8(wbeta + hidden + ch), w3 = ld8(wbeta + 2 * hidden + ch);
-    float zp = 0.f;
+        cp_async_commit();
+    };
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-        zp += w1.v[c] * af.v[c] + w2.v[c] * sf.v[c] + w3.v[c] * (af.v[c] - sf.v[c]);
-    const float zl = group_sum<LANES>(zp);
-    const float beta = 1.0f / (1.0f + expf(-zl));
-    F8 o;
-    float sum = 0.f;
+    for (int i = 0; i < S - 1; ++i) issue(i);
+
+    // gate logit  w1.a + w2.s + w3.(a - s)  =  (w1 + w3).a + (w2 - w3).s : two independent 8-term chains per lane
+    F8 w13, w23;
+    {
+        const F8 w1 = ld8(wbeta + ch), w2 = ld8(wbeta + hidden + ch), w3 = ld8(wbeta + 2 * hidden + ch);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        o.v[c] = beta * sf.v[c] + (1.0f - beta) * af.v[c];
-        sum += o.v[c];
+        for (int c = 0; c < 8; ++c) {
+            w13.v[c] = w1.v[c] + w3.v[c];
+            w23.v[c] = w2.v[c] - w3.v[c];
+        }
     }
-    const float mean = group_sum<LANES>(sum) / (float)hidden;
-    float sq = 0.f;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const float d = o.v[c] - mean;
-        sq = fmaf(d, d, sq);
-    }
-    const float var = group_sum<LANES>(sq) / (float)hidden;
-    const float rstd = 1.0f / sqrtf(var + eps);
-    if (!ok) return;
     const F8 gm = ld8(gamma + ch), bs = ld8(bias + ch);
-    float keep[8];
+    F8 cf;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) keep[c] = 1.f;
-    if (p_drop > 0.f)
-        dropout8(seed, offset + (X.rng_step ? *X.rng_step : 0ull), (uint64_t)row * hidden + ch, p_drop, inv_keep, keep);
-    F8 out;
+    for (int c = 0; c < 8; ++c) cf.v[c] = 0.f;
+    if (agge && X.cvec) cf = ld8(X.cvec + ch);
+    const uint64_t rng_off = offset + (X.rng_step ? *X.rng_step : 0ull);
+    const float inv_h = 1.0f / (float)hidden;
+
+    for (int64_t it = 0; it < iters; ++it) {
+        issue(it + S - 1);
+        cp_async_wait<S - 1>();
+        const int64_t row = slot + it * slots;
+        const bool ok = row < n_rows;
+        const bool has_agg = ok && row < agg_rows;
+        const uint4 *st = my_ring + (size_t)(it % S) * (R::NCH * 32);
+        F8 af, sf, xf;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const float yv = (o.v[c] - mean) * rstd * gm.v[c] + bs.v[c];
-        out.v[c] = xf.v[c] + fmaxf(yv, 0.f) * keep[c];
-    }
-    st8(y + row * hidden + ch, out);
-    if (y_lp) st8(y_lp + row * hidden + ch, out);
-    if (sub == 0) {
-        beta_out[row] = beta;
-        mean_out[row] = mean;
-        rstd_out[row] = rstd;
+        for (int c = 0; c < 8; ++c) af.v[c] = sf.v[c] = xf.v[c] = 0.f;
+        if (ok) {
+            sf = lds8(st, C_XR, T());
+            xf = x ? lds8(st, C_X, float()) : lds8(st, C_X, T());
+        }
+        if (has_agg) {
+            af = lds8(st, C_AGG, float());
+            if (agge) {                 // agg = aggv + (Wc[t] abar_t)  [HEADS, agg_rows, C]  + c_t * S_t
+                const F8 ef = lds8(st, C_AGGE, T());
+                const float sv = X.cvec ? __ldg(X.stat_s + row * X.heads + t) : 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) af.v[c] += ef.v[c] + cf.v[c] * sv;
+            }
+            if (X.agg_out) st8(X.agg_out + row * hidden + ch, af);
+        }
+        float za = 0.f, zs = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            za = fmaf(w13.v[c], af.v[c], za);
+            zs = fmaf(w23.v[c], sf.v[c], zs);
+        }
+        const float zl = group_sum<LANES>(za + zs);
+        const float beta = 1.0f / (1.0f + expf(-zl));
+        F8 o;
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            o.v[c] = beta * sf.v[c] + (1.0f - beta) * af.v[c];
+            sum += o.v[c];
+        }
+        const float mean = group_sum<LANES>(sum) * inv_h;
+        float sq = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float d = o.v[c] - mean;
+            sq = fmaf(d, d, sq);
+        }
+        const float var = group_sum<LANES>(sq) * inv_h;
+        const float rstd = 1.0f / sqrtf(var + eps);
+        if (!ok) continue;
+        float keep[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) keep[c] = 1.f;
+        if (p_drop > 0.f) dropout8(seed, rng_off, (uint64_t)row * hidden + ch, p_drop, inv_keep, keep);
+        F8 out;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float yv = (o.v[c] - mean) * rstd * gm.v[c] + bs.v[c];
+            out.v[c] = xf.v[c] + fmaxf(yv, 0.f) * keep[c];
+        }
+        st8(y + row * hidden + ch, out);
+        if (y_lp) st8(y_lp + row * hidden + ch, out);
+        if (sub == 0) {
+            beta_out[row] = beta;
+            mean_out[row] = mean;
+            rstd_out[row] = rstd;
+        }
     }
 }
 
@@ -419,9 +508,11 @@ static void launch_epi_fwd(const float *agg, const void *xr, const float *x, con
                            int64_t n_rows, int hidden, float eps, float p_drop, uint64_t seed, uint64_t offset,
                            const GateExtra &X, cudaStream_t st) {
     const int rows_per_block = EPI_WARPS * (32 / LANES);
-    const unsigned grid = (unsigned)((n_rows + rows_per_block - 1) / rows_per_block);
+    const int64_t want = (n_rows + rows_per_block - 1) / rows_per_block;
+    const unsigned grid = (unsigned)(want < EPI_PARTIAL_BLOCKS ? want : EPI_PARTIAL_BLOCKS);      // persistent: 2 CTAs per SM
     const float inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
-    gate_ln_fwd_kernel<T, LANES><<<grid, EPI_THREADS, 0, st>>>(agg, (const T *)xr, x, wbeta, gamma, bias, y, (T *)y_lp,
+    cudaFuncSetAttribute(gate_ln_fwd_kernel<T, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, EpiRing<T>::BYTES);
+    gate_ln_fwd_kernel<T, LANES><<<grid, EPI_THREADS, EpiRing<T>::BYTES, st>>>(agg, (const T *)xr, x, wbeta, gamma, bias, y, (T *)y_lp,
                                                                beta, mean, rstd, n_rows, hidden, eps, p_drop, inv_keep,
                                                                seed, offset, X);
 }
