@@ -272,6 +272,37 @@ def test_gate_ln_forward_backward(hidden, dtype):
         assert rel_err(got.grad.float().cpu(), want.grad) < tol, name
 
 
+@pytest.mark.parametrize("hidden,dtype", [(256, torch.bfloat16), (256, torch.float32), (64, torch.bfloat16), (8, torch.float32)])
+def test_gate_ln_forward_many_rows_active_prefix(hidden, dtype):
+    """Enough rows that every warp of the persistent forward wraps its cp.async ring several times; only a prefix of the
+    rows has an aggregate (line-graph elision), the aggregate is assembled in-kernel, the residual enters in either dtype."""
+    n, na, heads = 30011, 2600, 4 if hidden >= 32 else 1
+    c = hidden // heads
+    g = torch.Generator().manual_seed(hidden + 1)
+    r = lambda *s: torch.randn(*s, generator=g)                                       # noqa: E731
+    aggv, agge, cvec, stat = r(na, hidden), r(heads, na, c).to(dtype), r(hidden), r(na, heads).abs()
+    xr, x32, xlp = r(n, hidden).to(dtype), r(n, hidden), r(n, hidden).to(dtype)
+    wb, gm, bl = r(3 * hidden) * 0.2, torch.rand(hidden, generator=g) + 0.5, r(hidden) * 0.3
+    d = lambda t: t.to(DEV)                                                           # noqa: E731
+    for x_in, x_lp in ((x32, None), (None, xlp)):
+        y, y_lp, agg, beta, mean, rstd = ops.raw_gate_ln_fwd2(d(aggv), d(agge), d(cvec), d(stat), heads, d(xr), None if x_in is None
+                                                              else d(x_in), d(wb), d(gm), d(bl), 1e-5, 0.0, 1, 0, True, None,
+                                                              agg_rows=na, x_lp=None if x_lp is None else d(x_lp))
+        a = torch.zeros(n, hidden, dtype=torch.float64)
+        a[:na] = (aggv.double() + agge.double().permute(1, 0, 2).reshape(na, hidden)
+                  + cvec.double() * stat.double().repeat_interleave(c, dim=1))
+        s = xr.double()
+        w1, w2, w3 = wb.double().split(hidden)
+        bt = torch.sigmoid(a @ w1 + s @ w2 + (a - s) @ w3)
+        o = bt[:, None] * s + (1 - bt[:, None]) * a
+        res = (x32 if x_in is not None else xlp).double()
+        ref = res + torch.relu(torch.nn.functional.layer_norm(o, (hidden,), gm.double(), bl.double(), 1e-5))
+        assert rel_err(y.cpu(), ref) < 1e-5
+        assert rel_err(y_lp.float().cpu(), ref) < (1e-5 if dtype == torch.float32 else 1e-2)
+        assert rel_err(agg[:na].cpu(), a[:na]) < 1e-6 and rel_err(beta.cpu(), bt) < 1e-5
+        assert rel_err(mean.cpu(), o.mean(1)) < 1e-5 and rel_err(rstd.cpu(), 1 / torch.sqrt(o.var(1, unbiased=False) + 1e-5)) < 1e-5
+
+
 def test_gate_ln_dropout_mask_shared_by_forward_and_backward():
     n, hidden = 500, 256
     g = torch.Generator().manual_seed(0)
