@@ -15,6 +15,7 @@
 // phase 2 and lands during the next chunk's phase 1), cp.async 16 B per lane.  Attention dropout is keyed by the
 // angle's CSR position, so forward and backward agree without an edge-id lookup.
 #include <math.h>
+#include <stdlib.h>
 
 #include "mma.cuh"
 
@@ -719,6 +720,7 @@ constexpr int LGA_WARPS = 6;
 constexpr int LGA_MAXL = 4;
 constexpr int LGA_IMG_ROWS = 8 * LGA_MAXL;                  // 32 rows of 528 B per target row
 constexpr int LGA_PER_WARP = 2 * LGA_IMG_ROWS * LG_ROWB;    // double-buffered by target row
+constexpr int LGA_COEF = LGA_MAXL * LG_E * 32;              // per warp: coef rows of the NEXT chunk, [layer][edge][8] f32 (cp.async)
 
 struct LgAngleParams {
     const __nv_bfloat16 *a_csr;
@@ -739,6 +741,8 @@ lg_angle_grad_kernel(const LgAngleParams P) {
     const int g = lane >> 2, q = lane & 3;
     const uint32_t img2 = smem_u32(smem_raw) + LG_IMG1;
     const uint32_t wbase_u32 = smem_u32(smem_raw) + LG_IMG + (uint32_t)warp * LGA_PER_WARP;
+    const unsigned char *cbase = smem_raw + LG_IMG + LGA_WARPS * LGA_PER_WARP + warp * LGA_COEF;
+    const uint32_t cbase_u32 = smem_u32(cbase);
     for (int off = lane * 16; off < LGA_PER_WARP; off += 512) sts128(wbase_u32 + off, make_uint4(0, 0, 0, 0));
     __syncthreads();
 
@@ -780,23 +784,29 @@ lg_angle_grad_kernel(const LgAngleParams P) {
             af[2] = e0 < P.n_edges ? __ldg(ap + (int64_t)e0 * 8 + 4 + q) : 0u;
             af[3] = e1 < P.n_edges ? __ldg(ap + (int64_t)e1 * 8 + 4 + q) : 0u;
         };
+        // the 16 coefficient rows of a chunk are 512 contiguous bytes per layer (CSR order): one 16-byte piece per lane,
+        // copied one chunk ahead so their latency hides behind the MMAs of the current chunk
+        auto stage_coef = [&](int pos) {
+            if (pos + (lane >> 1) < P.n_edges) {
+#pragma unroll
+                for (int l = 0; l < LGA_MAXL; ++l)
+                    if (l < P.n_layers) cp_async16(cbase_u32 + l * (LG_E * 32) + lane * 16, P.coef[l] + (int64_t)pos * 8 + lane * 4);
+            }
+        };
         Chunk A, B;
         uint32_t afA[4], afB[4] = {0u, 0u, 0u, 0u};
         fetch(A, afA);
         int buf = 0;
         stage_row(0, A.row);
+        stage_coef(A.pos);
         cp_async_commit();
         B.n = 0; B.row = 0; B.pos = 0; B.first = false; B.last = false;
         const uint32_t toff = (uint32_t)(((lane >> 4) * 8 + (lane & 7)) * LG_ROWB + ((lane >> 3) & 1) * 16);
 
         for (;;) {
             const bool have_next = !cur.done();
-            if (have_next) {
-                fetch(B, afB);
-                if (B.first) stage_row(buf ^ 1, B.row);
-            }
-            cp_async_commit();
-            cp_async_wait<1>();
+            if (have_next) fetch(B, afB);
+            cp_async_wait<0>();              // this chunk's coefficient rows and its target row's image (both issued a chunk ago)
             __syncwarp();
             const uint32_t image = wbase_u32 + (uint32_t)buf * LGA_IMG_ROWS * LG_ROWB;
             const int n = A.n;
@@ -810,13 +820,19 @@ lg_angle_grad_kernel(const LgAngleParams P) {
                     const int l = 2 * kp + hlf;
                     float2 x0 = make_float2(0.f, 0.f), x1 = make_float2(0.f, 0.f);
                     if (l < P.n_layers) {
-                        if (v0) x0 = __ldg(reinterpret_cast<const float2 *>(P.coef[l] + (int64_t)(A.pos + g) * 8 + 2 * q));
-                        if (v1) x1 = __ldg(reinterpret_cast<const float2 *>(P.coef[l] + (int64_t)(A.pos + g + 8) * 8 + 2 * q));
+                        if (v0) x0 = *reinterpret_cast<const float2 *>(cbase + l * (LG_E * 32) + g * 32 + q * 8);
+                        if (v1) x1 = *reinterpret_cast<const float2 *>(cbase + l * (LG_E * 32) + (g + 8) * 32 + q * 8);
                     }
                     cf[kp][0][hlf] = pack_bf16(x0.x, x0.y);
                     cf[kp][1][hlf] = pack_bf16(x1.x, x1.y);
                 }
             }
+            __syncwarp();                    // every lane has its fragments: the coefficient buffer can take the next chunk
+            if (have_next) {
+                stage_coef(B.pos);
+                if (B.first) stage_row(buf ^ 1, B.row);
+            }
+            cp_async_commit();
             const uint32_t ba0 = movmatrix_trans(afA[0]), ba1 = movmatrix_trans(afA[1]);
             const uint32_t ba2 = movmatrix_trans(afA[2]), ba3 = movmatrix_trans(afA[3]);
 #pragma unroll
@@ -884,7 +900,7 @@ __global__ void lg_angle_reduce_kernel(const float *__restrict__ partials, float
 
 static int lg_grid(int64_t n_nodes, int64_t n_edges, int warps) {
     const int64_t work = n_edges + (int64_t)ROW_KAPPA * n_nodes;
-    int64_t blocks = 148 * 3;
+    int64_t blocks = 148 * 2;          // one CTA is resident per SM; two per SM even out the row-granular static split
     const int64_t min_work_per_warp = 64;
     if (work / (blocks * warps) < min_work_per_warp) blocks = work / (min_work_per_warp * warps) + 1;
     return (int)blocks;
@@ -1045,9 +1061,14 @@ extern "C" int alignn_lg_angle_grad(const void *a_csr, const float *w1, const fl
     }
     p.partials = partials; p.n_nodes = (int)n_nodes; p.n_edges = (int)n_edges; p.in_dim = in_dim; p.n_layers = n_layers;
     p.ldqt = ldqt; p.hsqt = hsqt; p.ldgt = ldgt; p.hsgt = hsgt;
-    constexpr int SMEM = LG_IMG + LGA_WARPS * LGA_PER_WARP;
+    constexpr int SMEM = LG_IMG + LGA_WARPS * (LGA_PER_WARP + LGA_COEF);
     static_assert(SMEM >= LGA_WARPS * 4096 * 4, "reduction buffer aliases the pipeline buffers");
-    const int grid = lg_grid(n_nodes, n_edges, LGA_WARPS);
+    static_assert(SMEM <= 227 * 1024, "over the per-CTA shared-memory limit");
+    int grid = lg_grid(n_nodes, n_edges, LGA_WARPS);
+    if (const char *e = getenv("ALIGNN_LGA_BLOCKS")) {           // tuning knob (never more CTAs than the partials buffer holds)
+        const int want = atoi(e);
+        if (want >= 1 && want < grid) grid = want;
+    }
     ALIGNN_CUDA_TRY(cudaFuncSetAttribute(lg_angle_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     lg_angle_grad_kernel<<<grid, LGA_WARPS * 32, SMEM, st>>>(p);
     ALIGNN_LAUNCH_CHECK();
