@@ -716,10 +716,11 @@ lgattn_bwd_kernel(const LgBwdParams P) {
 // dW1ext[256 x 16] += mask(DF^T)[256 x 16 edges] . a[16 edges x 16].  Accumulators stay in registers for the whole
 // kernel; CTA-level then grid-level reductions run in a fixed order (no atomics).
 // ------------------------------------------------------------------------------------------------------------
-constexpr int LGA_WARPS = 6;
+constexpr int LGA_WARPS = 8;                                // two per scheduler; 8 x 32 x 255 registers is the whole file
 constexpr int LGA_MAXL = 4;
 constexpr int LGA_IMG_ROWS = 8 * LGA_MAXL;                  // 32 rows of 528 B per target row
-constexpr int LGA_PER_WARP = 2 * LGA_IMG_ROWS * LG_ROWB;    // double-buffered by target row
+constexpr int LGA_PER_WARP = LGA_IMG_ROWS * LG_ROWB;        // ONE image per warp: restaged at a row change (once per ~8 chunks;
+                                                            // the other warps cover it), which is what lets 8 warps fit
 constexpr int LGA_COEF = LGA_MAXL * LG_E * 32;              // per warp: coef rows of the NEXT chunk, [layer][edge][8] f32 (cp.async)
 
 struct LgAngleParams {
@@ -763,8 +764,8 @@ lg_angle_grad_kernel(const LgAngleParams P) {
     if (!cur.done()) {
         const uint32_t *ap = reinterpret_cast<const uint32_t *>(P.a_csr);
         // image rows of layer l: 8l + t = gt^l head t (pairs with a~), 8l + 4 + t = qt^l head t (pairs with ds)
-        auto stage_row = [&](int buf, int row) {
-            const uint32_t dst = wbase_u32 + (uint32_t)buf * LGA_IMG_ROWS * LG_ROWB + lane * 16;
+        auto stage_row = [&](int row) {
+            const uint32_t dst = wbase_u32 + lane * 16;
 #pragma unroll
             for (int l = 0; l < LGA_MAXL; ++l) {
                 if (l < P.n_layers) {
@@ -796,8 +797,7 @@ lg_angle_grad_kernel(const LgAngleParams P) {
         Chunk A, B;
         uint32_t afA[4], afB[4] = {0u, 0u, 0u, 0u};
         fetch(A, afA);
-        int buf = 0;
-        stage_row(0, A.row);
+        stage_row(A.row);
         stage_coef(A.pos);
         cp_async_commit();
         B.n = 0; B.row = 0; B.pos = 0; B.first = false; B.last = false;
@@ -808,7 +808,7 @@ lg_angle_grad_kernel(const LgAngleParams P) {
             if (have_next) fetch(B, afB);
             cp_async_wait<0>();              // this chunk's coefficient rows and its target row's image (both issued a chunk ago)
             __syncwarp();
-            const uint32_t image = wbase_u32 + (uint32_t)buf * LGA_IMG_ROWS * LG_ROWB;
+            const uint32_t image = wbase_u32;
             const int n = A.n;
             const bool v0 = g < n, v1 = g + 8 < n;
             // B fragments of COEF^T: k = coefficient column (2q, 2q+1) of layer 2kp (+8: layer 2kp+1), n = edge g
@@ -828,10 +828,7 @@ lg_angle_grad_kernel(const LgAngleParams P) {
                 }
             }
             __syncwarp();                    // every lane has its fragments: the coefficient buffer can take the next chunk
-            if (have_next) {
-                stage_coef(B.pos);
-                if (B.first) stage_row(buf ^ 1, B.row);
-            }
+            if (have_next) stage_coef(B.pos);
             cp_async_commit();
             const uint32_t ba0 = movmatrix_trans(afA[0]), ba1 = movmatrix_trans(afA[1]);
             const uint32_t ba2 = movmatrix_trans(afA[2]), ba3 = movmatrix_trans(afA[3]);
@@ -860,7 +857,10 @@ lg_angle_grad_kernel(const LgAngleParams P) {
             }
             __syncwarp();
             if (!have_next) break;
-            if (B.first) buf ^= 1;
+            if (B.first) {                   // every lane is done with this row's image
+                stage_row(B.row);
+                cp_async_commit();
+            }
             A = B;
 #pragma unroll
             for (int i = 0; i < 4; ++i) afA[i] = afB[i];
