@@ -445,8 +445,9 @@ struct LgBwdParams {
     uint64_t seed, offset;
 };
 
-constexpr int LGB_WARPS = 6;
-constexpr int LGB_PER_WARP = 4 * LG_TILE;    // (K, V) x 2 stages
+constexpr int LGB_WARPS = 8;                 // two per scheduler (6 left two schedulers with a single warp)
+constexpr int LGB_PER_WARP = 3 * LG_TILE;    // K0, K1, V: K is read by both phases (double-buffered), V by phase 1 only --
+                                             // the next chunk's V rows are gathered behind phase 2 into the same tile
 
 __global__ void __launch_bounds__(LGB_WARPS * 32, 1)
 lgattn_bwd_kernel(const LgBwdParams P) {
@@ -524,9 +525,10 @@ lgattn_bwd_kernel(const LgBwdParams P) {
     Chunk A, B;
     int jA, jB = 0;
     uint32_t afA[4], afB[4] = {0u, 0u, 0u, 0u};
+    const uint32_t vtile = wbase_u32 + 2 * LG_TILE;
     fetch(A, jA, afA);
     gather_rows(wbase_u32, P.k, P.ldk, jA, A.n, lane);
-    gather_rows(wbase_u32 + LG_TILE, P.v, P.ldv, jA, A.n, lane);
+    gather_rows(vtile, P.v, P.ldv, jA, A.n, lane);
     cp_async_commit();
 
     uint4 xf[8], kvf[2];
@@ -543,12 +545,10 @@ lgattn_bwd_kernel(const LgBwdParams P) {
         const bool have_next = !cur.done();
         if (have_next) {
             fetch(B, jB, afB);
-            const uint32_t nb = wbase_u32 + (uint32_t)(s ^ 1) * 2 * LG_TILE;
-            gather_rows(nb, P.k, P.ldk, jB, B.n, lane);
-            gather_rows(nb + LG_TILE, P.v, P.ldv, jB, B.n, lane);
+            gather_rows(wbase_u32 + (uint32_t)(s ^ 1) * LG_TILE, P.k, P.ldk, jB, B.n, lane);
         }
         cp_async_commit();
-        const uint32_t ktile = wbase_u32 + (uint32_t)s * 2 * LG_TILE, vtile = ktile + LG_TILE;
+        const uint32_t ktile = wbase_u32 + (uint32_t)s * LG_TILE;
         const int row = A.row, n = A.n;
         if (A.first) {
             zero_rows(next_unwritten, row);
@@ -576,7 +576,7 @@ lgattn_bwd_kernel(const LgBwdParams P) {
         float dr00 = 1.f, dr01 = 1.f, dr10 = 1.f, dr11 = 1.f;   // keep-scales: off the critical path (see forward)
         if (P.p_drop > 0.f)
             dropout_scale_quad(P.seed, rng_off, (uint64_t)A.pos, g, q, P.p_drop, P.inv_keep, dr00, dr01, dr10, dr11);
-        cp_async_wait<1>();
+        cp_async_wait<1>();              // K and V of this chunk (K of the next may still be in flight)
         __syncwarp();
 
         // ---- phase 1 -------------------------------------------------------------------------------------------------
@@ -646,6 +646,9 @@ lgattn_bwd_kernel(const LgBwdParams P) {
         const uint32_t bk0 = g < 4 ? 0u : tlo, bk1 = g < 4 ? 0u : thi;
 
         if (have_next && B.first) load_row(xf, kvf, B.row);
+        __syncwarp();                    // every lane is done with this chunk's V rows: the tile takes the next chunk's
+        if (have_next) gather_rows(vtile, P.v, P.ldv, jB, B.n, lane);
+        cp_async_commit();
 
         // ---- phase 2 -------------------------------------------------------------------------------------------------
         {
@@ -665,7 +668,8 @@ lgattn_bwd_kernel(const LgBwdParams P) {
         }
         if (A.last) {
             __syncwarp();
-            const uint32_t st0 = vtile + (uint32_t)((2 * q) * LG_STG + g) * 4, st1 = st0 + LG_STG * 4;   // V is dead
+            const uint32_t stg = ktile;      // this chunk's K rows are dead after phase 2
+            const uint32_t st0 = stg + (uint32_t)((2 * q) * LG_STG + g) * 4, st1 = st0 + LG_STG * 4;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 sts32f(st0 + j * 64, acc[j][0]);
@@ -679,18 +683,22 @@ lgattn_bwd_kernel(const LgBwdParams P) {
                 const int ch = half * 128 + 4 * lane;
 #pragma unroll
                 for (int t = 0; t < LG_HEADS; ++t) {
-                    const float4 x = lds128f(vtile + (uint32_t)(t * LG_STG + ch) * 4);
+                    const float4 x = lds128f(stg + (uint32_t)(t * LG_STG + ch) * 4);
                     uint2 ov;
                     ov.x = pack_bf16(x.x, x.y);
                     ov.y = pack_bf16(x.z, x.w);
                     *reinterpret_cast<uint2 *>(P.bbar + (int64_t)row * P.ldbb + (int64_t)t * P.hsbb + ch) = ov;
                 }
-                const float4 y = lds128f(vtile + (uint32_t)((4 + (ch >> 6)) * LG_STG + ch) * 4);
+                const float4 y = lds128f(stg + (uint32_t)((4 + (ch >> 6)) * LG_STG + ch) * 4);
                 uint2 ov;
                 ov.x = pack_bf16(y.x, y.y);
                 ov.y = pack_bf16(y.z, y.w);
                 *reinterpret_cast<uint2 *>(P.dq + (int64_t)row * P.lddq + ch) = ov;
             }
+            // the fp32 staging values must not stay behind as "K rows": rows past a later chunk's edge count are never
+            // gathered but still enter K^T . DS with ds = 0, and 0 x (a NaN bit pattern) would poison dq
+            __syncwarp();
+            for (int off = lane * 16; off < LG_TILE; off += 512) sts128(stg + off, make_uint4(0, 0, 0, 0));
             next_unwritten = row + 1;
         }
         __syncwarp();
