@@ -17,6 +17,7 @@
 // (rows padded to 528 B so ldmatrix is conflict-free); B operands of phase 1 come straight from global memory in a channel
 // permutation shared by both operands (one 16-byte load feeds two MMAs); P goes from accumulator to B-fragment
 // layout with two movmatrix.  No atomics; every row's result is independent of the launch geometry.
+#include <stdlib.h>
 #include <math.h>
 
 #include "mma.cuh"
@@ -28,7 +29,11 @@ constexpr int MM_HEADS = 4;
 constexpr int MM_E = 16;                      // edges per chunk
 constexpr int MM_ROWB = 528;                  // bytes per staged row (512 + 16: 8 consecutive rows hit 8 distinct 16-byte bank groups)
 constexpr int MM_TILE = MM_E * MM_ROWB;       // 8448
-constexpr int MM_WARPS = 4;
+constexpr int MM_WARPS = 8;                   // two per scheduler
+constexpr int MM_STAGES = 1;                  // (K, V, F) tile sets per warp.  One set x 8 warps fills the SM's shared memory:
+                                              // a warp gathers, waits and computes in turn and its scheduler partner covers
+                                              // the wait -- measured faster than 4 warps with two sets each (one warp per
+                                              // scheduler, nothing to cover MMA latency or the row-start loads)
 constexpr int MM_STG = 260;                   // floats per column of the epilogue staging buffer
 
 struct MmFwdParams {
@@ -64,7 +69,7 @@ __device__ __forceinline__ void load_fwd_row(FwdRowFrags &rf, const MmFwdParams 
 
 __global__ void __launch_bounds__(MM_WARPS * 32, 1)
 edgeattn_mma_fwd_kernel(const MmFwdParams P) {
-    constexpr int PER_WARP = 2 * 3 * MM_TILE + 64;
+    constexpr int PER_WARP = MM_STAGES * 3 * MM_TILE + 64;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, q = lane & 3;
@@ -79,7 +84,7 @@ edgeattn_mma_fwd_kernel(const MmFwdParams P) {
     const int e_end = __ldg(P.rowptr + r1);
 
     // padding rows of a chunk are multiplied by exact zeros in phase 2: they must hold finite values
-    for (int off = lane * 16; off < 2 * 3 * MM_TILE; off += 32 * 16) sts128(base_u32 + off, make_uint4(0, 0, 0, 0));
+    for (int off = lane * 16; off < MM_STAGES * 3 * MM_TILE; off += 32 * 16) sts128(base_u32 + off, make_uint4(0, 0, 0, 0));
     __syncwarp();
 
     StageCursor<MM_E> prod, cons;
@@ -142,8 +147,8 @@ edgeattn_mma_fwd_kernel(const MmFwdParams P) {
     const int t_own = g & 3;
 
     for (int it = 0; !cons.done(); ++it) {
-        const int s = it & 1;
-        issue(s ^ 1);
+        const int s = MM_STAGES == 2 ? (it & 1) : 0;
+        if (MM_STAGES == 2) issue(s ^ 1);
         StageCursor<MM_E> nxt = cons;
         nxt.advance(P.rowptr);
         const int n = cons.count();
@@ -157,28 +162,34 @@ edgeattn_mma_fwd_kernel(const MmFwdParams P) {
             m0 = m1 = -INFINITY;
             z0 = z1 = zd0 = zd1 = 0.f;
         }
-        cp_async_wait<1>();   // everything but the group just committed (the next chunk) has landed
+        cp_async_wait<MM_STAGES - 1>();   // everything but the group just committed (the next chunk, if prefetched) has landed
         __syncwarp();
         const uint32_t ktile = base_u32 + (uint32_t)s * 3 * MM_TILE, vtile = ktile + MM_TILE, ftile = ktile + 2 * MM_TILE;
 
         // ---- phase 1: logits ------------------------------------------------------------------------------
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        float c[4];
         {
+            // four independent accumulator chains (8 MMAs each) instead of one of 32: with one warp per scheduler nothing
+            // else hides the MMA latency
+            float ca[4] = {0.f, 0.f, 0.f, 0.f}, cb_[4] = {0.f, 0.f, 0.f, 0.f};
+            float ck0[4] = {0.f, 0.f, 0.f, 0.f}, ck1[4] = {0.f, 0.f, 0.f, 0.f};
             const uint32_t fa = ftile + g * MM_ROWB + q * 16, ka = ktile + g * MM_ROWB + q * 16;
 #pragma unroll
             for (int cb = 0; cb < 8; ++cb) {
                 const uint4 x = lds128(fa + cb * 64), y = lds128(fa + 8 * MM_ROWB + cb * 64);
-                mma_bf16(c, x.x, y.x, x.y, y.y, rf.qt[cb].x, rf.qt[cb].y);
-                mma_bf16(c, x.z, y.z, x.w, y.w, rf.qt[cb].z, rf.qt[cb].w);
+                mma_bf16(ca, x.x, y.x, x.y, y.y, rf.qt[cb].x, rf.qt[cb].y);
+                mma_bf16(cb_, x.z, y.z, x.w, y.w, rf.qt[cb].z, rf.qt[cb].w);
             }
 #pragma unroll
             for (int cb = 0; cb < 8; ++cb) {
                 const uint4 x = lds128(ka + cb * 64), y = lds128(ka + 8 * MM_ROWB + cb * 64);
                 const bool own = (cb >> 1) == t_own;
                 const uint4 bq = rf.qv[cb & 1];
-                mma_bf16(c, x.x, y.x, x.y, y.y, own ? bq.x : 0u, own ? bq.y : 0u);
-                mma_bf16(c, x.z, y.z, x.w, y.w, own ? bq.z : 0u, own ? bq.w : 0u);
+                mma_bf16(ck0, x.x, y.x, x.y, y.y, own ? bq.x : 0u, own ? bq.y : 0u);
+                mma_bf16(ck1, x.z, y.z, x.w, y.w, own ? bq.z : 0u, own ? bq.w : 0u);
             }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) c[i] = (ca[i] + cb_[i]) + (ck0[i] + ck1[i]);
         }
         // ---- online softmax over the chunk (columns = heads; rows g and g+8) --------------------------------
         const bool v0 = g < n, v1 = g + 8 < n;
@@ -272,6 +283,7 @@ edgeattn_mma_fwd_kernel(const MmFwdParams P) {
             next_unwritten = row + 1;
         }
         __syncwarp();          // every lane is done with stage s before it is refilled
+        if (MM_STAGES == 1) issue(0);
         cons = nxt;
     }
     zero_rows(next_unwritten, r1);
@@ -331,12 +343,12 @@ __device__ __forceinline__ void load_bwd_row(BwdRowFrags &rf, const MmBwdParams 
 template <bool ACCUM>
 __global__ void __launch_bounds__(MM_WARPS * 32, 1)
 edgeattn_mma_bwd_kernel(const MmBwdParams P) {
-    constexpr int PER_WARP = 2 * 3 * MM_TILE + 64 + 128;
+    constexpr int PER_WARP = MM_STAGES * 3 * MM_TILE + 64 + 128;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, q = lane & 3;
     unsigned char *base = smem_raw + (size_t)warp * PER_WARP;
-    int *eid_stash = reinterpret_cast<int *>(base + 2 * 3 * MM_TILE + 64);   // [2][16]
+    int *eid_stash = reinterpret_cast<int *>(base + MM_STAGES * 3 * MM_TILE + 64);   // [MM_STAGES][16]
     const uint32_t base_u32 = smem_u32(base);
 
     const int64_t W = (int64_t)gridDim.x * MM_WARPS, w = (int64_t)blockIdx.x * MM_WARPS + warp;
@@ -346,7 +358,7 @@ edgeattn_mma_bwd_kernel(const MmBwdParams P) {
     if (r0 >= r1) return;
     const int e_end = __ldg(P.rowptr + r1);
 
-    for (int off = lane * 16; off < 2 * 3 * MM_TILE; off += 32 * 16) sts128(base_u32 + off, make_uint4(0, 0, 0, 0));
+    for (int off = lane * 16; off < MM_STAGES * 3 * MM_TILE; off += 32 * 16) sts128(base_u32 + off, make_uint4(0, 0, 0, 0));
     __syncwarp();
 
     StageCursor<MM_E> prod, cons;
@@ -405,8 +417,8 @@ edgeattn_mma_bwd_kernel(const MmBwdParams P) {
     const int hsel = 2 * (q & 1);   // this lane's coefficient columns are heads hsel, hsel + 1
 
     for (int it = 0; !cons.done(); ++it) {
-        const int s = it & 1;
-        issue(s ^ 1);
+        const int s = MM_STAGES == 2 ? (it & 1) : 0;
+        if (MM_STAGES == 2) issue(s ^ 1);
         StageCursor<MM_E> nxt = cons;
         nxt.advance(P.rowptr);
         const int n = cons.count();
@@ -437,37 +449,42 @@ edgeattn_mma_bwd_kernel(const MmBwdParams P) {
             iz0 = 1.0f / (__ldg(P.stat_z + row * MM_HEADS + hsel) + 1e-16f);
             iz1 = 1.0f / (__ldg(P.stat_z + row * MM_HEADS + hsel + 1) + 1e-16f);
         }
-        cp_async_wait<1>();   // everything but the group just committed (the next chunk) has landed
+        cp_async_wait<MM_STAGES - 1>();   // everything but the group just committed (the next chunk, if prefetched) has landed
         __syncwarp();
         const uint32_t ktile = base_u32 + (uint32_t)s * 3 * MM_TILE, vtile = ktile + MM_TILE, ftile = ktile + 2 * MM_TILE;
 
         // ---- phase 1: logits (cols 0..3) and d a~ (cols 4..7) --------------------------------------------------
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        float c[4];
         {
+            // four independent accumulator chains instead of one of 48 (see the forward kernel)
+            float ca[4] = {0.f, 0.f, 0.f, 0.f}, cb_[4] = {0.f, 0.f, 0.f, 0.f};
+            float ck0[4] = {0.f, 0.f, 0.f, 0.f}, ck1[4] = {0.f, 0.f, 0.f, 0.f};
             const uint32_t fa = ftile + g * MM_ROWB + q * 16, ka = ktile + g * MM_ROWB + q * 16,
                            va = vtile + g * MM_ROWB + q * 16;
 #pragma unroll
             for (int cb = 0; cb < 8; ++cb) {
                 const uint4 x = lds128(fa + cb * 64), y = lds128(fa + 8 * MM_ROWB + cb * 64);
-                mma_bf16(c, x.x, y.x, x.y, y.y, rf.x[cb].x, rf.x[cb].y);
-                mma_bf16(c, x.z, y.z, x.w, y.w, rf.x[cb].z, rf.x[cb].w);
+                mma_bf16(ca, x.x, y.x, x.y, y.y, rf.x[cb].x, rf.x[cb].y);
+                mma_bf16(cb_, x.z, y.z, x.w, y.w, rf.x[cb].z, rf.x[cb].w);
             }
 #pragma unroll
             for (int cb = 0; cb < 8; ++cb) {
                 const uint4 x = lds128(ka + cb * 64), y = lds128(ka + 8 * MM_ROWB + cb * 64);
                 const bool own = (cb >> 1) == g;          // g < 4 and own head
                 const uint4 b = rf.kv[cb & 1];
-                mma_bf16(c, x.x, y.x, x.y, y.y, own ? b.x : 0u, own ? b.y : 0u);
-                mma_bf16(c, x.z, y.z, x.w, y.w, own ? b.z : 0u, own ? b.w : 0u);
+                mma_bf16(ck0, x.x, y.x, x.y, y.y, own ? b.x : 0u, own ? b.y : 0u);
+                mma_bf16(ck1, x.z, y.z, x.w, y.w, own ? b.z : 0u, own ? b.w : 0u);
             }
 #pragma unroll
             for (int cb = 0; cb < 8; ++cb) {
                 const uint4 x = lds128(va + cb * 64), y = lds128(va + 8 * MM_ROWB + cb * 64);
                 const bool own = (cb >> 1) + 4 == g;      // g >= 4 and own head
                 const uint4 b = rf.kv[cb & 1];
-                mma_bf16(c, x.x, y.x, x.y, y.y, own ? b.x : 0u, own ? b.y : 0u);
-                mma_bf16(c, x.z, y.z, x.w, y.w, own ? b.z : 0u, own ? b.w : 0u);
+                mma_bf16(ck0, x.x, y.x, x.y, y.y, own ? b.x : 0u, own ? b.y : 0u);
+                mma_bf16(ck1, x.z, y.z, x.w, y.w, own ? b.z : 0u, own ? b.w : 0u);
             }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) c[i] = (ca[i] + cb_[i]) + (ck0[i] + ck1[i]);
         }
         // lanes q < 2 hold logits of heads (2q, 2q+1), lanes q >= 2 hold d of heads (2(q-2), 2(q-2)+1): swap halves
         float o[4];
@@ -600,15 +617,21 @@ edgeattn_mma_bwd_kernel(const MmBwdParams P) {
             next_unwritten = row + 1;
         }
         __syncwarp();
+        if (MM_STAGES == 1) issue(0);
         cons = nxt;
     }
     zero_rows(next_unwritten, r1);
 }
 
 static int mm_grid(int64_t n_nodes, int64_t n_edges) {
-    // one CTA per SM is resident (shared memory); ~3 waves of cost-balanced row ranges even out SM-to-SM variance
+    // one CTA per SM is resident (shared memory): one wave of cost-balanced row ranges (more waves only repeat the
+    // per-CTA set-up: 78.9 vs 101.4 us for the backward at 8 192 rows)
     const int64_t work = n_edges + (int64_t)ROW_KAPPA * n_nodes;
-    int64_t blocks = 148 * 3;
+    int64_t blocks = 148;
+    if (const char *e = getenv("ALIGNN_MM_BLOCKS")) {            // tuning knob
+        const int want = atoi(e);
+        if (want >= 1) blocks = want;
+    }
     const int64_t min_work_per_warp = 64;
     if (work / (blocks * MM_WARPS) < min_work_per_warp) blocks = work / (min_work_per_warp * MM_WARPS) + 1;
     return (int)blocks;
@@ -650,7 +673,7 @@ extern "C" int alignn_edgeattn_mma_fwd_s(const void *q, const void *k, const voi
     p.p_drop = p_drop; p.inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
     p.seed = seed; p.offset = offset;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    constexpr int SMEM = MM_WARPS * (2 * 3 * MM_TILE + 64);
+    constexpr int SMEM = MM_WARPS * (MM_STAGES * 3 * MM_TILE + 64);
     ALIGNN_CUDA_TRY(cudaFuncSetAttribute(edgeattn_mma_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     edgeattn_mma_fwd_kernel<<<mm_grid(n_nodes, n_edges), MM_WARPS * 32, SMEM, st>>>(p);
     ALIGNN_LAUNCH_CHECK();
@@ -697,7 +720,7 @@ extern "C" int alignn_edgeattn_mma_bwd_dst_s(const float *dagg, const void *dagg
     p.p_drop = p_drop; p.inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
     p.seed = seed; p.offset = offset; p.relu_mask = relu_mask;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    constexpr int SMEM = MM_WARPS * (2 * 3 * MM_TILE + 64 + 128);
+    constexpr int SMEM = MM_WARPS * (MM_STAGES * 3 * MM_TILE + 64 + 128);
     const int grid = mm_grid(n_nodes, n_edges);
     if (df_in) {
         ALIGNN_CUDA_TRY(cudaFuncSetAttribute(edgeattn_mma_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
