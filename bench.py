@@ -30,9 +30,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
-NCU_TRAFFIC = {   # profiles/r01_v14_ncu_lg_{pyg,bonds}.txt, config 2, per launch
-    "pyg": {"lgattn_fwd": 75_901_952, "lgattn_bwd_dst": 140_308_480, "conv_bwd_src": 53_103_104},
-    "bonds": {"lgattn_fwd": 662_797_568, "lgattn_bwd_dst": 1_117_352_192, "conv_bwd_src": 217_685_248},
+NCU_TRAFFIC = {   # profiles/r01_v20_ncu_lg_{pyg,bonds}.txt, config 2, per launch (dram__bytes_read.sum + dram__bytes_write.sum)
+    "pyg": {"lgattn_fwd": 77_006_592, "lgattn_bwd_dst": 139_667_712, "conv_bwd_src": 53_102_592},
+    "bonds": {"lgattn_fwd": 664_554_752, "lgattn_bwd_dst": 1_120_396_800, "conv_bwd_src": 220_822_272},
 }
 METRIC = "ALIGNN train graphs/sec (fwd+bwd)"
 UNIT = "graphs/s"
@@ -392,7 +392,7 @@ def main_b200(args):
             "traffic": (sum(NCU_TRAFFIC[args.lg_inc].get(k2, 0) for k2 in ("lgattn_bwd_dst", "conv_bwd_src"))
                         if args.workload == "config2" else None),
             "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of alignn_lgattn_bwd_dst + alignn_conv_bwd_src from the "
-                            "committed ncu --set full capture (profiles/r01_v14_ncu_lg_*.txt); lg_angle_grad not in that capture",
+                            "committed ncu --set full capture (profiles/r01_v20_ncu_lg_*.txt); lg_angle_grad not in that capture",
             "formula": "SURVEY.md 8(d) B_b with Nn = active rows, Ne = angles: s*H*(3Nn+Ne) re-read + 4*H*Nn dagg + "
                        "s*H*(3Nn+Ne) gradients + 8*h*Nn stats + 4*(4Ne+2Nn) plan",
             "conv_forward": {"kernel": "alignn_lgattn_fwd", "algorithmic_bytes": b_fwd, "avg_launch_ms": round(t_fwd, 4),
