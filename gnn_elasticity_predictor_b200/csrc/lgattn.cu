@@ -509,7 +509,7 @@ lgattn_bwd_kernel(const LgBwdParams P) {
         }
     };
     // lane (g, q): g < 4 -> qt[g] / q (head g);  g >= 4 -> gt[g-4] / dagg (head g-4)
-    auto load_row = [&](uint4 (&xf)[8], uint4 (&kvf)[2], int row) {
+    auto load_row = [&](uint4 (&xf)[8], uint32_t (&kvf)[8], int row) {
         const int t = g & 3;
         const __nv_bfloat16 *wide = g < 4 ? P.qt + (int64_t)row * P.ldqt + (int64_t)t * P.hsqt
                                           : P.gt + (int64_t)row * P.ldgt + (int64_t)t * P.hsgt;
@@ -517,9 +517,14 @@ lgattn_bwd_kernel(const LgBwdParams P) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) xf[c] = __ldg(pt + 4 * c);
         const __nv_bfloat16 *nar = g < 4 ? P.q + (int64_t)row * P.ldq : P.dagg_lp + (int64_t)row * LG_HID;
-        const uint4 *pq = reinterpret_cast<const uint4 *>(nar + 64 * t) + q;
-        kvf[0] = __ldg(pq);
-        kvf[1] = __ldg(pq + 4);
+        // B fragments of the own-head block in NATURAL channel order (k-step i of the head: channels 16i + 2q, +1 and
+        // 16i + 8 + 2q, +1), matching A fragments read with ldmatrix
+        const uint32_t *pq = reinterpret_cast<const uint32_t *>(nar + 64 * t) + q;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            kvf[2 * i] = __ldg(pq + 8 * i);
+            kvf[2 * i + 1] = __ldg(pq + 8 * i + 4);
+        }
     };
 
     Chunk A, B;
@@ -531,7 +536,8 @@ lgattn_bwd_kernel(const LgBwdParams P) {
     gather_rows(vtile, P.v, P.ldv, jA, A.n, lane);
     cp_async_commit();
 
-    uint4 xf[8], kvf[2];
+    uint4 xf[8];
+    uint32_t kvf[8];
     load_row(xf, kvf, A.row);
     float acc[16][4];
     float D0 = 0.f, D1 = 0.f, G0 = 0.f, G1 = 0.f, mh0 = 0.f, mh1 = 0.f, iz0 = 0.f, iz1 = 0.f;
@@ -597,22 +603,22 @@ lgattn_bwd_kernel(const LgBwdParams P) {
                 mma_bf16(cb_, pack_relu_bf16(h[2][0], h[2][1]), pack_relu_bf16(h[2][2], h[2][3]),
                          pack_relu_bf16(h[3][0], h[3][1]), pack_relu_bf16(h[3][2], h[3][3]), xf[cb].z, xf[cb].w);
             }
-            const uint32_t ka = ktile + g * LG_ROWB + q * 16, va = vtile + g * LG_ROWB + q * 16;
+            // A fragments with ldmatrix: 8 consecutive rows of the 528-byte-stride tiles fall in 8 distinct bank groups
+            // (the 128-bit per-lane reads this replaces were 2-way conflicted: a third of the kernel's wavefronts)
+            const uint32_t aoff = (uint32_t)(((lane & 7) + 8 * ((lane >> 3) & 1)) * LG_ROWB + (lane >> 4) * 16);
 #pragma unroll
-            for (int cb = 0; cb < 8; ++cb) {
-                const uint4 x = lds128(ka + cb * 64), y = lds128(ka + 8 * LG_ROWB + cb * 64);
-                const bool own = (cb >> 1) == g;
-                const uint4 b = kvf[cb & 1];
-                mma_bf16(ck0, x.x, y.x, x.y, y.y, own ? b.x : 0u, own ? b.y : 0u);
-                mma_bf16(ck1, x.z, y.z, x.w, y.w, own ? b.z : 0u, own ? b.w : 0u);
+            for (int kk = 0; kk < 16; ++kk) {
+                uint32_t a[4];
+                ldsm_x4(a, ktile + aoff + kk * 32);
+                const bool own = (kk >> 2) == g;
+                mma_bf16((kk & 1) ? ck1 : ck0, a[0], a[1], a[2], a[3], own ? kvf[2 * (kk & 3)] : 0u, own ? kvf[2 * (kk & 3) + 1] : 0u);
             }
 #pragma unroll
-            for (int cb = 0; cb < 8; ++cb) {
-                const uint4 x = lds128(va + cb * 64), y = lds128(va + 8 * LG_ROWB + cb * 64);
-                const bool own = (cb >> 1) + 4 == g;
-                const uint4 b = kvf[cb & 1];
-                mma_bf16(ck0, x.x, y.x, x.y, y.y, own ? b.x : 0u, own ? b.y : 0u);
-                mma_bf16(ck1, x.z, y.z, x.w, y.w, own ? b.z : 0u, own ? b.w : 0u);
+            for (int kk = 0; kk < 16; ++kk) {
+                uint32_t a[4];
+                ldsm_x4(a, vtile + aoff + kk * 32);
+                const bool own = (kk >> 2) + 4 == g;
+                mma_bf16((kk & 1) ? ck1 : ck0, a[0], a[1], a[2], a[3], own ? kvf[2 * (kk & 3)] : 0u, own ? kvf[2 * (kk & 3) + 1] : 0u);
             }
         }
         float c[4], o[4];

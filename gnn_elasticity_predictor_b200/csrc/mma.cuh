@@ -38,6 +38,14 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t smem_ad
                  : "r"(smem_addr));
 }
 
+// four 8x8 b16 matrices, not transposed: with lane l pointing at row (l & 7) + 8 * ((l >> 3) & 1), column 8 * (l >> 4) of a
+// row-major 16 x 16 tile the four registers are the A fragment (a0..a3) of mma.m16n8k16
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t smem_addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(smem_addr));
+}
+
 __device__ __forceinline__ uint4 lds128(uint32_t smem_addr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_addr));
