@@ -54,7 +54,7 @@ struct MmFwdParams {
 
 struct FwdRowFrags {
     uint4 qt[8];   // lane (g, q): qt[g & 3][row][32 c + 8 q .. +7], c = 0..7
-    uint4 qv[2];   // q[row][64 (g & 3) + 32 c + 8 q .. +7], c = 0..1
+    uint32_t qv[8];   // own-head q in natural channel order: k-step i -> q[row][64 (g & 3) + 16 i + 2 q, +1] and [.. + 8 + 2 q, +1]
 };
 
 __device__ __forceinline__ void load_fwd_row(FwdRowFrags &rf, const MmFwdParams &P, int64_t row, int g, int q) {
@@ -62,9 +62,12 @@ __device__ __forceinline__ void load_fwd_row(FwdRowFrags &rf, const MmFwdParams 
     const uint4 *pt = reinterpret_cast<const uint4 *>(P.qt + row * P.ldqt + (int64_t)t * P.hsqt) + q;
 #pragma unroll
     for (int c = 0; c < 8; ++c) rf.qt[c] = __ldg(pt + 4 * c);
-    const uint4 *pq = reinterpret_cast<const uint4 *>(P.q + row * P.ldq + 64 * t) + q;
-    rf.qv[0] = __ldg(pq);
-    rf.qv[1] = __ldg(pq + 4);
+    const uint32_t *pq = reinterpret_cast<const uint32_t *>(P.q + row * P.ldq + 64 * t) + q;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        rf.qv[2 * i] = __ldg(pq + 8 * i);
+        rf.qv[2 * i + 1] = __ldg(pq + 8 * i + 4);
+    }
 }
 
 __global__ void __launch_bounds__(MM_WARPS * 32, 1)
@@ -173,20 +176,21 @@ edgeattn_mma_fwd_kernel(const MmFwdParams P) {
             // else hides the MMA latency
             float ca[4] = {0.f, 0.f, 0.f, 0.f}, cb_[4] = {0.f, 0.f, 0.f, 0.f};
             float ck0[4] = {0.f, 0.f, 0.f, 0.f}, ck1[4] = {0.f, 0.f, 0.f, 0.f};
-            const uint32_t fa = ftile + g * MM_ROWB + q * 16, ka = ktile + g * MM_ROWB + q * 16;
+            const uint32_t fa = ftile + g * MM_ROWB + q * 16;
 #pragma unroll
             for (int cb = 0; cb < 8; ++cb) {
                 const uint4 x = lds128(fa + cb * 64), y = lds128(fa + 8 * MM_ROWB + cb * 64);
                 mma_bf16(ca, x.x, y.x, x.y, y.y, rf.qt[cb].x, rf.qt[cb].y);
                 mma_bf16(cb_, x.z, y.z, x.w, y.w, rf.qt[cb].z, rf.qt[cb].w);
             }
+            // K A-fragments with ldmatrix: conflict-free on the 528-byte-stride tile (per-lane 128-bit reads are 2-way conflicted)
+            const uint32_t aoff = (uint32_t)(((lane & 7) + 8 * ((lane >> 3) & 1)) * MM_ROWB + (lane >> 4) * 16);
 #pragma unroll
-            for (int cb = 0; cb < 8; ++cb) {
-                const uint4 x = lds128(ka + cb * 64), y = lds128(ka + 8 * MM_ROWB + cb * 64);
-                const bool own = (cb >> 1) == t_own;
-                const uint4 bq = rf.qv[cb & 1];
-                mma_bf16(ck0, x.x, y.x, x.y, y.y, own ? bq.x : 0u, own ? bq.y : 0u);
-                mma_bf16(ck1, x.z, y.z, x.w, y.w, own ? bq.z : 0u, own ? bq.w : 0u);
+            for (int kk = 0; kk < 16; ++kk) {
+                uint32_t a[4];
+                ldsm_x4(a, ktile + aoff + kk * 32);
+                const bool own = (kk >> 2) == t_own;
+                mma_bf16((kk & 1) ? ck1 : ck0, a[0], a[1], a[2], a[3], own ? rf.qv[2 * (kk & 3)] : 0u, own ? rf.qv[2 * (kk & 3) + 1] : 0u);
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) c[i] = (ca[i] + cb_[i]) + (ck0[i] + ck1[i]);
@@ -325,7 +329,7 @@ struct MmBwdParams {
 
 struct BwdRowFrags {
     uint4 x[8];    // lane (g, q): g < 4: qt[g][row][32 c + 8 q ..], else gt[g - 4][row][...]
-    uint4 kv[2];   // g < 4: q[row][64 g + 32 c + 8 q ..], else dagg_lp[row][64 (g - 4) + 32 c + 8 q ..]
+    uint32_t kv[8];   // g < 4: q[row], else dagg_lp[row]: own-head block in natural channel order (see FwdRowFrags::qv)
 };
 
 __device__ __forceinline__ void load_bwd_row(BwdRowFrags &rf, const MmBwdParams &P, int64_t row, int g, int q) {
@@ -335,9 +339,12 @@ __device__ __forceinline__ void load_bwd_row(BwdRowFrags &rf, const MmBwdParams 
 #pragma unroll
     for (int c = 0; c < 8; ++c) rf.x[c] = __ldg(pt + 4 * c);
     const __nv_bfloat16 *nar = g < 4 ? P.q + row * P.ldq : P.dagg_lp + row * MM_HID;
-    const uint4 *pq = reinterpret_cast<const uint4 *>(nar + 64 * t) + q;
-    rf.kv[0] = __ldg(pq);
-    rf.kv[1] = __ldg(pq + 4);
+    const uint32_t *pq = reinterpret_cast<const uint32_t *>(nar + 64 * t) + q;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        rf.kv[2 * i] = __ldg(pq + 8 * i);
+        rf.kv[2 * i + 1] = __ldg(pq + 8 * i + 4);
+    }
 }
 
 template <bool ACCUM>
@@ -459,29 +466,28 @@ edgeattn_mma_bwd_kernel(const MmBwdParams P) {
             // four independent accumulator chains instead of one of 48 (see the forward kernel)
             float ca[4] = {0.f, 0.f, 0.f, 0.f}, cb_[4] = {0.f, 0.f, 0.f, 0.f};
             float ck0[4] = {0.f, 0.f, 0.f, 0.f}, ck1[4] = {0.f, 0.f, 0.f, 0.f};
-            const uint32_t fa = ftile + g * MM_ROWB + q * 16, ka = ktile + g * MM_ROWB + q * 16,
-                           va = vtile + g * MM_ROWB + q * 16;
+            const uint32_t fa = ftile + g * MM_ROWB + q * 16;
 #pragma unroll
             for (int cb = 0; cb < 8; ++cb) {
                 const uint4 x = lds128(fa + cb * 64), y = lds128(fa + 8 * MM_ROWB + cb * 64);
                 mma_bf16(ca, x.x, y.x, x.y, y.y, rf.x[cb].x, rf.x[cb].y);
                 mma_bf16(cb_, x.z, y.z, x.w, y.w, rf.x[cb].z, rf.x[cb].w);
             }
+            // K / V A-fragments with ldmatrix (conflict-free on the 528-byte-stride tiles)
+            const uint32_t aoff = (uint32_t)(((lane & 7) + 8 * ((lane >> 3) & 1)) * MM_ROWB + (lane >> 4) * 16);
 #pragma unroll
-            for (int cb = 0; cb < 8; ++cb) {
-                const uint4 x = lds128(ka + cb * 64), y = lds128(ka + 8 * MM_ROWB + cb * 64);
-                const bool own = (cb >> 1) == g;          // g < 4 and own head
-                const uint4 b = rf.kv[cb & 1];
-                mma_bf16(ck0, x.x, y.x, x.y, y.y, own ? b.x : 0u, own ? b.y : 0u);
-                mma_bf16(ck1, x.z, y.z, x.w, y.w, own ? b.z : 0u, own ? b.w : 0u);
+            for (int kk = 0; kk < 16; ++kk) {
+                uint32_t a[4];
+                ldsm_x4(a, ktile + aoff + kk * 32);
+                const bool own = (kk >> 2) == g;          // g < 4 and own head
+                mma_bf16((kk & 1) ? ck1 : ck0, a[0], a[1], a[2], a[3], own ? rf.kv[2 * (kk & 3)] : 0u, own ? rf.kv[2 * (kk & 3) + 1] : 0u);
             }
 #pragma unroll
-            for (int cb = 0; cb < 8; ++cb) {
-                const uint4 x = lds128(va + cb * 64), y = lds128(va + 8 * MM_ROWB + cb * 64);
-                const bool own = (cb >> 1) + 4 == g;      // g >= 4 and own head
-                const uint4 b = rf.kv[cb & 1];
-                mma_bf16(ck0, x.x, y.x, x.y, y.y, own ? b.x : 0u, own ? b.y : 0u);
-                mma_bf16(ck1, x.z, y.z, x.w, y.w, own ? b.z : 0u, own ? b.w : 0u);
+            for (int kk = 0; kk < 16; ++kk) {
+                uint32_t a[4];
+                ldsm_x4(a, vtile + aoff + kk * 32);
+                const bool own = (kk >> 2) + 4 == g;      // g >= 4 and own head
+                mma_bf16((kk & 1) ? ck1 : ck0, a[0], a[1], a[2], a[3], own ? rf.kv[2 * (kk & 3)] : 0u, own ? rf.kv[2 * (kk & 3) + 1] : 0u);
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) c[i] = (ca[i] + cb_[i]) + (ck0[i] + ck1[i]);

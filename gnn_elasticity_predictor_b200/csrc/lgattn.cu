@@ -214,14 +214,19 @@ lgattn_fwd_kernel(const LgFwdParams P) {
             wcol.shift(P.col, wbase, e_end, lane);
         }
     };
-    auto load_row = [&](uint4 (&qtf)[8], uint4 (&qvf)[2], int row) {
+    auto load_row = [&](uint4 (&qtf)[8], uint32_t (&qvf)[8], int row) {
         const int t = g & 3;
         const uint4 *pt = reinterpret_cast<const uint4 *>(P.qt + (int64_t)row * P.ldqt + (int64_t)t * P.hsqt) + q;
 #pragma unroll
         for (int c = 0; c < 8; ++c) qtf[c] = __ldg(pt + 4 * c);
-        const uint4 *pq = reinterpret_cast<const uint4 *>(P.q + (int64_t)row * P.ldq + 64 * t) + q;
-        qvf[0] = __ldg(pq);
-        qvf[1] = __ldg(pq + 4);
+        // own-head q in NATURAL channel order (k-step i: channels 16i + 2q, +1 and 16i + 8 + 2q, +1): pairs with K
+        // A fragments read by ldmatrix (conflict-free; per-lane 128-bit reads of the 528-byte-stride tile are not)
+        const uint32_t *pq = reinterpret_cast<const uint32_t *>(P.q + (int64_t)row * P.ldq + 64 * t) + q;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            qvf[2 * i] = __ldg(pq + 8 * i);
+            qvf[2 * i + 1] = __ldg(pq + 8 * i + 4);
+        }
     };
     auto zero_rows = [&](int lo, int hi) {
         F8 zf;
@@ -249,7 +254,8 @@ lgattn_fwd_kernel(const LgFwdParams P) {
     gather_rows(vtile, P.v, P.ldv, jA, A.n, lane);
     cp_async_commit();
 
-    uint4 qtf[8], qvf[2];
+    uint4 qtf[8];
+    uint32_t qvf[8];
     load_row(qtf, qvf, A.row);
     float acc[16][4];
     float m0 = -INFINITY, m1 = -INFINITY, z0 = 0.f, z1 = 0.f, zd0 = 0.f, zd1 = 0.f;
@@ -298,14 +304,13 @@ lgattn_fwd_kernel(const LgFwdParams P) {
                 mma_bf16(cb_, pack_relu_bf16(h[2][0], h[2][1]), pack_relu_bf16(h[2][2], h[2][3]),
                          pack_relu_bf16(h[3][0], h[3][1]), pack_relu_bf16(h[3][2], h[3][3]), qtf[cb].z, qtf[cb].w);
             }
-            const uint32_t ka = ktile + g * LG_ROWB + q * 16;
+            const uint32_t aoff = (uint32_t)(((lane & 7) + 8 * ((lane >> 3) & 1)) * LG_ROWB + (lane >> 4) * 16);
 #pragma unroll
-            for (int cb = 0; cb < 8; ++cb) {
-                const uint4 x = lds128(ka + cb * 64), y = lds128(ka + 8 * LG_ROWB + cb * 64);
-                const bool own = (cb >> 1) == t_own;
-                const uint4 bq = qvf[cb & 1];
-                mma_bf16(ck0, x.x, y.x, x.y, y.y, own ? bq.x : 0u, own ? bq.y : 0u);
-                mma_bf16(ck1, x.z, y.z, x.w, y.w, own ? bq.z : 0u, own ? bq.w : 0u);
+            for (int kk = 0; kk < 16; ++kk) {
+                uint32_t a[4];
+                ldsm_x4(a, ktile + aoff + kk * 32);
+                const bool own = (kk >> 2) == t_own;
+                mma_bf16((kk & 1) ? ck1 : ck0, a[0], a[1], a[2], a[3], own ? qvf[2 * (kk & 3)] : 0u, own ? qvf[2 * (kk & 3) + 1] : 0u);
             }
         }
         const float c0 = (ca[0] + cb_[0]) + (ck0[0] + ck1[0]), c1 = (ca[1] + cb_[1]) + (ck0[1] + ck1[1]);
