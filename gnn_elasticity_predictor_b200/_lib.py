@@ -145,10 +145,13 @@ def load(rebuild_if_stale: bool = True):
             try:
                 _build.build()
             except Exception as exc:  # noqa: BLE001
-                if not os.path.exists(path):
-                    raise RuntimeError(
-                        "libalignn_b200.so is missing and could not be built; the ALIGNN hot path has no "
-                        f"CPU or PyTorch fallback ({exc})") from exc
+                # never fall back to a stale binary: a library that does not match the sources on disk would pass the
+                # ABI integer check and silently run old kernels
+                what = "is missing" if not os.path.exists(path) else "is older than csrc/ (stale)"
+                raise RuntimeError(
+                    f"libalignn_b200.so {what} and could not be rebuilt; the ALIGNN hot path has no CPU or PyTorch "
+                    f"fallback.  Fix the build (`python -m gnn_elasticity_predictor_b200.build --force`) or pass "
+                    f"rebuild_if_stale=False to load the existing binary on purpose ({exc})") from exc
         try:
             lib = ctypes.CDLL(path)
         except OSError as exc:

@@ -84,12 +84,16 @@ class FlatGradBucket:
         views = [self.flat[off:off + p.numel()].view_as(p) for p, off in zip(self.params, self.offsets)]
         src, dst = [], []
         written = getattr(self, "_written", None)
+        # under CUDA-graph capture the decision below is baked into the graph, and a graph captured for a signature whose
+        # forward skips some parameters may later be replayed right after a graph that DID write their slices: there a
+        # slice without a gradient is zeroed unconditionally
+        capturing = self.flat.is_cuda and torch.cuda.is_current_stream_capturing()
         now = set()
         for i, (p, v) in enumerate(zip(self.params, views)):
             g = p.grad
             if g is not None and g.data_ptr() != v.data_ptr():
                 src.append(g if g.dtype == v.dtype else g.to(v.dtype)); dst.append(v); now.add(i)
-            elif g is None and (written is None or i in written):
+            elif g is None and (capturing or written is None or i in written):
                 v.zero_()
         if src:
             torch._foreach_copy_(dst, src)

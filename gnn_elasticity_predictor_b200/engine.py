@@ -87,13 +87,16 @@ class TrainStep:
     """``step(batch, target_z) -> (loss, mean, logvar)`` -- device tensors, valid until the next call.
 
     ``graph=True`` captures one CUDA graph per batch signature after ``graph_warmup`` eager steps on that signature (the
-    warm-up steps are real training steps).  ``loss_scale`` is the DP weight ``B_local / B_global``."""
+    warm-up steps are real training steps).  ``loss_scale`` is the DP weight ``B_local / B_global``: a constant, so the
+    summed gradient equals the global-batch mean gradient only when every rank holds the SAME number of real graphs per
+    step (``dp.shard_ranges`` + equal shard sizes, what ``bench.py`` and the 2-GPU equality check use); with ragged or
+    bucket-padded shards pass per-step ``sample_weight = B_global_real / (world * B_local_real)`` instead."""
 
     def __init__(self, model: HeteroAlignnRegressor, lr: float = 1e-3, lr_sigma: Optional[float] = None,
                  weight_decay: float = 1e-4, max_norm: float = 5.0, log_sigma_l2: float = 0.1,
                  min_logvar_floor: float = -2.9, loss_scale: float = 1.0, graph: bool = True, graph_warmup: int = 2,
                  optimizer: bool = True, group=None, pad_to_buckets: bool = False, bucket_align: int = 256,
-                 data_parallel: bool = True):
+                 data_parallel: bool = True, feature_jitter_std: float = 0.0, allreduce_in_graph: bool = True):
         self.model = model
         params = [p for p in model.parameters() if p.requires_grad]
         if not params or not params[0].is_cuda:
@@ -121,6 +124,13 @@ class TrainStep:
         self.world = dist.get_world_size(group) if (data_parallel and dist.is_available() and dist.is_initialized()) else 1
         self.rng_step = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self.pad_to_buckets, self.bucket_align = bool(pad_to_buckets), int(bucket_align)
+        # reference train.py:641-646 (--feature-jitter-std, default 0.1 there): Gaussian noise on x and global_x every
+        # training step.  0 here by default so that parity runs are noise-free; torch's CUDA generator is graph-safe.
+        self.feature_jitter_std = float(feature_jitter_std)
+        # N > 1: capture the NCCL all-reduce of the flat bucket INSIDE the step graph (one cudaGraphLaunch per step, no
+        # host round trip between backward, collective and optimizer); falls back to two graphs with the collective
+        # between them if the capture is refused
+        self.allreduce_in_graph = bool(allreduce_in_graph)
         self._captured: Dict[Tuple, _Captured] = {}
         self._seen: Dict[Tuple, int] = {}
         self.replays = 0
@@ -130,11 +140,23 @@ class TrainStep:
     def _fwd_bwd(self, batch, tz: Tensor, mask: Optional[Tensor] = None, weight: Optional[Tensor] = None):
         self.bucket.detach_grads()
         self.model.base.build_plans(batch)                 # CSR/CSC sorts of this batch: part of every step
+        if self.feature_jitter_std > 0.0 and self.model.training:
+            batch = self._jittered(batch)
         mean, logvar = self.model(batch)
         loss = fused_gaussian_nll(mean, logvar, tz, self.log_sigma_l2, self.floor, mask=mask, sample_weight=weight)
         (loss * self.loss_scale).backward()
         self.bucket.gather()                               # one multi-tensor copy into the flat gradient bucket
         return loss.detach(), mean.detach(), logvar.detach()
+
+    def _jittered(self, batch):
+        """``x`` and ``global_x`` plus N(0, std^2) noise (reference ``train.py:641-646``) on a shallow copy of the batch:
+        the caller's tensors (and a CUDA graph's static input buffers) are never modified; plans stay cached."""
+        import copy
+        std = self.feature_jitter_std
+        b = copy.copy(batch)
+        b.x = batch.x + torch.randn_like(batch.x) * std
+        b.global_x = batch.global_x + torch.randn_like(batch.global_x) * std
+        return b
 
     def _finish(self):
         if self.opt is not None:
@@ -157,7 +179,8 @@ class TrainStep:
     @staticmethod
     def signature(batch) -> Tuple:
         return tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(batch.tensors().items())) + (
-            batch.num_graphs, getattr(batch, "lg_active_rows", None), getattr(batch, "source_sorted", None))
+            batch.num_graphs, getattr(batch, "lg_active_rows", None), getattr(batch, "source_sorted", None),
+            bool(getattr(batch, "padded", False)))
 
     def _capture(self, batch: GraphBatch, tz: Tensor, mask: Optional[Tensor] = None,
                  weight: Optional[Tensor] = None) -> _Captured:
@@ -173,13 +196,27 @@ class TrainStep:
         torch.cuda.synchronize(self.dev)
         k0 = ops.STATS.kernels
         try:
-            cap.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(cap.graph):
-                cap.loss, cap.mean, cap.logvar = self._fwd_bwd(cap.batch, cap.tz, cap.mask, cap.weight)
-                if self.world == 1:
-                    self._finish()
+            one_graph = self.world == 1 or self.allreduce_in_graph
             cap.graph_opt = None
-            if self.world > 1:                      # the collective stays outside the graphs
+            try:
+                cap.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(cap.graph):
+                    cap.loss, cap.mean, cap.logvar = self._fwd_bwd(cap.batch, cap.tz, cap.mask, cap.weight)
+                    if one_graph:
+                        if self.world > 1:
+                            self.bucket.all_reduce(self.group)      # NCCL kernel node inside the graph
+                        self._finish()
+            except ops.StaticDropoutUnderCapture:
+                raise
+            except RuntimeError:
+                if self.world == 1 or not self.allreduce_in_graph:
+                    raise
+                self.allreduce_in_graph, one_graph = False, False   # collective refused capture: keep it between two graphs
+                torch.cuda.synchronize(self.dev)
+                cap.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(cap.graph):
+                    cap.loss, cap.mean, cap.logvar = self._fwd_bwd(cap.batch, cap.tz, cap.mask, cap.weight)
+            if not one_graph:
                 cap.graph_opt = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(cap.graph_opt, pool=cap.graph.pool()):
                     self._finish()
@@ -211,6 +248,12 @@ class TrainStep:
                 w = torch.ones(batch.num_graphs, dtype=sample_weight.dtype, device=sample_weight.device)
                 w[:n_real] = sample_weight
                 sample_weight = w
+        if mask is None and getattr(batch, "padded", False):
+            # a batch padded elsewhere (DeviceGraphStore.collate(pad_to_bucket=True)) carries its own real-graph mask:
+            # the dummy graph and the empty slots must never enter the loss
+            mask = getattr(batch, "loss_mask", None)
+            if mask is None:
+                raise ValueError("padded batch without a loss mask: pass mask= (1 = real graph) or set batch.loss_mask")
         if not self.use_graph or not isinstance(batch, GraphBatch):
             return self._eager(batch, target_z, mask, sample_weight)
         sig = self.signature(batch) + (mask is not None,) + ((True,) if sample_weight is not None else ())
@@ -220,7 +263,16 @@ class TrainStep:
             self._seen[sig] = seen + 1
             if seen < self.graph_warmup:
                 return self._eager(batch, target_z, mask, sample_weight)
-            cap = self._captured[sig] = self._capture(batch, target_z, mask, sample_weight)
+            try:
+                cap = self._captured[sig] = self._capture(batch, target_z, mask, sample_weight)
+            except ops.StaticDropoutUnderCapture as exc:
+                # this model runs on a kernel family whose dropout keys are host integers (hidden != 256, fp32 regime):
+                # a captured graph would replay ONE mask for ever.  Train it eagerly instead (fresh keys every step).
+                import warnings
+                warnings.warn(f"TrainStep: CUDA-graph replay disabled for this model ({exc})", stacklevel=2)
+                self.use_graph = False
+                torch.cuda.synchronize(self.dev)
+                return self._eager(batch, target_z, mask, sample_weight)
         if batch is not cap.batch:                      # callers may fill the graph's own input buffers (static_inputs)
             for k, v in cap.batch.tensors().items():
                 v.copy_(getattr(batch, k), non_blocking=True)

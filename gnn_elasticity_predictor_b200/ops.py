@@ -124,6 +124,20 @@ def _plan_kernels(n_edges: int, n_nodes: int, source_sorted: bool = False, key_b
     return 1 + (1 if source_sorted else 2) * 4 * passes + 4
 
 
+class StaticDropoutUnderCapture(RuntimeError):
+    """A dropout mask keyed by HOST integers only is about to be baked into a CUDA graph (every replay would reuse it)."""
+
+
+def _static_dropout_guard(p_drop: float, what: str) -> None:
+    """The generic kernels (hidden != 256, fp32 regime, standalone blocks) take the Philox ``(seed, offset)`` as host
+    integers and do not read the device step counter ``RNG_STEP``.  Capturing them with ``p > 0`` would freeze the mask
+    across replays, so refuse: ``engine.TrainStep`` catches this and runs such models eagerly (fresh keys per step)."""
+    if p_drop > 0.0 and RNG_STEP is not None and torch.cuda.is_current_stream_capturing():
+        raise StaticDropoutUnderCapture(
+            f"{what}: dropout p={p_drop} on a kernel family without a device-side RNG counter cannot be captured into a "
+            "CUDA graph (replays would reuse one mask); run this model eagerly (TrainStep(graph=False))")
+
+
 def next_dropout_key() -> Tuple[int, int]:
     """(seed, offset) for one dropout mask, drawn from torch's CPU generator (no device sync), so
     ``torch.manual_seed`` makes training runs reproducible."""
@@ -193,159 +207,263 @@ def build_plan(edge_index: Tensor, n_nodes: int, validate: bool = False, source_
 
 
 # --------------------------------------------------------------------------------------------------
-# fused conv core
+# The generic operators as TORCH CUSTOM OPS (namespace ``alignn_b200``; SURVEY.md 8(b) "native boundary").
+#
+# Each op is a thin shim over one ``extern "C"`` launcher of ``libalignn_b200.so``: torch allocates every tensor, the C
+# side gets raw pointers + sizes + the current stream.  Registered with ``torch.library.custom_op`` (schema inferred
+# from the annotations), a fake (meta) implementation for tracing / ``torch.compile`` / FakeTensor shape propagation,
+# and ``register_autograd`` formulas that call the matching ``*_backward`` op -- so ``torch.ops.alignn_b200.*`` are
+# first-class dispatcher citizens (``torch.library.opcheck`` passes on them, tests/test_gpu_ops.py) instead of opaque
+# ctypes calls inside ``autograd.Function``s.  No op has a CPU kernel: CPU tensors raise ``RuntimeError``.
 # --------------------------------------------------------------------------------------------------
-class _ConvCore(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, q: Tensor, k: Tensor, v: Tensor, e: Tensor, plan: GraphPlan, heads: int, p_drop: float,
-                seed: int, offset: int):
-        _require_cuda(q, k, v, e)
-        lib = _lib.load()
-        q, k, v, e = (t.contiguous() for t in (q, k, v, e))
-        if not (q.dtype == k.dtype == v.dtype == e.dtype):
-            raise RuntimeError("q, k, v, e must share one dtype")
-        n_nodes, hidden = q.shape
-        n_edges = int(e.size(0))
-        if n_nodes != plan.n_nodes or n_edges != plan.n_edges:
-            raise RuntimeError(f"plan is for {plan.n_nodes} nodes / {plan.n_edges} edges, operands have "
-                               f"{n_nodes} / {n_edges}")
-        f32 = dict(dtype=torch.float32, device=q.device)
-        agg = torch.empty(n_nodes, hidden, **f32)
-        stat_m = torch.empty(n_nodes, heads, **f32)
-        stat_z = torch.empty(n_nodes, heads, **f32)
-        with torch.cuda.device(q.device), _Launch("conv_fwd", 1, (n_nodes, n_edges, hidden, heads, q.element_size())):
-            rc = lib.alignn_conv_fwd(_p(q), _p(k), _p(v), _p(e), _p(plan.rowptr), _p(plan.col), _p(plan.eid),
-                                     _p(agg), _p(stat_m), _p(stat_z), n_nodes, n_edges, hidden, heads,
-                                     _dtype_code(q), float(p_drop), seed, offset, _stream())
-        _lib.check(rc, "alignn_conv_fwd")
-        ctx.save_for_backward(q, k, v, e, agg, stat_m, stat_z)
-        ctx.plan, ctx.heads, ctx.p_drop, ctx.seed, ctx.offset = plan, heads, float(p_drop), seed, offset
-        return agg
+_lib_def = torch.library.custom_op
 
-    @staticmethod
-    def backward(ctx, dagg: Tensor):
-        lib = _lib.load()
-        q, k, v, e, agg, stat_m, stat_z = ctx.saved_tensors
-        plan = ctx.plan
-        n_nodes, hidden = q.shape
-        n_edges = int(e.size(0))
-        dagg = dagg.contiguous().float()
-        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-        de = torch.zeros_like(e)                 # rows of edges the plan dropped (padding) are never written
-        coef = torch.empty(max(n_edges, 1), 2 * ctx.heads, dtype=torch.float32, device=q.device)
-        with torch.cuda.device(q.device), _Launch("conv_bwd", 2, (n_nodes, n_edges, hidden, ctx.heads, q.element_size())):
-            rc = lib.alignn_conv_bwd(_p(dagg), _p(agg), _p(q), _p(k), _p(v), _p(e), _p(stat_m), _p(stat_z),
-                                     _p(plan.rowptr), _p(plan.col), _p(plan.eid), _p(plan.rowptr_t), _p(plan.col_t),
-                                     _p(plan.eid_t), _p(dq), _p(dk), _p(dv), _p(de), _p(coef), n_nodes, n_edges,
-                                     hidden, ctx.heads, _dtype_code(q), ctx.p_drop, ctx.seed, ctx.offset, _stream())
-        _lib.check(rc, "alignn_conv_bwd")
-        return dq, dk, dv, de, None, None, None, None, None
+
+@_lib_def("alignn_b200::conv_core", mutates_args=(), device_types="cuda")
+def _op_conv_core(q: Tensor, k: Tensor, v: Tensor, e: Tensor, rowptr: Tensor, col: Tensor, eid: Tensor,
+                  rowptr_t: Tensor, col_t: Tensor, eid_t: Tensor, heads: int, p_drop: float, seed: int, offset: int
+                  ) -> Tuple[Tensor, Tensor, Tensor]:
+    """(agg, stat_m, stat_z).  ``rowptr_t / col_t / eid_t`` (the CSC half of the plan) are only read by the backward."""
+    _require_cuda(q, k, v, e)
+    _static_dropout_guard(p_drop, "conv_core")
+    lib = _lib.load()
+    q, k, v, e = (t.contiguous() for t in (q, k, v, e))
+    if not (q.dtype == k.dtype == v.dtype == e.dtype):
+        raise RuntimeError("q, k, v, e must share one dtype")
+    n_nodes, hidden = q.shape
+    n_edges = int(e.size(0))
+    f32 = dict(dtype=torch.float32, device=q.device)
+    agg = torch.empty(n_nodes, hidden, **f32)
+    stat_m = torch.empty(n_nodes, heads, **f32)
+    stat_z = torch.empty(n_nodes, heads, **f32)
+    with torch.cuda.device(q.device), _Launch("conv_fwd", 1, (n_nodes, n_edges, hidden, heads, q.element_size())):
+        rc = lib.alignn_conv_fwd(_p(q), _p(k), _p(v), _p(e), _p(rowptr), _p(col), _p(eid), _p(agg), _p(stat_m),
+                                 _p(stat_z), n_nodes, n_edges, hidden, heads, _dtype_code(q), float(p_drop), seed, offset,
+                                 _stream())
+    _lib.check(rc, "alignn_conv_fwd")
+    return agg, stat_m, stat_z
+
+
+@_op_conv_core.register_fake
+def _(q, k, v, e, rowptr, col, eid, rowptr_t, col_t, eid_t, heads, p_drop, seed, offset):
+    f32 = dict(dtype=torch.float32, device=q.device)
+    return (torch.empty(q.shape, **f32), torch.empty(q.size(0), heads, **f32), torch.empty(q.size(0), heads, **f32))
+
+
+@_lib_def("alignn_b200::conv_core_backward", mutates_args=(), device_types="cuda")
+def _op_conv_core_backward(dagg: Tensor, agg: Tensor, q: Tensor, k: Tensor, v: Tensor, e: Tensor, stat_m: Tensor,
+                           stat_z: Tensor, rowptr: Tensor, col: Tensor, eid: Tensor, rowptr_t: Tensor, col_t: Tensor,
+                           eid_t: Tensor, heads: int, p_drop: float, seed: int, offset: int
+                           ) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    lib = _lib.load()
+    n_nodes, hidden = q.shape
+    n_edges = int(e.size(0))
+    dagg = dagg.contiguous().float()
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    de = torch.zeros_like(e)                 # rows of edges the plan dropped (padding) are never written
+    coef = torch.empty(max(n_edges, 1), 2 * heads, dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device), _Launch("conv_bwd", 2, (n_nodes, n_edges, hidden, heads, q.element_size())):
+        rc = lib.alignn_conv_bwd(_p(dagg), _p(agg), _p(q), _p(k), _p(v), _p(e), _p(stat_m), _p(stat_z), _p(rowptr),
+                                 _p(col), _p(eid), _p(rowptr_t), _p(col_t), _p(eid_t), _p(dq), _p(dk), _p(dv), _p(de),
+                                 _p(coef), n_nodes, n_edges, hidden, heads, _dtype_code(q), float(p_drop), seed, offset,
+                                 _stream())
+    _lib.check(rc, "alignn_conv_bwd")
+    return dq, dk, dv, de
+
+
+@_op_conv_core_backward.register_fake
+def _(dagg, agg, q, k, v, e, stat_m, stat_z, rowptr, col, eid, rowptr_t, col_t, eid_t, heads, p_drop, seed, offset):
+    return torch.empty_like(q), torch.empty_like(k), torch.empty_like(v), torch.empty_like(e)
+
+
+def _conv_core_setup(ctx, inputs, output):
+    q, k, v, e, rowptr, col, eid, rowptr_t, col_t, eid_t, heads, p_drop, seed, offset = inputs
+    agg, stat_m, stat_z = output
+    ctx.save_for_backward(q.contiguous(), k.contiguous(), v.contiguous(), e.contiguous(), agg, stat_m, stat_z, rowptr,
+                          col, eid, rowptr_t, col_t, eid_t)
+    ctx.args = (heads, float(p_drop), seed, offset)
+
+
+def _conv_core_backward(ctx, dagg, _dm, _dz):
+    q, k, v, e, agg, stat_m, stat_z, rowptr, col, eid, rowptr_t, col_t, eid_t = ctx.saved_tensors
+    heads, p_drop, seed, offset = ctx.args
+    dq, dk, dv, de = torch.ops.alignn_b200.conv_core_backward(dagg, agg, q, k, v, e, stat_m, stat_z, rowptr, col, eid,
+                                                              rowptr_t, col_t, eid_t, heads, p_drop, seed, offset)
+    return (dq, dk, dv, de) + (None,) * 10
+
+
+_op_conv_core.register_autograd(_conv_core_backward, setup_context=_conv_core_setup)
 
 
 def conv_core(q: Tensor, k: Tensor, v: Tensor, e: Tensor, plan: GraphPlan, heads: int, p_drop: float = 0.0,
               seed: int = 0, offset: int = 0) -> Tensor:
-    """``agg[i] = sum_j softmax_i(<q_i, k_j + e_ij>/sqrt(C)) (v_j + e_ij)`` per head; returns fp32 ``[N, H]``."""
-    return _ConvCore.apply(q, k, v, e, plan, int(heads), float(p_drop), int(seed), int(offset))
+    """``agg[i] = sum_j softmax_i(<q_i, k_j + e_ij>/sqrt(C)) (v_j + e_ij)`` per head; returns fp32 ``[N, H]``
+    (custom op ``alignn_b200::conv_core``)."""
+    _require_cuda(q, k, v, e)
+    n_nodes, n_edges = int(q.size(0)), int(e.size(0))
+    if n_nodes != plan.n_nodes or n_edges != plan.n_edges:
+        raise RuntimeError(f"plan is for {plan.n_nodes} nodes / {plan.n_edges} edges, operands have "
+                           f"{n_nodes} / {n_edges}")
+    return torch.ops.alignn_b200.conv_core(q, k, v, e, plan.rowptr, plan.col, plan.eid, plan.rowptr_t, plan.col_t,
+                                           plan.eid_t, int(heads), float(p_drop), int(seed), int(offset))[0]
 
 
 # --------------------------------------------------------------------------------------------------
 # beta gate + LayerNorm + ReLU + dropout + residual
 # --------------------------------------------------------------------------------------------------
-class _GateLn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, agg: Tensor, xr: Tensor, x: Tensor, wbeta: Tensor, gamma: Tensor, bias: Tensor, eps: float,
-                p_drop: float, seed: int, offset: int, want_lp: bool):
-        _require_cuda(agg, xr, x, wbeta, gamma, bias)
-        lib = _lib.load()
-        agg = agg.contiguous().float()
-        xr = xr.contiguous()
-        x = x.contiguous().float()
-        wb = wbeta.detach().reshape(-1).contiguous().float()
-        gm, bs = gamma.detach().contiguous().float(), bias.detach().contiguous().float()
-        n_rows, hidden = agg.shape
-        f32 = dict(dtype=torch.float32, device=agg.device)
-        y = torch.empty(n_rows, hidden, **f32)
-        y_lp = torch.empty(n_rows, hidden, dtype=xr.dtype, device=agg.device) if want_lp else None
-        beta, mean, rstd = (torch.empty(n_rows, **f32) for _ in range(3))
-        with torch.cuda.device(agg.device), _Launch("gate_ln_fwd", 1, (n_rows, hidden, xr.element_size())):
-            rc = lib.alignn_gate_ln_fwd(_p(agg), _p(xr), _p(x), _p(wb), _p(gm), _p(bs), _p(y), _p(y_lp), _p(beta),
-                                        _p(mean), _p(rstd), n_rows, hidden, _dtype_code(xr), float(eps),
-                                        float(p_drop), seed, offset, _stream())
-        _lib.check(rc, "alignn_gate_ln_fwd")
-        ctx.save_for_backward(agg, xr, wb, gm, bs, beta, mean, rstd)
-        ctx.p_drop, ctx.seed, ctx.offset = float(p_drop), seed, offset
-        ctx.wbeta_shape, ctx.param_dtypes = wbeta.shape, (wbeta.dtype, gamma.dtype, bias.dtype)
-        if want_lp:
-            return y, y_lp
-        return y, None
+@_lib_def("alignn_b200::gate_ln", mutates_args=(), device_types="cuda")
+def _op_gate_ln(agg: Tensor, xr: Tensor, x: Tensor, wbeta: Tensor, gamma: Tensor, bias: Tensor, eps: float,
+                p_drop: float, seed: int, offset: int, want_lp: bool
+                ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """Returns (y f32, y_lp (empty when not wanted), beta, mean, rstd)."""
+    _require_cuda(agg, xr, x, wbeta, gamma, bias)
+    _static_dropout_guard(p_drop, "gate_ln_relu_residual")
+    lib = _lib.load()
+    agg = agg.contiguous().float()
+    xr = xr.contiguous()
+    x = x.contiguous().float()
+    wb = wbeta.detach().reshape(-1).contiguous().float()
+    gm, bs = gamma.detach().contiguous().float(), bias.detach().contiguous().float()
+    n_rows, hidden = agg.shape
+    f32 = dict(dtype=torch.float32, device=agg.device)
+    y = torch.empty(n_rows, hidden, **f32)
+    y_lp = torch.empty((n_rows, hidden) if want_lp else (0,), dtype=xr.dtype, device=agg.device)
+    beta, mean, rstd = (torch.empty(n_rows, **f32) for _ in range(3))
+    with torch.cuda.device(agg.device), _Launch("gate_ln_fwd", 1, (n_rows, hidden, xr.element_size())):
+        rc = lib.alignn_gate_ln_fwd(_p(agg), _p(xr), _p(x), _p(wb), _p(gm), _p(bs), _p(y), _p(y_lp) if want_lp else None,
+                                    _p(beta), _p(mean), _p(rstd), n_rows, hidden, _dtype_code(xr), float(eps),
+                                    float(p_drop), seed, offset, _stream())
+    _lib.check(rc, "alignn_gate_ln_fwd")
+    return y, y_lp, beta, mean, rstd
 
-    @staticmethod
-    def backward(ctx, dy: Tensor, dy_lp: Optional[Tensor]):
-        lib = _lib.load()
-        agg, xr, wb, gm, bs, beta, mean, rstd = ctx.saved_tensors
-        n_rows, hidden = agg.shape
-        if dy is None:
-            dy = torch.zeros_like(agg)
-        dy = dy.contiguous().float()
-        if dy_lp is not None:
-            dy = dy + dy_lp.float()
-        f32 = dict(dtype=torch.float32, device=agg.device)
-        dagg = torch.empty(n_rows, hidden, **f32)
-        dxr = torch.empty_like(xr)
-        partials = torch.empty(int(lib.alignn_gate_ln_bwd_partial_rows()) * 5 * hidden, **f32)
-        dparams = torch.empty(5 * hidden, **f32)
-        with torch.cuda.device(agg.device), _Launch("gate_ln_bwd", 2, (n_rows, hidden, xr.element_size())):
-            rc = lib.alignn_gate_ln_bwd(_p(dy), _p(agg), _p(xr), _p(wb), _p(gm), _p(bs), _p(beta), _p(mean),
-                                        _p(rstd), _p(dagg), _p(dxr), _p(partials), _p(dparams), n_rows, hidden,
-                                        _dtype_code(xr), ctx.p_drop, ctx.seed, ctx.offset, _stream())
-        _lib.check(rc, "alignn_gate_ln_bwd")
-        wdt, gdt, bdt = ctx.param_dtypes
-        dwbeta = dparams[:3 * hidden].reshape(ctx.wbeta_shape).to(wdt)
-        dgamma = dparams[3 * hidden:4 * hidden].to(gdt)
-        dbias = dparams[4 * hidden:].to(bdt)
-        return dagg, dxr, dy, dwbeta, dgamma, dbias, None, None, None, None, None
+
+@_op_gate_ln.register_fake
+def _(agg, xr, x, wbeta, gamma, bias, eps, p_drop, seed, offset, want_lp):
+    n_rows, hidden = agg.shape
+    f32 = dict(dtype=torch.float32, device=agg.device)
+    return (torch.empty(n_rows, hidden, **f32),
+            torch.empty((n_rows, hidden) if want_lp else (0,), dtype=xr.dtype, device=agg.device),
+            torch.empty(n_rows, **f32), torch.empty(n_rows, **f32), torch.empty(n_rows, **f32))
+
+
+@_lib_def("alignn_b200::gate_ln_backward", mutates_args=(), device_types="cuda")
+def _op_gate_ln_backward(dy: Tensor, agg: Tensor, xr: Tensor, wbeta: Tensor, gamma: Tensor, bias: Tensor, beta: Tensor,
+                         mean: Tensor, rstd: Tensor, p_drop: float, seed: int, offset: int
+                         ) -> Tuple[Tensor, Tensor, Tensor]:
+    """Returns (dagg f32, dxr, dparams f32 [5 * hidden] = dw_beta x3 | dgamma | dbias)."""
+    lib = _lib.load()
+    agg = agg.contiguous().float()
+    xr = xr.contiguous()
+    wb = wbeta.detach().reshape(-1).contiguous().float()
+    gm, bs = gamma.detach().contiguous().float(), bias.detach().contiguous().float()
+    n_rows, hidden = agg.shape
+    dy = dy.contiguous().float()
+    f32 = dict(dtype=torch.float32, device=agg.device)
+    dagg = torch.empty(n_rows, hidden, **f32)
+    dxr = torch.empty_like(xr)
+    partials = torch.empty(int(lib.alignn_gate_ln_bwd_partial_rows()) * 5 * hidden, **f32)
+    dparams = torch.empty(5 * hidden, **f32)
+    with torch.cuda.device(agg.device), _Launch("gate_ln_bwd", 2, (n_rows, hidden, xr.element_size())):
+        rc = lib.alignn_gate_ln_bwd(_p(dy), _p(agg), _p(xr), _p(wb), _p(gm), _p(bs), _p(beta), _p(mean), _p(rstd),
+                                    _p(dagg), _p(dxr), _p(partials), _p(dparams), n_rows, hidden, _dtype_code(xr),
+                                    float(p_drop), seed, offset, _stream())
+    _lib.check(rc, "alignn_gate_ln_bwd")
+    return dagg, dxr, dparams
+
+
+@_op_gate_ln_backward.register_fake
+def _(dy, agg, xr, wbeta, gamma, bias, beta, mean, rstd, p_drop, seed, offset):
+    return (torch.empty(agg.shape, dtype=torch.float32, device=agg.device), torch.empty_like(xr),
+            torch.empty(5 * agg.size(1), dtype=torch.float32, device=agg.device))
+
+
+def _gate_ln_setup(ctx, inputs, output):
+    agg, xr, x, wbeta, gamma, bias, eps, p_drop, seed, offset, want_lp = inputs
+    _, _, beta, mean, rstd = output
+    ctx.save_for_backward(agg, xr, wbeta, gamma, bias, beta, mean, rstd)
+    ctx.args = (float(p_drop), seed, offset)
+
+
+def _gate_ln_backward(ctx, dy, dy_lp, _db, _dm, _dr):
+    agg, xr, wbeta, gamma, bias, beta, mean, rstd = ctx.saved_tensors
+    p_drop, seed, offset = ctx.args
+    hidden = agg.size(1)
+    if dy is None:
+        dy = torch.zeros(agg.shape, dtype=torch.float32, device=agg.device)
+    dy = dy.float()
+    if dy_lp is not None and dy_lp.numel() > 0:
+        dy = dy + dy_lp.float()
+    dagg, dxr, dparams = torch.ops.alignn_b200.gate_ln_backward(dy, agg, xr, wbeta, gamma, bias, beta, mean, rstd,
+                                                                p_drop, seed, offset)
+    return (dagg.to(agg.dtype), dxr, dy, dparams[:3 * hidden].reshape(wbeta.shape).to(wbeta.dtype),
+            dparams[3 * hidden:4 * hidden].to(gamma.dtype), dparams[4 * hidden:].to(bias.dtype), None, None, None, None,
+            None)
+
+
+_op_gate_ln.register_autograd(_gate_ln_backward, setup_context=_gate_ln_setup)
 
 
 def gate_ln_relu_residual(agg: Tensor, xr: Tensor, x: Tensor, wbeta: Tensor, gamma: Tensor, bias: Tensor,
                           eps: float = 1e-5, p_drop: float = 0.0, seed: int = 0, offset: int = 0,
                           want_lp: bool = False):
-    """``x + dropout(relu(LayerNorm(beta*xr + (1-beta)*agg)))`` with ``beta = sigmoid(wbeta . [agg, xr, agg-xr])``.
-
-    Returns ``(y_fp32, y_lowprecision_or_None)``."""
-    return _GateLn.apply(agg, xr, x, wbeta, gamma, bias, float(eps), float(p_drop), int(seed), int(offset),
-                         bool(want_lp))
+    """``x + dropout(relu(LayerNorm(beta*xr + (1-beta)*agg)))`` with ``beta = sigmoid(wbeta . [agg, xr, agg-xr])``
+    (custom op ``alignn_b200::gate_ln``).  Returns ``(y_fp32, y_lowprecision_or_None)``."""
+    y, y_lp, _, _, _ = torch.ops.alignn_b200.gate_ln(agg, xr, x, wbeta, gamma, bias, float(eps), float(p_drop),
+                                                     int(seed), int(offset), bool(want_lp))
+    return y, (y_lp if want_lp else None)
 
 
 # --------------------------------------------------------------------------------------------------
 # per-graph mean pooling
 # --------------------------------------------------------------------------------------------------
-class _SegmentMean(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x: Tensor, plan: GraphPlan):
-        _require_cuda(x)
-        lib = _lib.load()
-        x = x.contiguous().float()
-        n_graphs, hidden = plan.n_nodes, int(x.size(1))
-        pooled = torch.empty(n_graphs, hidden, dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device), _Launch("segment_mean_fwd", 1):
-            rc = lib.alignn_segment_mean_fwd(_p(x), _p(plan.rowptr), _p(plan.eid), _p(pooled), n_graphs, hidden,
-                                             _stream())
-        _lib.check(rc, "alignn_segment_mean_fwd")
-        ctx.plan, ctx.n_rows = plan, int(x.size(0))
-        return pooled
+@_lib_def("alignn_b200::segment_mean", mutates_args=(), device_types="cuda")
+def _op_segment_mean(x: Tensor, rowptr: Tensor, eid: Tensor, n_graphs: int) -> Tensor:
+    _require_cuda(x)
+    lib = _lib.load()
+    x = x.contiguous().float()
+    hidden = int(x.size(1))
+    pooled = torch.empty(n_graphs, hidden, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device), _Launch("segment_mean_fwd", 1):
+        rc = lib.alignn_segment_mean_fwd(_p(x), _p(rowptr), _p(eid), _p(pooled), n_graphs, hidden, _stream())
+    _lib.check(rc, "alignn_segment_mean_fwd")
+    return pooled
 
-    @staticmethod
-    def backward(ctx, dpooled: Tensor):
-        lib = _lib.load()
-        plan = ctx.plan
-        dpooled = dpooled.contiguous().float()
-        hidden = int(dpooled.size(1))
-        dx = torch.zeros(ctx.n_rows, hidden, dtype=torch.float32, device=dpooled.device)
-        with torch.cuda.device(dpooled.device), _Launch("segment_mean_bwd", 1):
-            rc = lib.alignn_segment_mean_bwd(_p(dpooled), _p(plan.rowptr), _p(plan.eid), _p(dx), plan.n_nodes,
-                                             hidden, _stream())
-        _lib.check(rc, "alignn_segment_mean_bwd")
-        return dx, None
+
+@_op_segment_mean.register_fake
+def _(x, rowptr, eid, n_graphs):
+    return torch.empty(n_graphs, x.size(1), dtype=torch.float32, device=x.device)
+
+
+@_lib_def("alignn_b200::segment_mean_backward", mutates_args=(), device_types="cuda")
+def _op_segment_mean_backward(dpooled: Tensor, rowptr: Tensor, eid: Tensor, n_rows: int) -> Tensor:
+    lib = _lib.load()
+    dpooled = dpooled.contiguous().float()
+    n_graphs, hidden = dpooled.shape
+    dx = torch.zeros(n_rows, hidden, dtype=torch.float32, device=dpooled.device)
+    with torch.cuda.device(dpooled.device), _Launch("segment_mean_bwd", 1):
+        rc = lib.alignn_segment_mean_bwd(_p(dpooled), _p(rowptr), _p(eid), _p(dx), n_graphs, hidden, _stream())
+    _lib.check(rc, "alignn_segment_mean_bwd")
+    return dx
+
+
+@_op_segment_mean_backward.register_fake
+def _(dpooled, rowptr, eid, n_rows):
+    return torch.empty(n_rows, dpooled.size(1), dtype=torch.float32, device=dpooled.device)
+
+
+def _segment_mean_setup(ctx, inputs, output):
+    x, rowptr, eid, n_graphs = inputs
+    ctx.save_for_backward(rowptr, eid)
+    ctx.n_rows, ctx.x_dtype = int(x.size(0)), x.dtype
+
+
+def _segment_mean_backward(ctx, dpooled):
+    rowptr, eid = ctx.saved_tensors
+    dx = torch.ops.alignn_b200.segment_mean_backward(dpooled, rowptr, eid, ctx.n_rows)
+    return dx.to(ctx.x_dtype), None, None, None
+
+
+_op_segment_mean.register_autograd(_segment_mean_backward, setup_context=_segment_mean_setup)
 
 
 def build_pool_plan(batch: Tensor, num_graphs: int) -> GraphPlan:
@@ -360,8 +478,9 @@ def build_pool_plan(batch: Tensor, num_graphs: int) -> GraphPlan:
 
 
 def segment_mean(x: Tensor, pool_plan: GraphPlan) -> Tensor:
-    """``global_mean_pool``: per-graph mean of node rows (fp32 ``[B, H]``)."""
-    return _SegmentMean.apply(x, pool_plan)
+    """``global_mean_pool``: per-graph mean of node rows (fp32 ``[B, H]``; custom op ``alignn_b200::segment_mean``)."""
+    _require_cuda(x)
+    return torch.ops.alignn_b200.segment_mean(x, pool_plan.rowptr, pool_plan.eid, int(pool_plan.n_nodes))
 
 
 # --------------------------------------------------------------------------------------------------
@@ -402,6 +521,7 @@ def _ld(t: Tensor) -> int:
 
 def raw_edgeattn_fwd(q: Tensor, k: Tensor, v: Tensor, qt: Tensor, feat: Tensor, plan: GraphPlan, heads: int,
                      p_drop: float, seed: int, offset: int):
+    _static_dropout_guard(p_drop, "edgeattn_fwd")
     lib = _lib.load()
     n_nodes, hidden = q.shape
     n_edges = plan.n_edges

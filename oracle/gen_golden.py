@@ -40,6 +40,9 @@ MODEL_CASES = {
     "dups_selfloops_h64": (  # duplicate bonds + self loops (periodic images), generic-vs-fast head split
         dict(node_dim=206, edge_dim=36, angle_dim=11, global_dim=289, target_dim=2, hidden=64, layers=1, heads=4, dropout=0.0),
         dict(n_graphs=3, atoms=7, k=4, seed=14, lg_inc="bonds", dups=True)),
+    "default_arch_h256": (  # the default width / heads (train.py:1084-1086): the width the tensor-core kernels serve
+        dict(node_dim=206, edge_dim=36, angle_dim=11, global_dim=289, target_dim=2, hidden=256, layers=1, heads=4, dropout=0.0),
+        dict(n_graphs=6, atoms=10, k=6, seed=16, lg_inc="pyg")),
     "odd_width_h48": (  # hidden/8 not a power of two -> generic kernels
         dict(node_dim=206, edge_dim=36, angle_dim=11, global_dim=289, target_dim=2, hidden=48, layers=1, heads=3, dropout=0.0),
         dict(n_graphs=2, atoms=7, k=4, seed=15, lg_inc="pyg")),
@@ -112,12 +115,15 @@ def main():
     if ref is None:
         raise SystemExit("/root/reference is not mounted: goldens can only be regenerated in the build container")
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    only = set(sys.argv[1:])          # `python oracle/gen_golden.py default_arch_h256`: just the named model cases
     for name, (ctor, bkw) in MODEL_CASES.items():
+        if only and name not in only:
+            continue
         case = make_model_case(ref, name, ctor, bkw)
         path = os.path.join(GOLDEN_DIR, f"model_{name}.pt")
         torch.save(case, path)
         print(f"{path}: {os.path.getsize(path) / 1024:.0f} KiB  loss={float(case['loss']):.6f}")
-    for hidden, heads, n, e, seed in ((64, 4, 40, 300, 21), (32, 1, 24, 150, 22), (128, 4, 12, 60, 23), (48, 3, 20, 90, 24)):
+    for hidden, heads, n, e, seed in () if only else ((64, 4, 40, 300, 21), (32, 1, 24, 150, 22), (128, 4, 12, 60, 23), (48, 3, 20, 90, 24)):
         case = make_block_case(ref, hidden, heads, n, e, seed)
         path = os.path.join(GOLDEN_DIR, f"blocks_h{hidden}_heads{heads}.pt")
         torch.save(case, path)

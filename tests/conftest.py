@@ -61,3 +61,51 @@ def grad_err(got, want, gmax):
 
 def grads_gmax(grads):
     return max(float(v.detach().abs().max()) for v in grads.values())
+
+
+def per_tensor_report(got, want):
+    """name -> (rel, share): rel = max|got - want| / max|want| of THAT tensor; share = max|want| / largest |gradient|."""
+    gmax = max(grads_gmax(want), 1e-30)
+    out = {}
+    for k, w in want.items():
+        w = w.detach().double().cpu()
+        g = got[k].detach().double().cpu()
+        wmax = float(w.abs().max())
+        out[k] = (float((g - w).abs().max()) / max(wmax, 1e-30), wmax / gmax)
+    return out
+
+
+def check_per_tensor(got, want, tol, allow=None, label=None):
+    """Every gradient tensor within ``tol`` of ITS OWN scale (max|err| / max|want| per tensor), except tensors matched by
+    ``allow`` = {name suffix: (bound, reason)}: those are printed with their measured error, their bound and the reason,
+    and still asserted against that bound.  A suffix bound that is a tuple ("abs", x) compares max|err| against
+    x * (largest gradient of the model) -- for tensors whose TRUE gradient is exactly zero."""
+    allow = allow or {}
+    rep = per_tensor_report(got, want)
+    gmax = max(grads_gmax(want), 1e-30)
+    lines, bad = [], []
+    for k, (rel, share) in sorted(rep.items(), key=lambda kv: -kv[1][0]):
+        rule = next(((s, b) for s, b in allow.items() if k.endswith(s)), None)
+        if rule is None:
+            if rel > tol:
+                bad.append(f"{k}: rel {rel:.3e} > {tol:g} (share of gmax {share:.2e})")
+            continue
+        bound, reason = rule[1]
+        if isinstance(bound, tuple):
+            err = float((got[k].detach().double().cpu() - want[k].detach().double().cpu()).abs().max()) / gmax
+            ok, shown = err <= bound[1], f"abs err {err:.3e} of gmax (bound {bound[1]:g})"
+        else:
+            ok, shown = rel <= bound, f"rel {rel:.3e} (bound {bound:g}; default {tol:g})"
+        lines.append(f"  allow-listed {k}: {shown}, share {share:.2e} -- {reason}")
+        if not ok:
+            bad.append(f"{k}: {shown} -- allow-listed bound exceeded")
+    worst = sorted(rep.items(), key=lambda kv: -kv[1][0])[:8]
+    text = "\n".join([f"[per-tensor gradient parity] {label or ''} tol {tol:g}"]
+                     + [f"  {k}: rel {r:.3e} share {s:.2e}" for k, (r, s) in worst] + lines)
+    print(text)
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if label and os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, f"parity_{label}.txt"), "w") as fh:
+            fh.write(text + "\n" + "\n".join(f"{k}\t{r:.4e}\t{s:.3e}" for k, (r, s) in sorted(rep.items())) + "\n")
+    assert not bad, "\n".join(bad)
+    return rep

@@ -97,3 +97,71 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "pyg_shim" not in src and "torch_geometric" not in src.replace("torch_geometric.", "PYG."), f
+
+
+def test_torch_custom_ops_are_registered_with_fake_kernels():
+    """SURVEY.md 8(b): the generic operators are torch custom ops (namespace ``alignn_b200``) over the C-ABI launchers;
+    their fake (meta) kernels propagate shapes / dtypes without a device (what Dynamo / FakeTensor tracing needs)."""
+    import torch
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    import gnn_elasticity_predictor_b200  # noqa: F401  (registers the ops)
+    names = ["conv_core", "conv_core_backward", "gate_ln", "gate_ln_backward", "segment_mean", "segment_mean_backward"]
+    for n in names:
+        assert hasattr(torch.ops.alignn_b200, n), n
+    with FakeTensorMode():
+        i32 = dict(dtype=torch.int32, device="cuda")
+        q = torch.empty(10, 64, device="cuda", dtype=torch.bfloat16)
+        e = torch.empty(30, 64, device="cuda", dtype=torch.bfloat16)
+        rp, c = torch.empty(11, **i32), torch.empty(30, **i32)
+        agg, m, z = torch.ops.alignn_b200.conv_core(q, q, q, e, rp, c, c, rp, c, c, 4, 0.0, 0, 0)
+        assert agg.shape == (10, 64) and agg.dtype == torch.float32 and m.shape == z.shape == (10, 4)
+        dq, dk, dv, de = torch.ops.alignn_b200.conv_core_backward(agg, agg, q, q, q, e, m, z, rp, c, c, rp, c, c, 4, 0.0, 0, 0)
+        assert dq.shape == q.shape and de.shape == e.shape and de.dtype == e.dtype
+        w = torch.empty(1, 192, device="cuda")
+        g = torch.empty(64, device="cuda")
+        y, y_lp, beta, mean, rstd = torch.ops.alignn_b200.gate_ln(agg, q, agg, w, g, g, 1e-5, 0.0, 0, 0, True)
+        assert y.shape == (10, 64) and y_lp.dtype == torch.bfloat16 and beta.shape == (10,)
+        pooled = torch.ops.alignn_b200.segment_mean(agg, rp, c, 3)
+        assert pooled.shape == (3, 64)
+
+
+def test_custom_ops_refuse_cpu_tensors():
+    import pytest
+    import torch
+    import gnn_elasticity_predictor_b200  # noqa: F401
+    q = torch.zeros(4, 32)
+    i = torch.zeros(5, dtype=torch.int32)
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        torch.ops.alignn_b200.conv_core(q, q, q, q, i, i, i, i, i, i, 1, 0.0, 0, 0)
+
+
+def test_compile_wrapper_keeps_reference_attribute_access_and_checkpoint_compat():
+    """train.py:1511 wraps the model in torch.compile; :1516-1517 then reads model.base / mean_heads / logvar_heads;
+    checkpoints written from the wrapper carry torch's `_orig_mod.` prefix and must load into a plain model."""
+    import torch
+    import gnn_elasticity_predictor_b200 as pkg
+    m = pkg.HeteroAlignnRegressor(pkg.AlignnRegressor(6, 8, 7, 0, 2, 32, 1, 1, 0.0), 2)
+    cm = torch.compile(m, mode="max-autotune")
+    assert cm.base is m.base and cm.mean_heads is m.mean_heads and cm.logvar_heads is m.logvar_heads
+    sd = cm.state_dict()
+    assert [k.replace("_orig_mod.", "") for k in sd] == list(m.state_dict())
+    cm.load_state_dict(sd)                                            # train.py:1921
+    m2 = pkg.HeteroAlignnRegressor(pkg.AlignnRegressor(6, 8, 7, 0, 2, 32, 1, 1, 0.0), 2)
+    m2.load_state_dict(sd, strict=True)
+    assert all(torch.equal(a, b) for a, b in zip(m2.state_dict().values(), m.state_dict().values()))
+
+
+def test_stale_library_that_cannot_be_rebuilt_raises(monkeypatch):
+    """_lib.load must never fall back to a stale binary when the rebuild fails (round-1 verdict, weak #9)."""
+    import pytest
+    from gnn_elasticity_predictor_b200 import _lib, build as b
+    monkeypatch.setattr(_lib, "_LIB", None)
+    monkeypatch.setattr(b, "is_current", lambda: False)
+
+    def boom(*a, **k):
+        raise RuntimeError("nvcc exploded")
+    monkeypatch.setattr(b, "build", boom)
+    with pytest.raises(RuntimeError, match="stale"):
+        _lib.load()
+    monkeypatch.setattr(_lib, "_LIB", None)
+    assert _lib.load(rebuild_if_stale=False) is not None             # explicit opt-in still loads the binary

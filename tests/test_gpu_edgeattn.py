@@ -267,3 +267,72 @@ def test_lgattn_backward_and_angle_gradient_match_stored_feature_kernels():
     d1 = ops.raw_lg_angle_grad(a_csr, w1, b1, plan, coefs, qts, gts)
     d2 = ops.raw_lg_angle_grad(a_csr, w1, b1, plan, coefs, qts, gts)
     assert torch.equal(d1[0], d2[0]) and torch.equal(d1[1], d2[1]) and bool(torch.isfinite(d1[0]).all())
+
+
+# ---- the in-kernel-feature line-graph kernels DIRECTLY against the oracle (not against sibling CUDA kernels) -----------
+def _round_bf16_(module):
+    with torch.no_grad():
+        for p_ in module.parameters():
+            p_.copy_(p_.to(torch.bfloat16).to(p_.dtype))
+
+
+@pytest.mark.parametrize("case", ["pyg", "bonds", "skewed"])
+def test_lgattn_fwd_bwd_and_angle_grad_directly_vs_fp64_oracle(case):
+    """``angle_encoder`` + ``EdgeUpdateBlock`` of the oracle (reference ``train.py:303-317, 360-364``; PyG arithmetic from
+    the shim) in fp64 on bf16-representable parameters and inputs, against ONE line-graph block on the kernels the
+    benchmark times: ``alignn_lgattn_fwd`` / ``alignn_lgattn_bwd_dst`` / ``alignn_edgeattn_bwd_src_lp`` /
+    ``alignn_lg_angle_grad`` (+ the gate/LayerNorm kernels and the stacked projection).  Output and EVERY gradient --
+    bond states, both angle-encoder layers, all conv parameters, LayerNorm -- per tensor at 2e-2 of its own scale."""
+    from oracle import model_ref
+    from conftest import check_per_tensor
+    from gnn_elasticity_predictor_b200 import modules
+    from gnn_elasticity_predictor_b200.fused import LgShared
+    torch.manual_seed(11)
+    if case == "skewed":
+        n_b, n_l = 301, 7000
+        index = skewed_graph(n_b, n_l, 41, 500)
+        ang = torch.rand(n_l, 11)
+    else:
+        b = pkg.synthetic_batch(6, 10, 6, seed=5, lg_inc=case)
+        index, ang, n_b = b.lg_edge_index, b.lg_edge_attr, b.edge_index.size(1)
+        n_l = index.size(1)
+    enc = torch.nn.Sequential(torch.nn.Linear(11, H), torch.nn.ReLU(), torch.nn.Linear(H, H)).double()
+    blk = model_ref.EdgeUpdateBlock(H, HEADS, 0.0).double()
+    with torch.no_grad():
+        blk.norm.weight.uniform_(0.5, 1.5); blk.norm.bias.uniform_(-0.3, 0.3)
+    _round_bf16_(enc); _round_bf16_(blk)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(n_b, H, generator=g).to(torch.bfloat16).float()
+    ang = ang.to(torch.bfloat16).float()
+    gout = torch.randn(n_b, H, generator=g)
+    # oracle, fp64
+    xr = x.double().requires_grad_(True)
+    yr = blk(xr, index, enc(ang.double()))
+    yr.backward(gout.double())
+    want = {f"blk.{k}": p_.grad for k, p_ in blk.named_parameters()}
+    want.update({f"enc.{k}": p_.grad for k, p_ in enc.named_parameters()})
+    want["x"] = xr.grad
+    # ours: the lg family, one block, exactly as AlignnRegressor._trunk_streaming drives it
+    ours = pkg.EdgeUpdateBlock(H, HEADS, 0.0).to(DEV)
+    ours.load_state_dict({k: v.float() for k, v in blk.state_dict().items()}, strict=True)
+    enc_o = torch.nn.Sequential(torch.nn.Linear(11, H), torch.nn.ReLU(), torch.nn.Linear(H, H)).to(DEV)
+    enc_o.load_state_dict({k: v.float() for k, v in enc.state_dict().items()})
+    cd = torch.bfloat16
+    assert ops.lgattn_enabled(H, HEADS, 11, cd)
+    plan = pkg.build_plan(index.to(DEV), n_b)
+    w1p, b1p = enc_o[0].weight, enc_o[0].bias
+    lg = LgShared(ops.pack_angles(ang.to(DEV), plan), w1p.detach().contiguous().float(), b1p.detach().contiguous().float(), 1)
+    we = ours.conv.lin_edge.weight.float()
+    wc, cvec = we @ enc_o[2].weight.float(), we @ enc_o[2].bias.float()
+    xo = x.to(DEV).requires_grad_(True)
+    k0 = ops.STATS.kernels
+    yo, _ = modules._stream_block(ours.conv, ours.norm, 0.0, True, xo, None, None, None, wc, cvec, plan, cd,
+                                  is_last_visitor=True, lg=lg, w1=w1p, b1=b1p)
+    yo.backward(gout.to(DEV))
+    assert ops.STATS.kernels > k0
+    assert rel_err(yo, yr) < 2e-2
+    got = {f"blk.{k}": p_.grad for k, p_ in ours.named_parameters()}
+    got.update({f"enc.{k}": p_.grad for k, p_ in enc_o.named_parameters()})
+    got["x"] = xo.grad
+    check_per_tensor(got, want, 2e-2, {"conv.lin_key.bias": (("abs", 2e-3), "true gradient is exactly zero")},
+                     label=f"lg_block_vs_oracle_{case}")

@@ -6,7 +6,7 @@ import os
 import pytest
 import torch
 
-from conftest import GOLDEN_DIR, Bag, grad_err, grads_gmax, load_golden, rel_err
+from conftest import GOLDEN_DIR, Bag, check_per_tensor, grad_err, grads_gmax, load_golden, rel_err
 from oracle import model_ref
 import gnn_elasticity_predictor_b200 as pkg
 
@@ -147,12 +147,29 @@ def test_config1_default_arch_bf16_autocast_vs_oracle(seed):
     mean, logvar, loss, grads = _loss_and_grads(ours, batch.to(DEV), autocast=True)
     assert rel_err(mean, r_mean) < 2e-2 and rel_err(logvar, r_logvar) < 2e-2
     assert rel_err(loss, r_loss) < 2e-2
-    for k, w in want.items():
-        err = float((grads[k].double() - w.cpu()).abs().max())
-        assert err < max(2e-2 * gmax, 1.5 * amp_err[k]), (k, err / gmax, amp_err[k] / gmax)
-        if float(w.abs().max()) > 1e-3 * gmax:
-            cos = float(torch.nn.functional.cosine_similarity(grads[k].double().flatten(), w.cpu().flatten(), dim=0))
-            assert cos > 0.95, (k, cos)
+    # per tensor, relative to the tensor's OWN scale: 2e-2, else -- by name, printed -- no worse than 1.5x what the
+    # reference's own AMP run measures on that tensor against the same fp64 target
+    from conftest import per_tensor_report
+    rep = per_tensor_report(grads, want)
+    amp_rep = per_tensor_report({k: p.grad for k, p in ref.named_parameters() if p.grad is not None}, want)
+    bad = []
+    for k, (rel, share) in sorted(rep.items(), key=lambda kv: -kv[1][0]):
+        if rel <= 2e-2:
+            continue
+        if k.endswith("conv.lin_key.bias"):          # true gradient exactly zero: absolute bound
+            err = float((grads[k].double() - want[k].cpu()).abs().max()) / gmax
+            print(f"  exception {k}: zero true gradient, abs err {err:.2e} of gmax")
+            if err > 2e-3:
+                bad.append((k, "abs", err))
+            continue
+        print(f"  exception {k}: rel {rel:.3e} (share {share:.1e}); the reference's own bf16 autocast: {amp_rep[k][0]:.3e}")
+        if rel > 1.5 * amp_rep[k][0]:
+            bad.append((k, rel, amp_rep[k][0]))
+        if share > 1e-3:
+            cos = float(torch.nn.functional.cosine_similarity(grads[k].double().flatten(), want[k].cpu().flatten(), dim=0))
+            if cos <= 0.95:
+                bad.append((k, "cos", cos))
+    assert not bad, bad
 
 
 def test_smoke_arch_eval_mode_and_no_grad():
@@ -191,17 +208,57 @@ def test_dropout_training_mode_runs_and_is_seed_reproducible():
     assert torch.equal(ours(batch)[0], ours(batch)[0])
 
 
-def test_config2_size_bf16_step_is_finite_and_deterministic():
-    """BASELINE config 2 shapes (256 x 32-atom cells, L = 1 081 344) through the full fwd+bwd."""
-    ours = pkg.HeteroAlignnRegressor(pkg.AlignnRegressor(206, 36, 11, 289, 2, 256, 4, 4, 0.0), 2).to(DEV)
-    batch = pkg.synthetic_batch(256, 32, 12, seed=0).to(DEV)
-    assert batch.sizes["L"] == 1081344
-    _, _, loss1, g1 = _loss_and_grads(ours, batch, autocast=True)
-    _, _, loss2, g2 = _loss_and_grads(ours, batch, autocast=True)
-    assert torch.isfinite(loss1) and all(torch.isfinite(v).all() for v in g1.values())
-    assert torch.equal(loss1, loss2)
+# Tensors whose TRUE gradient is exactly zero: the segment softmax is invariant to adding one vector to every key of a
+# row, so d loss / d lin_key.bias == 0 and every implementation (the fp32 CPU oracle vs the fp64 oracle included) produces
+# rounding noise only.  They are held to an absolute bound relative to the largest gradient of the model instead.
+ZERO_TRUE_GRADIENT = {"conv.lin_key.bias": (("abs", 2e-3), "true gradient is exactly zero (softmax shift invariance)")}
+
+
+def test_h256_golden_made_by_the_reference_classes_bf16_tensor_core_path():
+    """The H=256 / 4-head fixture made by the reference's own classes (oracle/gen_golden.py), run through the bf16
+    regime = the tensor-core kernels the benchmark times (the fp32 parametrisation above runs the CUDA-core family)."""
+    g = load_golden("model_default_arch_h256.pt")
+    ctor = g["ctor"]
+    model = pkg.HeteroAlignnRegressor(pkg.AlignnRegressor(**ctor), ctor["target_dim"]).to(DEV)
+    model.load_state_dict(g["state_dict"], strict=True)
+    model.train()
+    batch = Bag(g["batch"], g["num_graphs"]).to(DEV)
+    mean, logvar, loss, grads = _loss_and_grads(model, batch, autocast=True)
+    assert rel_err(mean, g["mean"]) < 2e-2 and rel_err(logvar, g["logvar"]) < 2e-2
+    assert rel_err(loss, g["loss"]) < 2e-2
+    check_per_tensor(grads, g["grads"], 2e-2, {**ZERO_TRUE_GRADIENT, **BF16_ALLOW_SMALL}, label="golden_h256_bf16")
+
+
+# bf16 regime, per-tensor bound 2e-2 of the tensor's own scale.  Exceptions, each by name with its reason; the bounds are
+# what the reference's OWN bf16-autocast run (the oracle on CPU under torch.autocast('cpu', bfloat16)) measures against
+# the same fp64 target at config-1 size (test_config1_default_arch_bf16_autocast_vs_oracle prints both side by side).
+BF16_ALLOW_SMALL = {}
+BF16_ALLOW_CONFIG2 = {}
+
+
+@pytest.mark.parametrize("lg_inc", ["pyg", "bonds"])
+def test_config2_bf16_forward_loss_and_every_gradient_vs_fp64_oracle(lg_inc):
+    """BASELINE config 2 (256 x 32-atom cells x 12 neighbours: N=8 192, E=98 304, L=1 081 344; H=256, 4+4 layers, 4 heads)
+    -- the exact workload bench.py times -- forward, loss and every parameter gradient against the oracle in fp64."""
+    ref, ours = _pair(256, 4, 4)
+    batch = pkg.synthetic_batch(256, 32, 12, seed=0, lg_inc=lg_inc)
+    assert batch.sizes == {"B": 256, "N": 8192, "E": 98304, "L": 1081344}
+    tz = pkg.zscore_targets(batch.y, 256)
+    torch.set_num_threads(max(torch.get_num_threads(), (os.cpu_count() or 1)))
+    ref = ref.double()
+    r_mean, r_logvar = ref(_as_double(batch))
+    r_loss = model_ref.gaussian_nll_loss(r_mean, r_logvar, tz.double())
+    r_loss.backward()
+    want = {k: p.grad for k, p in ref.named_parameters() if p.grad is not None}
+    mean, logvar, loss, grads = _loss_and_grads(ours, batch.to(DEV), autocast=True)
+    assert rel_err(mean, r_mean) < 2e-2 and rel_err(logvar, r_logvar) < 2e-2
+    assert rel_err(loss, r_loss) < 2e-2
+    check_per_tensor(grads, want, 2e-2, {**ZERO_TRUE_GRADIENT, **BF16_ALLOW_CONFIG2}, label=f"config2_bf16_{lg_inc}")
+    # determinism of the hand-written path at this size (atomics-free): two runs agree bit for bit on the loss
+    _, _, loss2, g2 = _loss_and_grads(ours, batch.to(DEV), autocast=True)
+    assert torch.equal(loss, loss2)
     for k in ("base.edge_blocks.0.conv.lin_edge.weight", "base.node_encoder.0.weight"):
-        assert rel_err(g1[k], g2[k]) < 1e-5, k     # hand-written kernels are atomics-free (cuBLAS split-K may not be)
+        assert rel_err(grads[k], g2[k]) < 1e-5, k     # cuBLAS split-K may reorder; ours may not
 
 
 # ---- streaming path (hidden = 256): blocks against the fp64 oracle, and against the materialised path ---------
