@@ -312,6 +312,18 @@ def test_lgattn_fwd_bwd_and_angle_grad_directly_vs_fp64_oracle(case):
     want = {f"blk.{k}": p_.grad for k, p_ in blk.named_parameters()}
     want.update({f"enc.{k}": p_.grad for k, p_ in enc.named_parameters()})
     want["x"] = xr.grad
+    # the reference's OWN bf16-autocast run of the same block (oracle on CPU): the per-tensor yardstick for exceptions
+    import copy
+    enc_a, blk_a = copy.deepcopy(enc).float(), copy.deepcopy(blk).float()
+    for m_ in (enc_a, blk_a):
+        m_.zero_grad(set_to_none=True)
+    xa = x.clone().requires_grad_(True)
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        ya = blk_a(xa, index, enc_a(ang))
+    ya.float().backward(gout)
+    amp = {f"blk.{k}": p_.grad for k, p_ in blk_a.named_parameters()}
+    amp.update({f"enc.{k}": p_.grad for k, p_ in enc_a.named_parameters()})
+    amp["x"] = xa.grad
     # ours: the lg family, one block, exactly as AlignnRegressor._trunk_streaming drives it
     ours = pkg.EdgeUpdateBlock(H, HEADS, 0.0).to(DEV)
     ours.load_state_dict({k: v.float() for k, v in blk.state_dict().items()}, strict=True)
@@ -335,4 +347,4 @@ def test_lgattn_fwd_bwd_and_angle_grad_directly_vs_fp64_oracle(case):
     got.update({f"enc.{k}": p_.grad for k, p_ in enc_o.named_parameters()})
     got["x"] = xo.grad
     check_per_tensor(got, want, 2e-2, {"conv.lin_key.bias": (("abs", 2e-3), "true gradient is exactly zero")},
-                     label=f"lg_block_vs_oracle_{case}")
+                     label=f"lg_block_vs_oracle_{case}", amp=amp)

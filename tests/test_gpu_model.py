@@ -6,7 +6,7 @@ import os
 import pytest
 import torch
 
-from conftest import GOLDEN_DIR, Bag, check_per_tensor, grad_err, grads_gmax, load_golden, rel_err
+from conftest import GOLDEN_DIR, Bag, check_per_tensor, grad_err, grads_gmax, load_golden, reference_amp_grads, rel_err
 from oracle import model_ref
 import gnn_elasticity_predictor_b200 as pkg
 
@@ -119,6 +119,12 @@ def test_config1_default_arch_fp32_vs_oracle(lg_inc):
         assert grad_err(grads[k], w, gmax) < 1e-4, k
 
 
+# Tensors whose TRUE gradient is exactly zero: the segment softmax is invariant to adding one vector to every key of a
+# row, so d loss / d lin_key.bias == 0 and every implementation (the fp32 CPU oracle vs the fp64 oracle included) produces
+# rounding noise only.  They are held to an absolute bound relative to the largest gradient of the model instead.
+ZERO_TRUE_GRADIENT = {"conv.lin_key.bias": (("abs", 2e-3), "true gradient is exactly zero (softmax shift invariance)")}
+
+
 @pytest.mark.parametrize("seed", [1, 2])
 def test_config1_default_arch_bf16_autocast_vs_oracle(seed):
     """bf16 autocast regime (reference ``train.py:632-636``).  Target = the oracle in fp64.  Tolerance: rel 2e-2 on
@@ -136,40 +142,18 @@ def test_config1_default_arch_bf16_autocast_vs_oracle(seed):
     r_loss.backward()
     want = {k: p.grad for k, p in ref64.named_parameters() if p.grad is not None}
     gmax = grads_gmax(want)
-    # the reference's own AMP error on the same batch (CPU bf16 autocast of the oracle)
-    with torch.autocast("cpu", dtype=torch.bfloat16):
-        a_mean, a_logvar = ref(batch)
-        a_loss = model_ref.gaussian_nll_loss(a_mean.float(), a_logvar.float(), tz)
-    a_loss.backward()
-    amp_err = {k: float((p.grad.double() - want[k]).abs().max()) for k, p in ref.named_parameters()
-               if p.grad is not None}
-
+    # the reference's own AMP run on the same batch (CPU bf16 autocast of the oracle): the per-tensor yardstick
+    amp = reference_amp_grads(ref, batch, tz, model_ref.gaussian_nll_loss)
     mean, logvar, loss, grads = _loss_and_grads(ours, batch.to(DEV), autocast=True)
     assert rel_err(mean, r_mean) < 2e-2 and rel_err(logvar, r_logvar) < 2e-2
     assert rel_err(loss, r_loss) < 2e-2
     # per tensor, relative to the tensor's OWN scale: 2e-2, else -- by name, printed -- no worse than 1.5x what the
     # reference's own AMP run measures on that tensor against the same fp64 target
-    from conftest import per_tensor_report
-    rep = per_tensor_report(grads, want)
-    amp_rep = per_tensor_report({k: p.grad for k, p in ref.named_parameters() if p.grad is not None}, want)
-    bad = []
-    for k, (rel, share) in sorted(rep.items(), key=lambda kv: -kv[1][0]):
-        if rel <= 2e-2:
-            continue
-        if k.endswith("conv.lin_key.bias"):          # true gradient exactly zero: absolute bound
-            err = float((grads[k].double() - want[k].cpu()).abs().max()) / gmax
-            print(f"  exception {k}: zero true gradient, abs err {err:.2e} of gmax")
-            if err > 2e-3:
-                bad.append((k, "abs", err))
-            continue
-        print(f"  exception {k}: rel {rel:.3e} (share {share:.1e}); the reference's own bf16 autocast: {amp_rep[k][0]:.3e}")
-        if rel > 1.5 * amp_rep[k][0]:
-            bad.append((k, rel, amp_rep[k][0]))
-        if share > 1e-3:
+    rep = check_per_tensor(grads, want, 2e-2, ZERO_TRUE_GRADIENT, label=f"config1_bf16_seed{seed}", amp=amp)
+    for k, (rel, share) in rep.items():
+        if rel > 2e-2 and share > 1e-3 and not k.endswith("conv.lin_key.bias"):
             cos = float(torch.nn.functional.cosine_similarity(grads[k].double().flatten(), want[k].cpu().flatten(), dim=0))
-            if cos <= 0.95:
-                bad.append((k, "cos", cos))
-    assert not bad, bad
+            assert cos > 0.95, (k, cos)
 
 
 def test_smoke_arch_eval_mode_and_no_grad():
@@ -208,12 +192,6 @@ def test_dropout_training_mode_runs_and_is_seed_reproducible():
     assert torch.equal(ours(batch)[0], ours(batch)[0])
 
 
-# Tensors whose TRUE gradient is exactly zero: the segment softmax is invariant to adding one vector to every key of a
-# row, so d loss / d lin_key.bias == 0 and every implementation (the fp32 CPU oracle vs the fp64 oracle included) produces
-# rounding noise only.  They are held to an absolute bound relative to the largest gradient of the model instead.
-ZERO_TRUE_GRADIENT = {"conv.lin_key.bias": (("abs", 2e-3), "true gradient is exactly zero (softmax shift invariance)")}
-
-
 def test_h256_golden_made_by_the_reference_classes_bf16_tensor_core_path():
     """The H=256 / 4-head fixture made by the reference's own classes (oracle/gen_golden.py), run through the bf16
     regime = the tensor-core kernels the benchmark times (the fp32 parametrisation above runs the CUDA-core family)."""
@@ -226,14 +204,14 @@ def test_h256_golden_made_by_the_reference_classes_bf16_tensor_core_path():
     mean, logvar, loss, grads = _loss_and_grads(model, batch, autocast=True)
     assert rel_err(mean, g["mean"]) < 2e-2 and rel_err(logvar, g["logvar"]) < 2e-2
     assert rel_err(loss, g["loss"]) < 2e-2
-    check_per_tensor(grads, g["grads"], 2e-2, {**ZERO_TRUE_GRADIENT, **BF16_ALLOW_SMALL}, label="golden_h256_bf16")
-
-
-# bf16 regime, per-tensor bound 2e-2 of the tensor's own scale.  Exceptions, each by name with its reason; the bounds are
-# what the reference's OWN bf16-autocast run (the oracle on CPU under torch.autocast('cpu', bfloat16)) measures against
-# the same fp64 target at config-1 size (test_config1_default_arch_bf16_autocast_vs_oracle prints both side by side).
-BF16_ALLOW_SMALL = {}
-BF16_ALLOW_CONFIG2 = {}
+    # yardstick for exceptions: the reference's own bf16 autocast on the same fixture (the oracle restatement is
+    # bit-identical to the reference classes that made it: tests/test_oracle_golden.py)
+    ref = model_ref.HeteroAlignnRegressor(model_ref.AlignnRegressor(**ctor), ctor["target_dim"])
+    ref.load_state_dict(g["state_dict"], strict=True)
+    cpu_batch = Bag(g["batch"], g["num_graphs"])
+    amp = reference_amp_grads(ref, cpu_batch, pkg.zscore_targets(cpu_batch.y, cpu_batch.num_graphs),
+                              model_ref.gaussian_nll_loss)
+    check_per_tensor(grads, g["grads"], 2e-2, ZERO_TRUE_GRADIENT, label="golden_h256_bf16", amp=amp)
 
 
 @pytest.mark.parametrize("lg_inc", ["pyg", "bonds"])
@@ -249,11 +227,14 @@ def test_config2_bf16_forward_loss_and_every_gradient_vs_fp64_oracle(lg_inc):
     r_mean, r_logvar = ref(_as_double(batch))
     r_loss = model_ref.gaussian_nll_loss(r_mean, r_logvar, tz.double())
     r_loss.backward()
-    want = {k: p.grad for k, p in ref.named_parameters() if p.grad is not None}
+    want = {k: p.grad.clone() for k, p in ref.named_parameters() if p.grad is not None}
     mean, logvar, loss, grads = _loss_and_grads(ours, batch.to(DEV), autocast=True)
     assert rel_err(mean, r_mean) < 2e-2 and rel_err(logvar, r_logvar) < 2e-2
     assert rel_err(loss, r_loss) < 2e-2
-    check_per_tensor(grads, want, 2e-2, {**ZERO_TRUE_GRADIENT, **BF16_ALLOW_CONFIG2}, label=f"config2_bf16_{lg_inc}")
+    # exceptions to 2e-2 per tensor: by name, printed, and no worse than 1.5x the reference's own bf16 autocast (oracle on
+    # the host cores under torch.autocast('cpu', bfloat16)) on the same batch against the same fp64 target
+    amp = reference_amp_grads(ref.float(), batch, tz, model_ref.gaussian_nll_loss)
+    check_per_tensor(grads, want, 2e-2, ZERO_TRUE_GRADIENT, label=f"config2_bf16_{lg_inc}", amp=amp)
     # determinism of the hand-written path at this size (atomics-free): two runs agree bit for bit on the loss
     _, _, loss2, g2 = _loss_and_grads(ours, batch.to(DEV), autocast=True)
     assert torch.equal(loss, loss2)
