@@ -29,11 +29,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
-NCU_TRAFFIC = {   # profiles/r01_v20_ncu_lg_{pyg,bonds}.txt, config 2, per launch (dram__bytes_read.sum + dram__bytes_write.sum)
-    "pyg": {"lgattn_fwd": 77_006_592, "lgattn_bwd_dst": 139_667_712, "conv_bwd_src": 53_102_592},
-    "bonds": {"lgattn_fwd": 664_554_752, "lgattn_bwd_dst": 1_120_396_800, "conv_bwd_src": 220_822_272},
-}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the line-graph kernels: read from the file that
+# scripts/ncu_traffic.py writes out of the committed `ncu --set full` capture of the SHIPPED kernels (profiles/)
+def load_ncu_traffic():
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh)
+    return {}
+
+
+NCU_TRAFFIC = load_ncu_traffic()
 METRIC = "ALIGNN train graphs/sec (fwd+bwd)"
 UNIT = "graphs/s"
 ARCH = dict(node_dim=206, edge_dim=36, angle_dim=11, global_dim=289, target_dim=2, hidden=256, layers=4, heads=4)
@@ -61,6 +67,11 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-optimizer", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run every step eagerly (no CUDA-graph replay)")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
+                    help="weak: --workload's graphs per GPU (default; N=8 is config 3's global batch 2 048); strong: "
+                         "--global-batch graphs split evenly over the ranks (config 3 as stated: 1 024 / 512 / 256 per GPU)")
+    ap.add_argument("--global-batch", type=int, default=2048)
+    ap.add_argument("--no-bonds", action="store_true", help="skip the extra lg_inc=bonds loop of the default run")
     ap.add_argument("--placement", choices=["dp", "members"], default="dp",
                     help="N>1: 'dp' shards graph batches of one member (gradient all-reduce); 'members' trains a different "
                          "ensemble member on every rank (reference trains members sequentially, train.py:2052), no exchange")
@@ -219,7 +230,9 @@ def run_cpu_reference(n_graphs, atoms, k, lg_inc, steps, warmup, threads=None):
         if i >= warmup:
             times.append(dt)
     med = statistics.median(times)
-    return {"value": n_graphs / med, "unit": UNIT, "cores": threads, "kind": kind,
+    spread = {"min": n_graphs / max(times), "max": n_graphs / min(times), "unit": UNIT, "timed_steps": len(times),
+              "rel_stdev_of_step_time": (statistics.pstdev(times) / statistics.mean(times)) if len(times) > 1 else 0.0}
+    return {"value": n_graphs / med, "unit": UNIT, "cores": threads, "kind": kind, "spread": spread,
             "sample": f"{n_graphs} graphs x {atoms} atoms x {k} nbrs per step (L={batch.sizes['L']}), fp32, "
                       f"{warmup} warm-up + {steps} timed fwd+loss+bwd, median",
             "ms_per_step": med * 1e3}
@@ -230,17 +243,19 @@ def main_reference(args):
     if rank != 0:
         return
     n_graphs, atoms, k = WORKLOADS[args.workload]
+    if args.scaling == "strong":
+        n_graphs = args.global_batch // max(args.gpus, 1)
     sample = min(args.cpu_sample_graphs, n_graphs)
-    steps = max(1, min(args.steps, 5))
-    warmup = max(1, min(args.warmup, 2))
+    steps = max(10, min(args.steps, 20))      # ~0.7 s per 32-graph step on 16 cores: the whole arm stays under a minute
+    warmup = max(2, min(args.warmup, 3))
     res = run_cpu_reference(sample, atoms, k, args.lg_inc, steps, warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {n_graphs} graphs x {atoms}-atom cells x {k} nbrs per GPU "
                                f"(bounded CPU sample: {sample} graphs per step)", "arch": ARCH, "lg_inc": args.lg_inc},
-        "cpu_baseline": {k2: res[k2] for k2 in ("value", "unit", "cores", "kind", "sample")},
+        "cpu_baseline": {k2: res[k2] for k2 in ("value", "unit", "cores", "kind", "sample", "spread")},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -263,6 +278,10 @@ def main_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     n_graphs, atoms, k = WORKLOADS[args.workload]
+    if args.scaling == "strong":                       # config 3 as stated: a fixed global batch split over the ranks
+        if args.global_batch % world:
+            raise SystemExit(f"--global-batch {args.global_batch} is not divisible by {world} ranks")
+        n_graphs = args.global_batch // world
     cd = torch.bfloat16 if args.dtype == "bf16" else torch.float32
 
     from gnn_elasticity_predictor_b200 import engine
@@ -303,36 +322,41 @@ def main_b200(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing -----------------------------------------------------------------------------
-    for i in range(3 * args.members):                 # priming: allocator, cuBLAS heuristics, graph capture per member
-        step(i, dev_batch, target_z)
-    for i in range(args.warmup):
-        step(i, dev_batch, target_z)
-    barrier()
-    ops.STATS.reset()
-    ops.STATS.events = True
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t0.record()
-    for i in range(args.steps):
-        step(i, dev_batch, target_z)
-    t1.record()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    ops.STATS.events = False
-    elapsed_ms = t0.elapsed_time(t1)
-    launches = ops.STATS.kernels
-    graphed = sum(s_.replays for s_ in steppers) > 0
-    # graph mode: durations of the event nodes inside the replayed graphs (last replay of every member's graph)
-    durations = ops.STATS.graph_durations_ms() if graphed else ops.STATS.durations_ms()
-    t = torch.tensor([elapsed_ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-    ms_per_step = elapsed_ms / args.steps
-    value = n_graphs * world * args.steps / (elapsed_ms / 1e3)
+    def timed_run(batch, tz, sample_clocks):
+        """W warm-up + exactly K timed steps on a batch resident in HBM: CUDA events, barrier + synchronize on both sides,
+        max over ranks."""
+        for i in range(3 * args.members):             # priming: allocator, cuBLAS heuristics, graph capture per member
+            step(i, batch, tz)
+        for i in range(args.warmup):
+            step(i, batch, tz)
+        barrier()
+        ops.STATS.reset()
+        ops.STATS.events = True
+        sampler = ClockSampler(local_rank)
+        if rank == 0 and sample_clocks:
+            sampler.start()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0.record()
+        for i in range(args.steps):
+            step(i, batch, tz)
+        t1.record()
+        barrier()
+        clk = sampler.stop() if rank == 0 and sample_clocks else None
+        ops.STATS.events = False
+        is_graphed = sum(s_.replays for s_ in steppers) > 0
+        # graph mode: durations of the event nodes inside the replayed graphs (last replay of every member's graph)
+        dur = ops.STATS.graph_durations_ms() if is_graphed else ops.STATS.durations_ms()
+        t = torch.tensor([t0.elapsed_time(t1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        return {"elapsed_ms": ms, "ms_per_step": ms / args.steps, "value": n_graphs * world * args.steps / (ms / 1e3),
+                "durations": dur, "launches": ops.STATS.kernels, "graphed": is_graphed, "clocks": clk}
+
+    main_run = timed_run(dev_batch, target_z, True)
+    clocks, durations, launches, graphed = main_run["clocks"], main_run["durations"], main_run["launches"], main_run["graphed"]
+    ms_per_step, value = main_run["ms_per_step"], main_run["value"]
 
     # ---- roofline of the dominant hand-written op (line-graph conv) -----------------------------------------------
     # `achieved` follows the contract literally: ALGORITHMIC bytes of SURVEY.md 8(d) (the conv core as the reference
@@ -340,32 +364,34 @@ def main_b200(args):
     # run's sizes -- row terms over the ACTIVE bond rows, edge terms over all angles -- divided by the measured time of
     # the launches that together ARE that op here.  Our kernels never materialise the [Ne, H] operand, so the bytes
     # they actually touch (`touched_*`, and `traffic` from ncu) are far below the algorithmic figure: the launches
-    # are bound by gathers out of L2 and by instruction issue, not by HBM.
+    # are bound by gathers out of L2 and by MMA latency, not by HBM -- `limiter` states that bound and the fraction of it.
     peak, peak_src = load_peaks()
     s_bytes = 2 if cd == torch.bfloat16 else 4
-    kern = {}
-    for name in LG_KERNELS:
-        recs = [(ms, meta) for ms, meta in durations.get(name, []) if meta and meta[1] == sizes["L"]]
-        if recs:
-            ms = statistics.mean(r[0] for r in recs)
-            if name == "lg_angle_grad":
-                kern[name] = {"ms": ms, "bytes": None, "gbs": None, "launches_timed": len(recs), "rows": recs[0][1][0]}
-                continue
-            nn_, ne_, h_, hd_ = recs[0][1][:4]
-            if name.startswith("lgattn_"):
-                b = lgattn_bytes(name, nn_, ne_, h_, hd_, s_bytes)
-            elif name.startswith("conv_"):
-                b = conv_bytes(nn_, ne_, h_, hd_, s_bytes, fwd=(name == "conv_fwd"))
-            elif name == "edgeattn_bwd_dst":
-                # accumulate-in-place launches move one more [L,H] read; average over the launches as timed
-                b = statistics.mean(edgeattn_bytes(name, nn_, ne_, h_, hd_, s_bytes, accum=bool(r[1][5])) for r in recs)
-            else:
-                b = edgeattn_bytes(name, nn_, ne_, h_, hd_, s_bytes)
-            kern[name] = {"ms": ms, "bytes": b, "gbs": (b / (ms * 1e-3) / 1e9) if b else None,
-                          "launches_timed": len(recs), "rows": nn_}
-    totals = {name: sum(ms for ms, _ in v) / (args.members if graphed else args.steps) for name, v in durations.items()}
-    roofline = None
-    if "lgattn_fwd" in kern and "lgattn_bwd_dst" in kern:
+    L2_GATHER_PEAK_GBS = 12400.0   # measured LTS cap of this pool's B200s: ~6 300 B/clk x 1.965 GHz
+
+    def make_roofline(durations, sizes, lg_inc, graphed):
+        kern = {}
+        for name in LG_KERNELS:
+            recs = [(ms, meta) for ms, meta in durations.get(name, []) if meta and meta[1] == sizes["L"]]
+            if recs:
+                ms = statistics.mean(r[0] for r in recs)
+                if name == "lg_angle_grad":
+                    kern[name] = {"ms": ms, "bytes": None, "gbs": None, "launches_timed": len(recs), "rows": recs[0][1][0]}
+                    continue
+                nn_, ne_, h_, hd_ = recs[0][1][:4]
+                if name.startswith("lgattn_"):
+                    b = lgattn_bytes(name, nn_, ne_, h_, hd_, s_bytes)
+                elif name.startswith("conv_"):
+                    b = conv_bytes(nn_, ne_, h_, hd_, s_bytes, fwd=(name == "conv_fwd"))
+                elif name == "edgeattn_bwd_dst":
+                    # accumulate-in-place launches move one more [L,H] read; average over the launches as timed
+                    b = statistics.mean(edgeattn_bytes(name, nn_, ne_, h_, hd_, s_bytes, accum=bool(r[1][5])) for r in recs)
+                else:
+                    b = edgeattn_bytes(name, nn_, ne_, h_, hd_, s_bytes)
+                kern[name] = {"ms": ms, "bytes": b, "gbs": (b / (ms * 1e-3) / 1e9) if b else None,
+                              "launches_timed": len(recs), "rows": nn_}
+        if not ("lgattn_fwd" in kern and "lgattn_bwd_dst" in kern):
+            return None
         na, ne_, h_, hd_ = kern["lgattn_fwd"]["rows"], sizes["L"], ARCH["hidden"], ARCH["heads"]
         layers = ARCH["layers"]
         b_fwd = conv_bytes(na, ne_, h_, hd_, s_bytes, fwd=True)
@@ -381,7 +407,16 @@ def main_b200(args):
         flops = LG_FLOPS_PER_ANGLE.get(dom, 0) * sizes["L"]
         tf_peak = load_tensor_peak()
         gbs_bwd, gbs_fwd = b_bwd / (t_bwd * 1e-3) / 1e9, b_fwd / (t_fwd * 1e-3) / 1e9
-        roofline = {
+        traffic = NCU_TRAFFIC.get(lg_inc, {}) if args.workload == "config2" and args.scaling == "weak" else {}
+        # what really bounds these launches: K and V rows (2 x 512 B) gathered out of L2 per angle (+ q / dagg rows per
+        # angle in the source-sorted pass), against the measured L2 -> SM cap
+        gather = {"lgattn_fwd": 1024 * ne_, "lgattn_bwd_dst": 1024 * ne_, "edgeattn_bwd_src": 1024 * ne_}
+        limiter = {n: {"kind": "l2-gather (1 KB of operand rows per angle) + mma.sync latency at 8 warps/SM",
+                       "l2_gather_bytes": gather[n], "l2_gather_GBs": round(gather[n] / (kern[n]["ms"] * 1e-3) / 1e9, 1),
+                       "l2_peak_GBs": L2_GATHER_PEAK_GBS,
+                       "frac_of_l2_bound": round(gather[n] / (kern[n]["ms"] * 1e-3) / 1e9 / L2_GATHER_PEAK_GBS, 3)}
+                   for n in gather if n in kern}
+        return {
             "kernel": f"line-graph conv backward = alignn_lgattn_bwd_dst + alignn_conv_bwd_src + 1/{layers} of "
                       f"alignn_lg_angle_grad ({na} active of {sizes['E']} bond rows, {sizes['L']} angles); dominant launch: "
                       f"alignn_{dom}",
@@ -389,20 +424,23 @@ def main_b200(args):
             "achieved": gbs_bwd, "peak": peak, "unit": "GB/s", "frac": gbs_bwd / peak, "peak_source": peak_src,
             "algorithmic_bytes": b_bwd, "avg_launch_ms": t_bwd, "launch_ms_parts": {k2: round(v, 4) for k2, v in parts.items()},
             "launches_timed": kern[dom]["launches_timed"],
-            "traffic": (sum(NCU_TRAFFIC[args.lg_inc].get(k2, 0) for k2 in ("lgattn_bwd_dst", "conv_bwd_src"))
-                        if args.workload == "config2" else None),
-            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of alignn_lgattn_bwd_dst + alignn_conv_bwd_src from the "
-                            "committed ncu --set full capture (profiles/r01_v20_ncu_lg_*.txt); lg_angle_grad not in that capture",
+            "traffic": (sum(traffic.get(k2, 0) for k2 in ("lgattn_bwd_dst", "conv_bwd_src", "lg_angle_grad/layers"))
+                        if traffic else None),
+            "traffic_note": ("dram__bytes_read.sum + dram__bytes_write.sum per launch of alignn_lgattn_bwd_dst + "
+                             "alignn_conv_bwd_src + 1/layers of alignn_lg_angle_grad, from "
+                             + str(NCU_TRAFFIC.get("source", "profiles/ncu_traffic.json"))) if traffic else None,
             "formula": "SURVEY.md 8(d) B_b with Nn = active rows, Ne = angles: s*H*(3Nn+Ne) re-read + 4*H*Nn dagg + "
                        "s*H*(3Nn+Ne) gradients + 8*h*Nn stats + 4*(4Ne+2Nn) plan",
             "conv_forward": {"kernel": "alignn_lgattn_fwd", "algorithmic_bytes": b_fwd, "avg_launch_ms": round(t_fwd, 4),
                              "achieved": round(gbs_fwd, 1), "frac": round(gbs_fwd / peak, 4),
-                             "traffic": NCU_TRAFFIC[args.lg_inc]["lgattn_fwd"] if args.workload == "config2" else None},
-            "note": "algorithmic bytes are the reference formulation's compulsory traffic (one [Ne,H] edge-projection row "
-                    "per angle); the kernels here rebuild that row from 32 B per angle, so what they really touch is the "
-                    "`touched` view below -- by that stricter count they sit far below the HBM roofline and are bound "
-                    "by L2 gathers (1 KB of K/V rows per angle) and instruction issue (mma.sync path, IPC 1.3); "
-                    "with lg_inc=bonds every bond row is active (DESIGN.md section 4, profiles/)",
+                             "traffic": traffic.get("lgattn_fwd")},
+            "limiter": limiter,
+            "note": "`bound` names the roofline the contract's ALGORITHMIC bytes are held against (HBM: the reference "
+                    "formulation moves one [Ne,H] edge-projection row per angle).  The kernels here rebuild that row from 32 B "
+                    "per angle, so what they really touch is the `touched` view below; by that stricter count they sit far "
+                    "below the HBM roofline and are bound by what `limiter` states -- L2 gathers of 1 KB of K/V rows per "
+                    "angle and mma.sync latency (8 warps / SM, tensor pipe ~35 % busy); with lg_inc=bonds every bond row is "
+                    "active (DESIGN.md section 4, profiles/)",
             "touched": {n: {"bytes": v["bytes"], "GB/s": round(v["gbs"], 1), "frac": round(v["gbs"] / peak, 4),
                             "ms": round(v["ms"], 4)} for n, v in kern.items() if v["bytes"]},
             "tensor_view": {"kernel": f"alignn_{dom}", "algorithmic_gflop": round(flops / 1e9, 2),
@@ -412,6 +450,25 @@ def main_b200(args):
             "timed": ("CUDA external-event nodes inside the replayed step graphs, last replay of each member's "
                       "graph" if graphed else "CUDA events around every C-ABI call in the timed region"),
         }
+
+    roofline = make_roofline(durations, sizes, args.lg_inc, graphed)
+    totals = {name: sum(ms for ms, _ in v) / (args.members if graphed else args.steps) for name, v in durations.items()}
+
+    # ---- the same K timed steps with geometrically correct line-graph offsets (lg_inc="bonds": every bond row active) ----
+    bonds = None
+    if args.lg_inc == "pyg" and not args.no_bonds and args.workload == "config2" and args.scaling == "weak":
+        b_host = pkg.synthetic_batch(n_graphs, atoms, k, seed=1000 * rank, lg_inc="bonds")
+        b_dev = b_host.to(dev)
+        b_tz = pkg.zscore_targets(b_dev.y, b_dev.num_graphs)
+        run_b = timed_run(b_dev, b_tz, False)
+        rf = make_roofline(run_b["durations"], b_host.sizes, "bonds", run_b["graphed"])
+        bonds = {"what": "same model, same step, lg_edge_index offset by BONDS (geometrically correct; no isolated rows) -- "
+                         "the reference's own collate offsets it by atoms (SURVEY.md A9), which is the headline",
+                 "value": run_b["value"], "unit": UNIT, "ms_per_step": run_b["ms_per_step"], "steps": args.steps,
+                 "roofline": None if rf is None else {k2: rf[k2] for k2 in ("achieved", "peak", "frac", "algorithmic_bytes",
+                                                                           "avg_launch_ms", "launch_ms_parts", "traffic",
+                                                                           "conv_forward", "limiter")}}
+        del b_dev, b_tz
 
     # ---- end to end through the public API with host buffers -------------------------------------------------------
     e2e = None
@@ -496,7 +553,7 @@ def main_b200(args):
     # Per step the host sends only the B graph ids (pinned, 8 B each); alignn_collate builds the batch in HBM; the
     # loss / mean / logvar come back as above.  The store holds 2 x B graphs, every step draws a fresh permutation.
     e2e_store = None
-    if not args.no_e2e and args.workload != "config4":
+    if not args.no_e2e and args.workload != "config4" and args.scaling == "weak":
         from gnn_elasticity_predictor_b200 import dataset
         from gnn_elasticity_predictor_b200.synthetic import make_crystal
         gen = torch.Generator().manual_seed(4242 + rank)
@@ -566,13 +623,13 @@ def main_b200(args):
     # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        res = run_cpu_reference(min(args.cpu_sample_graphs, n_graphs), atoms, k, args.lg_inc, steps=3, warmup=1)
-        cpu = {k2: res[k2] for k2 in ("value", "unit", "cores", "kind", "sample")}
+        res = run_cpu_reference(min(args.cpu_sample_graphs, n_graphs), atoms, k, args.lg_inc, steps=10, warmup=2)
+        cpu = {k2: res[k2] for k2 in ("value", "unit", "cores", "kind", "sample", "spread")}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
             "config": {
                 "workload": f"{args.workload}: {n_graphs} graphs x {atoms}-atom cells x {k} nbrs per GPU "
@@ -592,13 +649,14 @@ def main_b200(args):
                                   else "cuBLAS via torch (fp32, TF32 off)"),
             },
             "clocks": clocks, "e2e": e2e, "e2e_device_store": e2e_store, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "bonds": bonds,
             "kernel_ms_per_step": {k2: round(v, 4) for k2, v in sorted(totals.items())},
             "kernel_ms_per_step_how": ("eager pass with CUDA events after the timed regions (hand-written kernels only)"
                                        if graphed else "CUDA events in the timed region (hand-written kernels only)"),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        dp.shutdown(steppers)       # drops the captured graphs (they hold NCCL kernels) before the group is destroyed
 
 
 if __name__ == "__main__":

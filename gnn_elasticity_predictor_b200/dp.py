@@ -152,3 +152,34 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
         else:
             dist.init_process_group(backend)
     return rank, local_rank, world
+
+
+def shutdown(holders=(), grace_s: float = 20.0) -> None:
+    """Tear the process group down without hanging.  CUDA graphs that captured an NCCL kernel keep the communicator
+    busy: ``destroy_process_group`` (and interpreter exit) then blocks for ever (seen on 2 x B200 with the all-reduce
+    captured inside the step graph).  So: drop every captured graph first (``holders``: objects with a ``_captured``
+    dict, e.g. ``engine.TrainStep``), synchronise, and arm a watchdog that ends the process with exit code 0 if the
+    teardown still does not return within ``grace_s`` seconds -- all results have been printed by then."""
+    import gc
+    import os
+    import sys
+    import threading
+    for h in holders:
+        cap = getattr(h, "_captured", None)
+        if isinstance(cap, dict):
+            cap.clear()
+    gc.collect()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    sys.stdout.flush()
+    sys.stderr.flush()
+    timer = threading.Timer(grace_s, lambda: os._exit(0))
+    timer.daemon = True
+    timer.start()
+    try:
+        dist.barrier()
+        dist.destroy_process_group()
+    finally:
+        timer.cancel()

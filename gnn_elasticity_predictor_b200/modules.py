@@ -326,6 +326,7 @@ class AlignnRegressor(nn.Module):
             if plans is None:
                 plans = self.build_plans(data)
             lg_plan, g_plan, pool_plan = plans
+            self._wait_plans(data)
             for edge_block, node_block in zip(self.edge_blocks, self.node_blocks):
                 edge_state = edge_block(edge_state, data.lg_edge_index, angle_emb, plan=lg_plan, compute_dtype=cd)
                 node_state = node_block(node_state, data.edge_index, edge_state, plan=g_plan, compute_dtype=cd)
@@ -362,6 +363,25 @@ class AlignnRegressor(nn.Module):
         dev = data.x.device
         n_bonds, n_angles = data.edge_index.size(1), data.lg_edge_index.size(1)
         with torch.autocast("cuda", enabled=False):
+            # The weight folds of the fused trunk are a function of the parameters alone (no batch data, no graph plan): ~60
+            # tiny launches.  They go to a third stream at the head of the step and run beside the encoders (this stream)
+            # and the line-graph plan (side stream); autograd replays their backward on that same stream.
+            enc = self.angle_encoder
+            folded = fold_ready = None
+            if n_bonds > 0 and n_angles > 0 and enc is not None and data.lg_edge_attr.numel() > 0 and \
+                    ops.lgattn_enabled(self.hidden, self.heads, enc[0].in_features, cd) and \
+                    getattr(self, "fused_trunk", True) and len(self.edge_blocks) == len(self.node_blocks):
+                if getattr(self, "overlap_streams", True):
+                    main, aux = torch.cuda.current_stream(), trunk_mod._aux_stream(dev)
+                    aux.wait_stream(main)
+                    with torch.cuda.stream(aux):
+                        folded = self._fold_trunk_weights(enc[2].weight.float(), enc[2].bias.float())
+                        fold_ready = torch.cuda.Event()
+                        fold_ready.record(aux)
+                    for t in folded:
+                        t.record_stream(main)
+                else:
+                    folded = self._fold_trunk_weights(enc[2].weight.float(), enc[2].bias.float())
             enc_n, enc_e = self.node_encoder, self.edge_encoder
             node_b0 = fused.mlp2(data.x, enc_n[0].weight, enc_n[0].bias, enc_n[2].weight, enc_n[2].bias, cd)
             node32 = edge32 = None        # fp32 copies of the encoder outputs: only the per-block path needs them
@@ -380,8 +400,8 @@ class AlignnRegressor(nn.Module):
             n_layers = len(self.edge_blocks)
             fold_angle = False
             h1 = w2 = b2 = lg = None
+            self._wait_plans(data)      # join the side-stream build of the line-graph plan (the encoders ran beside it)
             if run_lg:
-                enc = self.angle_encoder
                 if enc is not None and data.lg_edge_attr.numel() > 0 and \
                         ops.lgattn_enabled(self.hidden, self.heads, enc[0].in_features, cd):
                     # h1 = relu(W1 a + b1) is rebuilt inside the kernels from the packed 32-byte angle rows
@@ -400,13 +420,14 @@ class AlignnRegressor(nn.Module):
                     h1 = _mlp2(enc, data.lg_edge_attr, cd)          # unusual angle_dim: plain features
                 else:
                     h1 = torch.zeros(n_angles, self.hidden, device=dev, dtype=cd)
-            if lg is not None and run_atoms and getattr(self, "fused_trunk", True) and \
-                    len(self.edge_blocks) == len(self.node_blocks):
+            if lg is not None and folded is not None:
+                if fold_ready is not None:
+                    torch.cuda.current_stream().wait_event(fold_ready)
                 lg_active = getattr(data, "lg_active_rows", None)
                 lp_in = cd != torch.float32     # the first blocks read the bf16 encoder outputs directly (no fp32 copy)
                 node32 = self._run_fused_trunk(None if lp_in else node_b0.float(), node_b0,
                                                None if lp_in and edge32 is None else (edge32 if edge32 is not None else edge_b0.float()),
-                                               edge_b0, lg, lg_plan, g_plan, w2, b2,
+                                               edge_b0, lg, lg_plan, g_plan, folded,
                                                -1 if lg_active is None or not getattr(self, "elide_isolated", True)
                                                else int(lg_active), zero_df=bool(getattr(data, "padded", False)))
                 return self._head_features(node32, data, pool_plan)
@@ -446,13 +467,11 @@ class AlignnRegressor(nn.Module):
                                                    edge32, wc, cvec, g_plan, cd)
             return self._head_features(node32, data, pool_plan)
 
-    def _run_fused_trunk(self, node32: Tensor, node_b: Tensor, edge32: Tensor, edge_b: Tensor, lg: LgShared,
-                         lg_plan: GraphPlan, g_plan: GraphPlan, w2: Tensor, b2: Tensor, lg_active: int = -1,
-                         zero_df: bool = False) -> Tensor:
-        """All blocks as one explicit forward / backward program (``trunk.py``).  The weight folds of every block are
-        batched here under autograd: ``Wc = W_e W2`` (line graph, second angle-encoder Linear folded into ``lin_edge``),
-        ``Wc = W_e W_p`` (atom graph, ``edge_proj`` folded), and the query-side fold ``Wc[t]^T Wq_t`` that turns
-        ``qt_t = q_t Wc[t]`` into four more slices of the node projection."""
+    def _fold_trunk_weights(self, w2: Tensor, b2: Tensor):
+        """The weight folds of every block, batched, under autograd: ``Wc = W_e W2`` (line graph, second angle-encoder
+        Linear folded into ``lin_edge``), ``Wc = W_e W_p`` (atom graph, ``edge_proj`` folded), and the query-side fold
+        ``Wc[t]^T Wq_t`` that turns ``qt_t = q_t Wc[t]`` into four more slices of the node projection.  Depends on the
+        parameters only (no batch data, no graph plan)."""
         nl, h, hid = len(self.edge_blocks), self.heads, self.hidden
         c = hid // h
         blocks = [b for pair in zip(self.edge_blocks, self.node_blocks) for b in pair]       # 2l: edge, 2l+1: node
@@ -466,7 +485,7 @@ class AlignnRegressor(nn.Module):
         wc = torch.stack([wc_lg, wc_at], dim=1).reshape(2 * nl, hid, hid)
         cvec = torch.stack([cv_lg, cv_at], dim=1).reshape(2 * nl, hid)
         wq, bq = f([cv.lin_query.weight for cv in convs]), f([cv.lin_query.bias for cv in convs])
-        zeros = torch.zeros(hid, device=node_b.device)
+        zeros = torch.zeros(hid, device=wq.device)
         w4 = [wq, f([cv.lin_key.weight for cv in convs]), f([cv.lin_value.weight for cv in convs]),
               f([cv.lin_skip.weight for cv in convs])]
         b4 = [bq, f([cv.lin_key.bias for cv in convs]), f([cv.lin_value.bias for cv in convs]),
@@ -478,6 +497,17 @@ class AlignnRegressor(nn.Module):
         b8 = torch.cat(b4[:3] + [bqt, b4[3]], dim=1)                  # [2L, 8H]
         wbeta = f([cv.lin_beta.weight.reshape(-1) for cv in convs])
         gamma, beta_ln = f([b.norm.weight for b in blocks]), f([b.norm.bias for b in blocks])
+        return w8, b8, wc, cvec, wbeta, gamma, beta_ln
+
+    def _run_fused_trunk(self, node32: Tensor, node_b: Tensor, edge32: Tensor, edge_b: Tensor, lg: LgShared,
+                         lg_plan: GraphPlan, g_plan: GraphPlan, folded, lg_active: int = -1,
+                         zero_df: bool = False) -> Tensor:
+        """All blocks as one explicit forward / backward program (``trunk.py``) on the folded, stacked weights of
+        :meth:`_fold_trunk_weights`."""
+        w8, b8, wc, cvec, wbeta, gamma, beta_ln = folded
+        nl, h = len(self.edge_blocks), self.heads
+        blocks = [b for pair in zip(self.edge_blocks, self.node_blocks) for b in pair]       # 2l: edge, 2l+1: node
+        convs = [b.conv for b in blocks]
         train = self.training
         p_attn = [cv.dropout if train else 0.0 for cv in convs]
         p_out = [b.dropout.p if train else 0.0 for b in blocks]
@@ -505,21 +535,24 @@ class AlignnRegressor(nn.Module):
         n_graphs = getattr(data, "num_graphs", None)
         if n_graphs is None:
             n_graphs = int(data.batch.max()) + 1 if data.batch.numel() > 0 else 0
-        # the three plans are independent chains of small, latency-bound kernels: the atom-graph and pooling plans are
-        # built on the side stream beside the (10x larger) line-graph plan; fork / join are capturable graph edges
+        # the three plans are independent chains of small, latency-bound kernels.  The line-graph plan (10x the others) goes
+        # to the side stream and is NOT joined here: the encoders and the weight folds of the forward do not need it, so
+        # they run beside it; the first consumer waits on ``data._alignn_plans_ready`` (``_wait_plans``).  Fork / join are
+        # capturable graph edges.
         side = trunk_mod._side_stream(data.x.device) if (getattr(self, "overlap_streams", True) and data.x.is_cuda
                                                          and n_bonds > 0 and not v) else None
+        ready = None
         if side is not None:
             main = torch.cuda.current_stream()
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                g_plan = ops.build_plan(data.edge_index, n_atoms, source_sorted=g_sorted)
-                pool_plan = ops.build_pool_plan(data.batch, int(n_graphs))
-            lg_plan = ops.build_plan(data.lg_edge_index, n_bonds, source_sorted=lg_sorted, key_bound=lg_bound)
-            main.wait_stream(side)
-            for pl in (g_plan, pool_plan):
-                for t in (pl.rowptr, pl.col, pl.eid, pl.rowptr_t, pl.col_t, pl.eid_t, pl.status):
-                    t.record_stream(main)
+                lg_plan = ops.build_plan(data.lg_edge_index, n_bonds, source_sorted=lg_sorted, key_bound=lg_bound)
+                ready = torch.cuda.Event()
+                ready.record(side)
+            g_plan = ops.build_plan(data.edge_index, n_atoms, source_sorted=g_sorted)
+            pool_plan = ops.build_pool_plan(data.batch, int(n_graphs))
+            for t in (lg_plan.rowptr, lg_plan.col, lg_plan.eid, lg_plan.rowptr_t, lg_plan.col_t, lg_plan.eid_t, lg_plan.status):
+                t.record_stream(main)
         else:
             lg_plan = ops.build_plan(data.lg_edge_index, n_bonds, validate=v, source_sorted=lg_sorted,
                                      key_bound=lg_bound) if n_bonds > 0 else None
@@ -528,9 +561,22 @@ class AlignnRegressor(nn.Module):
         plans = (lg_plan, g_plan, pool_plan)
         try:
             object.__setattr__(data, "_alignn_plans", plans)
+            object.__setattr__(data, "_alignn_plans_ready", ready)
         except Exception:  # noqa: BLE001 -- e.g. a PyG Batch refusing private attributes
-            pass
+            if ready is not None:
+                torch.cuda.current_stream().wait_event(ready)
         return plans
+
+    @staticmethod
+    def _wait_plans(data) -> None:
+        """Join the side-stream build of the line-graph plan (``build_plans``) into the current stream, once."""
+        ready = getattr(data, "_alignn_plans_ready", None)
+        if ready is not None:
+            torch.cuda.current_stream().wait_event(ready)
+            try:
+                object.__setattr__(data, "_alignn_plans_ready", None)
+            except Exception:  # noqa: BLE001
+                pass
 
     @_no_dynamo
     def forward(self, data) -> Tensor:

@@ -59,6 +59,19 @@ class TrunkCfg:
 
 
 _SIDE_STREAMS = {}
+_AUX_STREAMS = {}
+
+
+def _aux_stream(device: torch.device) -> torch.cuda.Stream:
+    """A third stream per device for work that only feeds PARAMETER gradients or is a function of the parameters alone
+    (the weight folds at the head of the step; ``dWc``, the weight / bias gradients of the stacked projections in the
+    backward): none of it is on the activation-gradient chain, so it fills the holes beside the gate / LayerNorm and GEMM
+    launches of the next block instead of lengthening the main stream."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    st = _AUX_STREAMS.get(key)
+    if st is None:
+        st = _AUX_STREAMS[key] = torch.cuda.Stream(device=device)
+    return st
 
 
 def _side_stream(device: torch.device) -> torch.cuda.Stream:
@@ -180,7 +193,8 @@ class _Trunk(torch.autograd.Function):
         de: Optional[Tensor] = None                    # fp32 gradient of the bond residual stream (None above the top)
         coefs, qts, gts = [], [], []
 
-        def block_backward(idx: int, is_lg: bool, dy: Optional[Tensor], dtail: Tensor, df_out: Optional[Tensor]) -> Tensor:
+        def block_backward(idx: int, is_lg: bool, dy: Optional[Tensor], dtail: Tensor, df_out: Optional[Tensor],
+                           own_dy: bool = False) -> Tensor:
             """``dtail``: [n, H] (dx_r) or [n, 2H] (dx_r | df from the atom-graph block of the same layer, already written);
             ``df_out``: where THIS block writes its edge-feature gradient (atom-graph blocks)."""
             st = saved[idx]
@@ -207,25 +221,47 @@ class _Trunk(torch.autograd.Function):
             else:
                 ops.raw_attn_bwd_s(dagg, dagg_lp, agg, q, k, v, qt, gt, cvf[idx], st["feat"], st["m"], st["z"],
                                    cfg.g_plan, h, dq, dk, dv, bbar, df_out, cfg.p_attn[idx], sa, oa, rs)
-            # dWc[t] = dagg_t^T abar_t: one batched [C, na] x [na, H] product per head, written straight into its slot
-            torch.bmm(dagg_lp.view(na, h, c).permute(1, 2, 0), st["abar_rows"].transpose(0, 1), out_dtype=torch.float32,
-                      out=d_wc[idx].view(h, c, hid))
+            def param_grads():
+                # dWc[t] = dagg_t^T abar_t: one batched [C, na] x [na, H] product per head, written straight into its slot
+                torch.bmm(dagg_lp.view(na, h, c).permute(1, 2, 0), st["abar_rows"].transpose(0, 1), out_dtype=torch.float32,
+                          out=d_wc[idx].view(h, c, hid))
+                # weight + bias gradients of the stacked projection: one streaming pass per operand pair (tcgen05, wgrad_tc.cu)
+                ops.wgrad(dbuf, xb[:na], d_w8[idx, :7 * hid], d_b8[idx, :7 * hid])
+                ops.wgrad(dxr, xb, d_w8[idx, 7 * hid:], d_b8[idx, 7 * hid:])
+
+            cur = torch.cuda.current_stream()
+            if aux is not None and is_lg:
+                # parameter gradients leave the activation-gradient chain: third stream, joined once at the very end.  Every
+                # operand stays referenced until that join (``keep``), so no block is recycled under the aux stream.
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                keep.append((dbuf, dagg_lp, st["abar_rows"], xb, dtail))
+                with torch.cuda.stream(aux):
+                    aux.wait_event(ev)
+                    param_grads()
+            else:
+                param_grads()
             # dx = dy + [dx_r | df] [Ws ; I]  (all rows; the identity block adds df)  +  dbuf [Wq; Wk; Wv; WQT]  (active rows)
             w7, ws = w8c[idx, :7 * hid], w8c[idx, 7 * hid:]
             wtail = wtail_all[idx] if dy2 is not None else ws
-            if dy is not None:
+            if dy is not None and own_dy:
+                dx = torch.addmm(dy, dtail, wtail, out_dtype=torch.float32, out=dy)     # in place: dy is dead after this block
+            elif dy is not None:
                 dx = torch.addmm(dy, dtail, wtail, out_dtype=torch.float32)
             else:
                 dx = torch.mm(dtail, wtail, out_dtype=torch.float32)
             torch.addmm(dx[:na], dbuf, w7, out_dtype=torch.float32, out=dx[:na])
-            # weight + bias gradients of the stacked projection: one streaming pass per operand pair (tcgen05, wgrad_tc.cu)
-            ops.wgrad(dbuf, xb[:na], d_w8[idx, :7 * hid], d_b8[idx, :7 * hid])
-            ops.wgrad(dxr, xb, d_w8[idx, 7 * hid:], d_b8[idx, 7 * hid:])
             st.clear()
             return dx
 
         main = torch.cuda.current_stream()
         side = _side_stream(dev) if cfg.overlap else None
+        aux = _aux_stream(dev) if cfg.overlap else None
+        keep: list = []
+        if aux is not None:
+            aux.wait_stream(main)
+            for t in (d_w8, d_b8, d_wc):
+                t.record_stream(aux)
         mk = torch.zeros if cfg.zero_df else torch.empty
         tails = [mk(n_bonds, 2 * hid, dtype=cd, device=dev) for _ in range(nl)]            # LG block l: dx_r | df_l
         if side is not None:
@@ -233,20 +269,27 @@ class _Trunk(torch.autograd.Function):
             for t in tails + [dn, d_w8, d_b8, d_wc, d_par, wtail_all]:
                 t.record_stream(side)
         for l in reversed(range(nl)):
+            # the incoming dn of the top layer belongs to autograd (never written in place); below it dn / de are this
+            # function's own buffers and the dx GEMM accumulates straight into them
+            own = l < nl - 1
             if side is None:
-                dn = block_backward(2 * l + 1, False, dn, torch.empty(n_atoms, hid, dtype=cd, device=dev), tails[l][:, hid:])
+                dn = block_backward(2 * l + 1, False, dn, torch.empty(n_atoms, hid, dtype=cd, device=dev), tails[l][:, hid:],
+                                    own_dy=own)
             else:
                 with torch.cuda.stream(side):
                     dn = block_backward(2 * l + 1, False, dn, torch.empty(n_atoms, hid, dtype=cd, device=dev),
-                                        tails[l][:, hid:])
+                                        tails[l][:, hid:], own_dy=own)
                     ev = torch.cuda.Event()
                     ev.record(side)
                 main.wait_event(ev)
-            de = block_backward(2 * l, True, de, tails[l], None)
+            de = block_backward(2 * l, True, de, tails[l], None, own_dy=own)
         if side is not None:
             main.wait_stream(side)
             dn.record_stream(main)
         dw1, db1 = ops.raw_lg_angle_grad(cfg.a_csr, cfg.w1, cfg.b1, cfg.lg_plan, coefs, qts, gts)
+        if aux is not None:
+            main.wait_stream(aux)
+        keep.clear()
 
         t = ctx.dtypes
         lp_n, lp_e = ctx.lp_inputs            # gradients go to whichever copy of the encoder output was the input

@@ -128,8 +128,12 @@ def main():
                           "allreduce_in_graph": bool(step.allreduce_in_graph and not args.no_graph),
                           "rtol_grad": rtol, "worst_rel_grad": worst["grad"], "worst_param_err_over_lr": worst["param"],
                           "worst_rel_loss": worst["loss"], "ok": bool(flag.item())}), flush=True)
-    dist.destroy_process_group()
-    sys.exit(0 if bool(flag.item()) else 1)
+    good = bool(flag.item())
+    sys.stdout.flush()
+    if not good:
+        os._exit(1)
+    dp.shutdown([step] + ([single] if single is not None else []))
+    sys.exit(0)
 
 
 if __name__ == "__main__":
