@@ -115,13 +115,17 @@ SIGNATURES = {
     "alignn_wgrad_supported": (c_int, [c_int, c_int]),
     "alignn_wgrad_partial_floats": (c_int64, [c_int64, c_int]),
     "alignn_wgrad": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "alignn_proj_tc_supported": (c_int, [c_int, c_int, c_int]),
+    "alignn_proj_tc": (c_int, [_P, c_int64, _P, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, c_int, _P]),
+    "alignn_proj_tc2": (c_int, [_P, c_int64, _P, c_int64, c_int64, _P, _P, c_int64, c_int, c_int, _P, c_int64, c_int, c_int,
+                                c_int64, c_int64, c_int, c_int, _P]),
     "alignn_gaussian_nll": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_float, c_float, _P, _P, _P, _P]),
     "alignn_ensemble_post": (c_int, [_P, _P, c_int, c_int64, c_int, c_float, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "alignn_segment_mean_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P]),
     "alignn_segment_mean_bwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P]),
 }
 
-ABI_VERSION = 20
+ABI_VERSION = 21
 F32, BF16 = 0, 1
 
 

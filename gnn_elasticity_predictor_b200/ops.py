@@ -865,6 +865,52 @@ def wgrad(a: Tensor, b: Tensor, w_out: Tensor, b_out: Optional[Tensor] = None) -
     _lib.check(rc, "alignn_wgrad")
 
 
+PROJ_TC = os.environ.get("ALIGNN_PROJ_TC", "1") == "1"       # tcgen05 + TMA node projections (csrc/proj_tc.cu) vs cuBLAS addmm
+
+
+def linear_lp(x: Tensor, w: Tensor, bias: Optional[Tensor] = None) -> Tensor:
+    """``x w^T + bias`` for the bf16 node projections (``nn.Linear`` of the reference's TransformerConv on the node state):
+    the hand-written tcgen05 / TMA GEMM (``alignn_proj_tc``) when the shape is one it takes (K = 256, N a multiple of 128,
+    bf16, unit column strides, 16-byte aligned rows), cuBLAS (``torch.addmm``) otherwise."""
+    lib = _lib.load()
+    m, k = x.shape
+    n = int(w.size(0))
+    ok = (PROJ_TC and x.is_cuda and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and m > 0
+          and (bias is None or (bias.dtype == torch.bfloat16 and bias.is_contiguous() and bias.data_ptr() % 16 == 0))
+          and bool(lib.alignn_proj_tc_supported(k, n, BF16_CODE)) and x.stride(1) == 1 and w.stride(1) == 1
+          and _ld(x) % 8 == 0 and _ld(w) % 8 == 0 and x.data_ptr() % 16 == 0 and w.data_ptr() % 16 == 0)
+    if not ok:
+        return torch.addmm(bias, x, w.t()) if bias is not None else torch.mm(x, w.t())
+    out = torch.empty(m, n, dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device), _Launch("proj_tc", 1, (m, n, k)):
+        rc = lib.alignn_proj_tc(_p(x), _ld(x), _p(w), _ld(w), _p(bias), _p(out), n, m, n, k, BF16_CODE, _stream())
+    _lib.check(rc, "alignn_proj_tc")
+    return out
+
+
+def block_projections(x: Tensor, w8: Tensor, b8: Tensor, n_active: int) -> Tuple[Tensor, Tensor]:
+    """The two node projections of one conv block from ONE pass over ``x [n, H]`` (bf16): ``x_r = x Ws^T + bs`` for every
+    row and ``q | k | v | qt_0..3 = x[:n_active] W7^T + b7`` for the active prefix, with ``w8 = [W7; Ws]`` (``[8H, H]``) and
+    ``b8`` stacked the same way (``trunk.py``).  One launch of the tcgen05 / TMA GEMM (``alignn_proj_tc2``); two cuBLAS
+    GEMMs when the shape is not one it takes.  Returns ``(x_r [n, H], proj [n_active, 7H])``."""
+    lib = _lib.load()
+    n, hid = x.shape
+    ok = (PROJ_TC and x.is_cuda and x.dtype == torch.bfloat16 and w8.dtype == torch.bfloat16 and b8.dtype == torch.bfloat16
+          and hid == 256 and tuple(w8.shape) == (8 * hid, hid) and w8.is_contiguous() and b8.is_contiguous() and n > 0
+          and x.stride(1) == 1 and _ld(x) % 8 == 0 and x.data_ptr() % 16 == 0 and w8.data_ptr() % 16 == 0
+          and b8.data_ptr() % 16 == 0)
+    if not ok:
+        w7, b7, ws, bs = w8[:7 * hid], b8[:7 * hid], w8[7 * hid:], b8[7 * hid:]
+        return torch.addmm(bs, x, ws.t()), torch.addmm(b7, x[:n_active], w7.t())
+    xr = torch.empty(n, hid, dtype=torch.bfloat16, device=x.device)
+    proj = torch.empty(n_active, 7 * hid, dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device), _Launch("proj_tc", 1, (n, n_active, hid)):
+        rc = lib.alignn_proj_tc2(_p(x), _ld(x), _p(w8), hid, 8 * hid, _p(b8), _p(xr), hid, hid, 7 * hid,
+                                 _p(proj), 7 * hid, 7 * hid if n_active > 0 else 0, 0, n, n_active, hid, BF16_CODE, _stream())
+    _lib.check(rc, "alignn_proj_tc2")
+    return xr, proj
+
+
 def colsum(x: Tensor, out: Optional[Tensor] = None) -> Tensor:
     """fp32 column sums of a 2-D tensor with unit column stride (deterministic hand-written reduction); ``out``: optional
     contiguous fp32 ``[width]`` destination."""

@@ -94,9 +94,7 @@ def _block_forward(idx: int, is_lg: bool, x32: Tensor, xb: Tensor, feat: Optiona
     na = cfg.lg_active if (is_lg and 0 <= cfg.lg_active < n) else n            # active prefix
     # q | k | v | qt_0..3 over the ACTIVE prefix ([na, 7H]) and x_r over all rows ([n, H]): two contiguous GEMM outputs
     # with the same shapes per row whether or not rows are elided, so elision changes no rounding anywhere.
-    w7, b7, ws, bs = w8c[:7 * hid], b8c[:7 * hid], w8c[7 * hid:], b8c[7 * hid:]
-    xr = torch.addmm(bs, xb, ws.t())                                          # [n, H]
-    proj = torch.addmm(b7, xb[:na], w7.t())                                   # [na, 7H]
+    xr, proj = ops.block_projections(xb, w8c, b8c, na)       # [n, H], [na, 7H]: ONE tcgen05 + TMA launch (csrc/proj_tc.cu)
     q, k, v = (proj[:, i * hid:(i + 1) * hid] for i in range(3))
     qt = proj[:, 3 * hid:].unflatten(1, (h, hid)).transpose(0, 1)             # [h, na, H] view, row stride 7H
     abar_rows = torch.empty(na, h, hid, dtype=xb.dtype, device=xb.device)     # row-interleaved: [na, 4H] for the dWc GEMM

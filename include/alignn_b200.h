@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define ALIGNN_ABI_VERSION 20
+#define ALIGNN_ABI_VERSION 21
 
 #define ALIGNN_F32 0
 #define ALIGNN_BF16 1
@@ -487,6 +487,27 @@ int alignn_wgrad_supported(int n, int dtype);
 int64_t alignn_wgrad_partial_floats(int64_t K, int M);
 int alignn_wgrad(const void *a, int64_t lda, const void *b, int64_t ldb, int64_t K, int M, int N, int dtype,
                  float *partials, float *c, float *colsum, void *stream);
+
+/* ---- per-node projection GEMM (tcgen05 / TMEM, TMA-fed) -------------------------------------------------------------
+ * Replaces the `nn.Linear`s PyG TransformerConv applies to the node state (reference scripts/train.py:308, 326:
+ * lin_query / lin_key / lin_value / lin_skip, called from TransformerConv.forward at train.py:315, 334), stacked and
+ * folded as gnn_elasticity_predictor_b200/fused.py describes:
+ *     C[M, N] = A[M, K] . W[N, K]^T + bias[N]      A, W, bias, C bf16 (row strides lda / ldw / ldc elements), fp32 accumulate
+ * K = 256 and N a multiple of 256 (alignn_proj_tc_supported).  csrc/proj_tc.cu: persistent CTAs, the [256, 256] weight block
+ * resident in shared memory, [128 x 64] boxes of A through a four-stage TMA ring (128-byte swizzle), 16 tcgen05.mma
+ * 128x256x16 per tile, two TMEM accumulators so the epilogue (bias, bf16, swizzled staging, TMA store) overlaps the next
+ * tile's MMAs.
+ * bias may be NULL.  Never allocates, never synchronises. */
+int alignn_proj_tc_supported(int K, int N, int dtype);
+int alignn_proj_tc(const void *a, int64_t lda, const void *w, int64_t ldw, const void *bias, void *c, int64_t ldc,
+                   int64_t M, int N, int K, int dtype, void *stream);
+/* The same pass over A for TWO column groups of one stacked weight W [w_rows, K]: C0[M, n_full] from W rows
+ * [w_row_full, +n_full) over all M rows, C1[M_pre, n_pre] from W rows [w_row_pre, +n_pre) over the first M_pre rows; bias is
+ * indexed like the rows of W.  What one conv block needs: x_r for every row + q | k | v | qt_0..3 for the rows that have
+ * line-graph neighbours (trunk.py). */
+int alignn_proj_tc2(const void *a, int64_t lda, const void *w, int64_t ldw, int64_t w_rows, const void *bias,
+                    void *c0, int64_t ldc0, int n_full, int w_row_full, void *c1, int64_t ldc1, int n_pre, int w_row_pre,
+                    int64_t M, int64_t M_pre, int K, int dtype, void *stream);
 
 #ifdef __cplusplus
 }

@@ -407,3 +407,52 @@ def test_wgrad_tcgen05_matches_fp64(k, m, strided, monkeypatch):
     w3, s3 = torch.empty_like(w1), torch.empty_like(s1)
     ops.wgrad(a, b, w3, s3)
     assert rel_err(w3, want_w) < 5e-5 and rel_err(s3, want_s) < 2e-5          # cuBLAS split-K: looser than the UMMA kernel
+
+
+@pytest.mark.parametrize("m,n,ld,with_bias", [(98304, 256, 256, True), (8544, 1792, 256, True), (1, 256, 256, False),
+                                               (129, 256, 2048, True), (1000, 512, 512, False)])
+def test_proj_tc_matches_fp32_reference(m, n, ld, with_bias):
+    """csrc/proj_tc.cu (tcgen05 + TMA node projection, ``nn.Linear`` of TransformerConv: reference train.py:308, 326) against
+    a plain PyTorch fp32 GEMM of the same bf16 operands: fp32 accumulation, one rounding to bf16 at the end -> within one
+    bf16 ulp (2^-8 relative) of the fp32 result; rows past the last full 128-row tile, strided A rows, no bias."""
+    from gnn_elasticity_predictor_b200 import _lib
+    lib = _lib.load()
+    assert lib.alignn_proj_tc_supported(256, n, ops.BF16_CODE)
+    g = torch.Generator(device=DEV).manual_seed(m + n)
+    big = (torch.randn(m, ld, device=DEV, generator=g) * 0.7).to(torch.bfloat16)
+    x = big[:, ld - 256:] if ld > 256 else big                   # strided rows when ld > 256
+    w = (torch.randn(n, 256, device=DEV, generator=g) * 0.06).to(torch.bfloat16)
+    b = (torch.randn(n, device=DEV, generator=g) * 0.5).to(torch.bfloat16) if with_bias else None
+    k0 = ops.STATS.kernels
+    out = ops.linear_lp(x, w, b)
+    assert ops.STATS.kernels == k0 + 1, "the tcgen05 kernel must be the one that ran"
+    want = x.float() @ w.float().t()
+    if b is not None:
+        want = want + b.float()
+    err = (out.float() - want).abs()
+    bound = want.abs() * 2.0 ** -8 + 1e-6
+    assert bool((err <= bound).all()), float((err / bound).max())
+    # and the same numbers as the library GEMM it replaces, up to the last bf16 bit of rare ties
+    lib_out = torch.addmm(b, x, w.t()) if b is not None else torch.mm(x, w.t())
+    assert float((out.float() - lib_out.float()).abs().max()) <= float(want.abs().max()) * 2.0 ** -7
+
+
+@pytest.mark.parametrize("n,na", [(98304, 8544), (8192, 8192), (300, 0), (1000, 129)])
+def test_block_projections_one_launch_matches_two_library_gemms(n, na):
+    """``ops.block_projections``: x_r over all rows + q|k|v|qt over the active prefix from one tcgen05 launch
+    (``alignn_proj_tc2``) against the two ``torch.addmm`` calls it replaces and an fp32 reference."""
+    g = torch.Generator(device=DEV).manual_seed(n + na)
+    x = (torch.randn(n, 256, device=DEV, generator=g) * 0.7).to(torch.bfloat16)
+    w8 = (torch.randn(2048, 256, device=DEV, generator=g) * 0.06).to(torch.bfloat16)
+    b8 = (torch.randn(2048, device=DEV, generator=g) * 0.5).to(torch.bfloat16)
+    k0 = ops.STATS.kernels
+    xr, proj = ops.block_projections(x, w8, b8, na)
+    assert ops.STATS.kernels == k0 + 1
+    assert xr.shape == (n, 256) and proj.shape == (na, 1792)
+    for got, rows, w, b in ((xr, x, w8[1792:], b8[1792:]), (proj, x[:na], w8[:1792], b8[:1792])):
+        if rows.size(0) == 0:
+            continue
+        want = rows.float() @ w.float().t() + b.float()
+        err = (got.float() - want).abs()
+        bound = want.abs() * 2.0 ** -8 + 1e-6
+        assert bool((err <= bound).all()), float((err / bound).max())
