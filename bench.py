@@ -454,6 +454,29 @@ def main_b200(args):
     roofline = make_roofline(durations, sizes, args.lg_inc, graphed)
     totals = {name: sum(ms for ms, _ in v) / (args.members if graphed else args.steps) for name, v in durations.items()}
 
+    # ---- the same kernels timed ALONE: the step graphs re-captured on ONE stream (no concurrent branch shares the SMs) -----
+    # In the timed region above the atom-graph chain, the parameter-gradient GEMMs and the plan build run on parallel graph
+    # branches, so a line-graph launch's event-to-event time includes the CTAs it waited for.  `roofline.frac` stays the
+    # in-step figure (the contract's timed region); `roofline.alone` is the per-kernel figure, with the serial step time.
+    if roofline is not None and graphed and args.workload == "config2":
+        for m_ in members:
+            m_.base.overlap_streams = False
+        saved_caps = [(s_._captured, s_._seen) for s_ in steppers]
+        for s_ in steppers:
+            s_._captured, s_._seen = {}, {}
+        run_s = timed_run(dev_batch, target_z, False)
+        rf_s = make_roofline(run_s["durations"], sizes, args.lg_inc, run_s["graphed"])
+        if rf_s is not None:
+            roofline["alone"] = {"how": "same step, graphs re-captured with every kernel on one stream (no overlap); "
+                                        "CUDA external-event nodes inside the replayed graphs",
+                                 "ms_per_step_serial": run_s["ms_per_step"], "achieved": rf_s["achieved"], "frac": rf_s["frac"],
+                                 "avg_launch_ms": rf_s["avg_launch_ms"], "launch_ms_parts": rf_s["launch_ms_parts"],
+                                 "conv_forward": {k2: rf_s["conv_forward"][k2] for k2 in ("avg_launch_ms", "achieved", "frac")}}
+        for m_ in members:
+            m_.base.overlap_streams = True
+        for s_, (c_, sn_) in zip(steppers, saved_caps):
+            s_._captured, s_._seen = c_, sn_
+
     # ---- the same K timed steps with geometrically correct line-graph offsets (lg_inc="bonds": every bond row active) ----
     bonds = None
     if args.lg_inc == "pyg" and not args.no_bonds and args.workload == "config2" and args.scaling == "weak":
@@ -644,8 +667,9 @@ def main_b200(args):
                         + ("; whole step replayed as one CUDA graph per member" if graphed else "; eager launches"),
                 "l2": "inputs larger than L2: every step streams > 1 GB of per-block activations / gradients (98 304 x 256 bond states x 8 blocks, fwd + bwd) through HBM, far above the 126 MB L2; no explicit flush",
                 "projections": "per-NODE projections only (the per-edge E x H x H GEMMs are eliminated algebraically); "
-                               + ("cuBLAS via torch (bf16), except the K = n_bonds weight + bias gradient of the skip projection: "
-                                  "hand-written tcgen05 + TMA kernel (csrc/wgrad_tc.cu)" if cd == torch.bfloat16
+                               + ("forward: x_r + q|k|v|qt of every block from one hand-written tcgen05 + TMA launch "
+                                  "(csrc/proj_tc.cu); weight + bias gradients: hand-written tcgen05 + TMA (csrc/wgrad_tc.cu); "
+                                  "dx / dWc / folded-weight products: cuBLAS via torch (bf16)" if cd == torch.bfloat16
                                   else "cuBLAS via torch (fp32, TF32 off)"),
             },
             "clocks": clocks, "e2e": e2e, "e2e_device_store": e2e_store, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,

@@ -104,14 +104,24 @@ edgeattn_mma_fwd_kernel(const MmFwdParams P) {
             const int n = prod.count();
             const int o = prod.pos + min(lane & 15, n - 1) - wbase;
             const int j = wcol.get(o), id = weid.get(o);
-            const uint32_t dst = base_u32 + (uint32_t)s * 3 * MM_TILE + lane * 16;
+            // one warp instruction copies a 128-byte piece of FOUR rows (lane = 8 * row-in-group + 16-byte slot): the row
+            // addresses are formed once per group of four rows, the four pieces of a row are immediate offsets
+            const int sub = lane >> 3, slot = (lane & 7) * 8;
+            const uint32_t dst = base_u32 + (uint32_t)s * 3 * MM_TILE + (uint32_t)sub * MM_ROWB + (lane & 7) * 16;
 #pragma unroll
-            for (int u = 0; u < MM_E; ++u) {
-                if (u < n) {   // warp-uniform
-                    const int ju = __shfl_sync(FULL, j, u), idu = __shfl_sync(FULL, id, u);
-                    cp_async16(dst + u * MM_ROWB, P.k + (int64_t)ju * P.ldk + lane * 8);
-                    cp_async16(dst + MM_TILE + u * MM_ROWB, P.v + (int64_t)ju * P.ldv + lane * 8);
-                    cp_async16(dst + 2 * MM_TILE + u * MM_ROWB, P.feat + (int64_t)idu * MM_HID + lane * 8);
+            for (int grp = 0; grp < MM_E / 4; ++grp) {
+                const int u = 4 * grp + sub;
+                const int ju = __shfl_sync(FULL, j, u), idu = __shfl_sync(FULL, id, u);
+                if (u < n) {
+                    const __nv_bfloat16 *pk = P.k + (int64_t)ju * P.ldk + slot, *pv = P.v + (int64_t)ju * P.ldv + slot;
+                    const __nv_bfloat16 *pf = P.feat + (int64_t)idu * MM_HID + slot;
+                    const uint32_t d = dst + (uint32_t)(4 * grp) * MM_ROWB;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        cp_async16(d + i * 128, pk + i * 64);
+                        cp_async16(d + MM_TILE + i * 128, pv + i * 64);
+                        cp_async16(d + 2 * MM_TILE + i * 128, pf + i * 64);
+                    }
                 }
             }
             prod.advance(P.rowptr);
@@ -382,14 +392,24 @@ edgeattn_mma_bwd_kernel(const MmBwdParams P) {
             const int o = prod.pos + min(lane & 15, n - 1) - wbase;
             const int j = wcol.get(o), id = weid.get(o);
             if (lane < 16) eid_stash[s * 16 + lane] = id;
-            const uint32_t dst = base_u32 + (uint32_t)s * 3 * MM_TILE + lane * 16;
+            // one warp instruction copies a 128-byte piece of FOUR rows (lane = 8 * row-in-group + 16-byte slot): the row
+            // addresses are formed once per group of four rows, the four pieces of a row are immediate offsets
+            const int sub = lane >> 3, slot = (lane & 7) * 8;
+            const uint32_t dst = base_u32 + (uint32_t)s * 3 * MM_TILE + (uint32_t)sub * MM_ROWB + (lane & 7) * 16;
 #pragma unroll
-            for (int u = 0; u < MM_E; ++u) {
-                if (u < n) {   // warp-uniform
-                    const int ju = __shfl_sync(FULL, j, u), idu = __shfl_sync(FULL, id, u);
-                    cp_async16(dst + u * MM_ROWB, P.k + (int64_t)ju * P.ldk + lane * 8);
-                    cp_async16(dst + MM_TILE + u * MM_ROWB, P.v + (int64_t)ju * P.ldv + lane * 8);
-                    cp_async16(dst + 2 * MM_TILE + u * MM_ROWB, P.feat + (int64_t)idu * MM_HID + lane * 8);
+            for (int grp = 0; grp < MM_E / 4; ++grp) {
+                const int u = 4 * grp + sub;
+                const int ju = __shfl_sync(FULL, j, u), idu = __shfl_sync(FULL, id, u);
+                if (u < n) {
+                    const __nv_bfloat16 *pk = P.k + (int64_t)ju * P.ldk + slot, *pv = P.v + (int64_t)ju * P.ldv + slot;
+                    const __nv_bfloat16 *pf = P.feat + (int64_t)idu * MM_HID + slot;
+                    const uint32_t d = dst + (uint32_t)(4 * grp) * MM_ROWB;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        cp_async16(d + i * 128, pk + i * 64);
+                        cp_async16(d + MM_TILE + i * 128, pv + i * 64);
+                        cp_async16(d + 2 * MM_TILE + i * 128, pf + i * 64);
+                    }
                 }
             }
             prod.advance(P.rowptr);
