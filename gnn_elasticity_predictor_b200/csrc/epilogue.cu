@@ -9,6 +9,7 @@
 // statistics live in registers (xor-shuffle reductions over the row's lanes), parameter gradients
 // are accumulated in registers by a persistent grid and reduced in a fixed order (no atomics).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -356,6 +357,160 @@ gate_ln_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ agg, 
     }
 }
 
+// ---- backward, hidden = 256 in bf16 (the training regime): one warp per row, two specialised loops ---------------------
+// The generic kernel above spends ~540 instructions per row, of which ~230 are arithmetic: per-row predicates (row in range?
+// row has an aggregate?), seven 64-bit row addresses, constants reloaded from local memory (the register budget of 2 CTAs /
+// SM does not hold five 8-wide constant vectors next to six accumulator vectors), three beta-gradient accumulators where two
+// suffice.  Here a warp walks ITS rows in order, first the rows that have an aggregate (row < agg_rows), then the isolated
+// ones (agg = 0: out = beta x_r, no dagg, no d/dc, and dbeta = <dout, x_r>): no predicate inside either loop, only the
+// constants each loop needs, dw_beta[2H:3H] = dw_beta[0:H] - dw_beta[H:2H] formed once at the end.  Same mask, same
+// statistics, same partial layout and the same fixed-order reduction as the generic kernel.
+template <bool HAS_AGG, bool DROP>
+__device__ __forceinline__ void glb256_row(int64_t row, int ch, const float *__restrict__ dy, const __nv_bfloat16 *__restrict__ dy2,
+                                           int64_t lddy2, const float *__restrict__ agg, const __nv_bfloat16 *__restrict__ xr,
+                                           int64_t ldxr, const float *__restrict__ beta_in, const float *__restrict__ mean_in,
+                                           const float *__restrict__ rstd_in, const float *__restrict__ stat_s, int heads, int head,
+                                           bool dcvec, float *__restrict__ dagg, __nv_bfloat16 *__restrict__ dagg_lp,
+                                           __nv_bfloat16 *__restrict__ dxr, int64_t lddxr, const F8 &gm, const F8 &bs, const F8 &w13,
+                                           const F8 &w23, float p_drop, float inv_keep, uint64_t seed, uint64_t rng_off,
+                                           F8 &a1, F8 &a2, F8 &ag, F8 &ab, F8 &ac) {
+    F8 gf;
+    if (dy) gf = ld8(dy + row * 256 + ch);
+    else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) gf.v[c] = 0.f;
+    }
+    if (dy2) {
+        const F8 g2 = ld8(dy2 + row * lddy2 + ch);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) gf.v[c] += g2.v[c];
+    }
+    const F8 sf = ld8(xr + row * ldxr + ch);
+    F8 af;
+    if (HAS_AGG) af = ld8(agg + row * 256 + ch);
+    const float beta = __ldg(beta_in + row), mean = __ldg(mean_in + row), rstd = __ldg(rstd_in + row);
+    if (DROP) {
+        float keep[8];
+        dropout8(seed, rng_off, (uint64_t)row * 256 + ch, p_drop, inv_keep, keep);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) gf.v[c] *= keep[c];
+    }
+    F8 xh, dxh;
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        // isolated rows: the forward's  beta * x_r + (1 - beta) * 0  rounds the product ONCE before the mean is subtracted;
+        // __fmul_rn keeps the compiler from contracting it into (beta * x_r - mean) here, which would move pre-activations
+        // that sit at zero across the ReLU threshold relative to the forward
+        const float o = HAS_AGG ? beta * sf.v[c] + (1.0f - beta) * af.v[c] : __fmul_rn(beta, sf.v[c]);
+        xh.v[c] = (o - mean) * rstd;
+        const float yv = xh.v[c] * gm.v[c] + bs.v[c];
+        const float dyv = yv > 0.f ? gf.v[c] : 0.f;
+        ag.v[c] = fmaf(dyv, xh.v[c], ag.v[c]);
+        ab.v[c] += dyv;
+        dxh.v[c] = dyv * gm.v[c];
+        s1 += dxh.v[c];
+        s2 = fmaf(dxh.v[c], xh.v[c], s2);
+    }
+    // both row sums through one butterfly
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        s1 += __shfl_xor_sync(FULL, s1, off);
+        s2 += __shfl_xor_sync(FULL, s2, off);
+    }
+    const float m1 = s1 * (1.0f / 256.0f), m2 = s2 * (1.0f / 256.0f);
+    F8 dof;
+    float bp = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        dof.v[c] = rstd * (dxh.v[c] - m1 - xh.v[c] * m2);
+        bp = fmaf(dof.v[c], HAS_AGG ? sf.v[c] - af.v[c] : sf.v[c], bp);
+    }
+    const float dbeta = group_sum<32>(bp);
+    const float dz = dbeta * beta * (1.0f - beta);
+    F8 ds;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        ds.v[c] = beta * dof.v[c] + dz * w23.v[c];
+        a2.v[c] = fmaf(dz, sf.v[c], a2.v[c]);
+    }
+    st8(dxr + row * lddxr + ch, ds);
+    if (HAS_AGG) {
+        const float srow = dcvec ? __ldg(stat_s + row * heads + head) : 0.f;
+        F8 da;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            da.v[c] = (1.0f - beta) * dof.v[c] + dz * w13.v[c];
+            a1.v[c] = fmaf(dz, af.v[c], a1.v[c]);
+            ac.v[c] = fmaf(da.v[c], srow, ac.v[c]);
+        }
+        st8(dagg + row * 256 + ch, da);
+        if (dagg_lp) st8(dagg_lp + row * 256 + ch, da);
+    }
+}
+
+template <bool DROP>
+__global__ void __launch_bounds__(EPI_THREADS, 2)
+gate_ln_bwd256_kernel(const float *__restrict__ dy, const float *__restrict__ agg, const __nv_bfloat16 *__restrict__ xr,
+                      const float *__restrict__ wbeta, const float *__restrict__ gamma, const float *__restrict__ bias,
+                      const float *__restrict__ beta_in, const float *__restrict__ mean_in, const float *__restrict__ rstd_in,
+                      float *__restrict__ dagg, __nv_bfloat16 *__restrict__ dxr, float *__restrict__ partials, int64_t n_rows,
+                      float p_drop, float inv_keep, uint64_t seed, uint64_t offset, const GateExtra X) {
+    constexpr int HID = 256;
+    __shared__ float red[EPI_WARPS][HID];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ch = lane * 8;
+    const int nvec = X.dcvec ? 6 : 5;
+    const int head = X.dcvec ? ch / (HID / X.heads) : 0;
+    const int64_t slots = (int64_t)gridDim.x * EPI_WARPS;
+    const int64_t agg_rows = X.agg_rows < 0 ? n_rows : X.agg_rows;
+    const uint64_t rng_off = offset + (X.rng_step ? *X.rng_step : 0ull);
+    const __nv_bfloat16 *dy2 = reinterpret_cast<const __nv_bfloat16 *>(X.dy2);
+    __nv_bfloat16 *dagg_lp = reinterpret_cast<__nv_bfloat16 *>(X.dagg_lp);
+
+    F8 w13, w23;
+    {
+        const F8 w1 = ld8(wbeta + ch), w2 = ld8(wbeta + HID + ch), w3 = ld8(wbeta + 2 * HID + ch);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            w13.v[c] = w1.v[c] + w3.v[c];
+            w23.v[c] = w2.v[c] - w3.v[c];
+        }
+    }
+    const F8 gm = ld8(gamma + ch), bs = ld8(bias + ch);
+    F8 a1, a2, ag, ab, ac;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) a1.v[c] = a2.v[c] = ag.v[c] = ab.v[c] = ac.v[c] = 0.f;
+
+    int64_t row = (int64_t)blockIdx.x * EPI_WARPS + warp;
+    for (; row < agg_rows; row += slots)
+        glb256_row<true, DROP>(row, ch, dy, dy2, X.lddy2, agg, xr, X.ldxr, beta_in, mean_in, rstd_in, X.stat_s, X.heads, head,
+                               X.dcvec, dagg, dagg_lp, dxr, X.lddxr, gm, bs, w13, w23, p_drop, inv_keep, seed, rng_off, a1, a2, ag, ab, ac);
+    for (; row < n_rows; row += slots)
+        glb256_row<false, DROP>(row, ch, dy, dy2, X.lddy2, agg, xr, X.ldxr, beta_in, mean_in, rstd_in, X.stat_s, X.heads, head,
+                                X.dcvec, dagg, dagg_lp, dxr, X.lddxr, gm, bs, w13, w23, p_drop, inv_keep, seed, rng_off, a1, a2, ag, ab, ac);
+
+    // fold the warps of the block in a fixed order, one vector at a time: dw_beta x3 | dgamma | dbias | dc
+#pragma unroll
+    for (int which = 0; which < 6; ++which) {
+        if (which >= nvec) break;                      // block-uniform
+        F8 src;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            src.v[c] = which == 0 ? a1.v[c] : which == 1 ? a2.v[c] : which == 2 ? a1.v[c] - a2.v[c] : which == 3 ? ag.v[c]
+                       : which == 4 ? ab.v[c] : ac.v[c];
+        st8(&red[warp][ch], src);
+        __syncthreads();
+        for (int c = threadIdx.x; c < HID; c += EPI_THREADS) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < EPI_WARPS; ++w) s += red[w][c];
+            partials[((int64_t)blockIdx.x * nvec + which) * HID + c] = s;
+        }
+        __syncthreads();
+    }
+}
+
 // out[i] = sum_b partials[b * width + i]: 8 threads per column stride the blocks, then a fixed-order fold (deterministic)
 constexpr int RP_COLS = 32, RP_ROWS = 8;
 __global__ void __launch_bounds__(RP_COLS * RP_ROWS)
@@ -565,7 +720,19 @@ static int dispatch_epi_bwd(const float *dy, const float *agg, const void *xr, c
     int lanes = 0;
 #define EPI_BWD(L) launch_epi_bwd<T, L>(dy, agg, xr, wbeta, gamma, bias, beta, mean, rstd, dagg, dxr, partials, n_rows, hidden, p_drop, seed, offset, X, st)
     if (extras && !epi_fast(hidden, &lanes)) return ALIGNN_ERR_BAD_SHAPE;
-    if (epi_fast(hidden, &lanes)) {
+    static const bool glb256 = [] { const char *e = getenv("ALIGNN_GLB256"); return !e || atoi(e) != 0; }();
+    if (glb256 && sizeof(T) == 2 && hidden == 256 && (!X.dcvec || (X.heads > 0 && 256 % X.heads == 0 && (256 / X.heads) % 8 == 0))) {
+        // the training regime: bf16, hidden 256 -> the two-loop kernel
+        const float inv_keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+        if (p_drop > 0.f)
+            gate_ln_bwd256_kernel<true><<<EPI_PARTIAL_BLOCKS, EPI_THREADS, 0, st>>>(
+                dy, agg, (const __nv_bfloat16 *)xr, wbeta, gamma, bias, beta, mean, rstd, dagg, (__nv_bfloat16 *)dxr, partials,
+                n_rows, p_drop, inv_keep, seed, offset, X);
+        else
+            gate_ln_bwd256_kernel<false><<<EPI_PARTIAL_BLOCKS, EPI_THREADS, 0, st>>>(
+                dy, agg, (const __nv_bfloat16 *)xr, wbeta, gamma, bias, beta, mean, rstd, dagg, (__nv_bfloat16 *)dxr, partials,
+                n_rows, p_drop, inv_keep, seed, offset, X);
+    } else if (epi_fast(hidden, &lanes)) {
         switch (lanes) {
             case 32: EPI_BWD(32); break;
             case 16: EPI_BWD(16); break;

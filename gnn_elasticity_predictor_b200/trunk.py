@@ -29,6 +29,7 @@ so in a batch of B > 1 crystals only the first ``lg_active`` bond rows have line
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional, Tuple
 
@@ -58,6 +59,7 @@ class TrunkCfg:
     zero_df: bool = False                # padded batches: bond rows that are no atom-graph edge get no df write
 
 
+DX_INPLACE = os.environ.get("ALIGNN_DX_INPLACE", "1") == "1"      # dx GEMM accumulates into the incoming gradient buffer
 _SIDE_STREAMS = {}
 _AUX_STREAMS = {}
 
@@ -242,7 +244,7 @@ class _Trunk(torch.autograd.Function):
             # dx = dy + [dx_r | df] [Ws ; I]  (all rows; the identity block adds df)  +  dbuf [Wq; Wk; Wv; WQT]  (active rows)
             w7, ws = w8c[idx, :7 * hid], w8c[idx, 7 * hid:]
             wtail = wtail_all[idx] if dy2 is not None else ws
-            if dy is not None and own_dy:
+            if dy is not None and own_dy and DX_INPLACE:
                 dx = torch.addmm(dy, dtail, wtail, out_dtype=torch.float32, out=dy)     # in place: dy is dead after this block
             elif dy is not None:
                 dx = torch.addmm(dy, dtail, wtail, out_dtype=torch.float32)
