@@ -72,6 +72,9 @@ def parse_args():
                          "--global-batch graphs split evenly over the ranks (config 3 as stated: 1 024 / 512 / 256 per GPU)")
     ap.add_argument("--global-batch", type=int, default=2048)
     ap.add_argument("--no-bonds", action="store_true", help="skip the extra lg_inc=bonds loop of the default run")
+    ap.add_argument("--early-allreduce", action="store_true",
+                    help="N>1: all-reduce the folded trunk gradients inside the backward instead of the whole bucket after it "
+                         "(A/B switch; measured no faster, profiles/r02_experiments)")
     ap.add_argument("--placement", choices=["dp", "members"], default="dp",
                     help="N>1: 'dp' shards graph batches of one member (gradient all-reduce); 'members' trains a different "
                          "ensemble member on every rank (reference trains members sequentially, train.py:2052), no exchange")
@@ -301,7 +304,8 @@ def main_b200(args):
         dp_mode = args.placement == "dp"
         steppers.append(engine.TrainStep(model, lr=1e-3, weight_decay=1e-4, max_norm=5.0,
                                          loss_scale=1.0 / world if dp_mode else 1.0, graph=not args.no_graph,
-                                         optimizer=not args.no_optimizer, data_parallel=dp_mode))
+                                         optimizer=not args.no_optimizer, data_parallel=dp_mode,
+                                         early_allreduce=args.early_allreduce))
 
     host_batches = [pkg.synthetic_batch(n_graphs, atoms, k, seed=1000 * rank + i, lg_inc=args.lg_inc).pin_memory()
                     for i in range(2)]

@@ -80,7 +80,7 @@ class FusedAdamW:
 
 
 class _Captured:
-    __slots__ = ("graph", "graph_opt", "batch", "tz", "mask", "weight", "loss", "mean", "logvar", "kernels")
+    __slots__ = ("graph", "graph_opt", "batch", "tz", "mask", "weight", "loss", "mean", "logvar", "kernels", "trunk_reduced")
 
 
 class TrainStep:
@@ -96,7 +96,8 @@ class TrainStep:
                  weight_decay: float = 1e-4, max_norm: float = 5.0, log_sigma_l2: float = 0.1,
                  min_logvar_floor: float = -2.9, loss_scale: float = 1.0, graph: bool = True, graph_warmup: int = 2,
                  optimizer: bool = True, group=None, pad_to_buckets: bool = False, bucket_align: int = 256,
-                 data_parallel: bool = True, feature_jitter_std: float = 0.0, allreduce_in_graph: bool = True):
+                 data_parallel: bool = True, feature_jitter_std: float = 0.0, allreduce_in_graph: bool = True,
+                 early_allreduce: bool = False):
         self.model = model
         params = [p for p in model.parameters() if p.requires_grad]
         if not params or not params[0].is_cuda:
@@ -131,6 +132,33 @@ class TrainStep:
         # host round trip between backward, collective and optimizer); falls back to two graphs with the collective
         # between them if the capture is refused
         self.allreduce_in_graph = bool(allreduce_in_graph)
+        # early_allreduce (N > 1, fused trunk; OFF by default): the gradients of the trunk's FOLDED weights (~95 % of the
+        # bucket) are all-reduced inside the trunk backward, beside the angle-encoder gradient kernel (trunk.py); what is left
+        # for the end of the step are the bucket slices of the parameters outside the trunk (~1.4 MB).  Parity-green
+        # (scripts/check_dp_equality.py) but not faster on 2 or 8 x B200: the persistent angle-gradient kernel holds every SM,
+        # the NCCL CTAs only get in at its wave boundary, and the folded buffer is 17 MB against the bucket's 13 MB
+        # (profiles/r02_experiments/dropped_experiments.txt)
+        self._trunk_reduced = False
+        self._rest_slices = None
+        if self.world > 1 and early_allreduce:
+            base = model.base
+            base._dp_group = group if group is not None else dist.group.WORLD
+            base._dp_done = self._mark_trunk_reduced
+            trunk_ids = {id(p) for blk in list(base.edge_blocks) + list(base.node_blocks) for p in blk.parameters()}
+            if base.angle_encoder is not None:
+                trunk_ids |= {id(p) for p in base.angle_encoder[2].parameters()}
+            runs, start = [], None
+            for p, off in zip(self.bucket.params, self.bucket.offsets):
+                if off >= n_active:
+                    break
+                if id(p) in trunk_ids:
+                    if start is not None:
+                        runs.append((start, off)); start = None
+                elif start is None:
+                    start = off
+            if start is not None:
+                runs.append((start, n_active))
+            self._rest_slices = runs
         self._captured: Dict[Tuple, _Captured] = {}
         self._seen: Dict[Tuple, int] = {}
         self.replays = 0
@@ -139,6 +167,7 @@ class TrainStep:
     # -- the step itself (eager; also what gets captured) ------------------------------------------------------
     def _fwd_bwd(self, batch, tz: Tensor, mask: Optional[Tensor] = None, weight: Optional[Tensor] = None):
         self.bucket.detach_grads()
+        self._trunk_reduced = False
         self.model.base.build_plans(batch)                 # CSR/CSC sorts of this batch: part of every step
         if self.feature_jitter_std > 0.0 and self.model.training:
             batch = self._jittered(batch)
@@ -158,6 +187,19 @@ class TrainStep:
         b.global_x = batch.global_x + torch.randn_like(batch.global_x) * std
         return b
 
+    def _mark_trunk_reduced(self) -> None:
+        self._trunk_reduced = True
+
+    def _all_reduce(self) -> None:
+        """The step's gradient exchange.  When the trunk backward has already reduced its folded gradients (see __init__)
+        only the slices of the other parameters are left; otherwise (per-block path, fp32 regime, ...) the whole bucket."""
+        if self._trunk_reduced and self._rest_slices is not None:
+            for a, b in self._rest_slices:
+                dist.all_reduce(self.bucket.flat[a:b], op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            self.bucket.all_reduce(self.group)
+        self._trunk_reduced = False
+
     def _finish(self):
         if self.opt is not None:
             self.opt.step()
@@ -168,7 +210,7 @@ class TrainStep:
         try:
             out = self._fwd_bwd(batch, tz, mask, weight)
             if self.world > 1:
-                self.bucket.all_reduce(self.group)
+                self._all_reduce()
             self._finish()
         finally:
             ops.RNG_STEP = prev
@@ -204,7 +246,7 @@ class TrainStep:
                     cap.loss, cap.mean, cap.logvar = self._fwd_bwd(cap.batch, cap.tz, cap.mask, cap.weight)
                     if one_graph:
                         if self.world > 1:
-                            self.bucket.all_reduce(self.group)      # NCCL kernel node inside the graph
+                            self._all_reduce()                      # NCCL kernel node(s) inside the graph
                         self._finish()
             except ops.StaticDropoutUnderCapture:
                 raise
@@ -216,6 +258,7 @@ class TrainStep:
                 cap.graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(cap.graph):
                     cap.loss, cap.mean, cap.logvar = self._fwd_bwd(cap.batch, cap.tz, cap.mask, cap.weight)
+            cap.trunk_reduced = self._trunk_reduced
             if not one_graph:
                 cap.graph_opt = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(cap.graph_opt, pool=cap.graph.pool()):
@@ -284,7 +327,8 @@ class TrainStep:
             cap.weight.copy_(sample_weight, non_blocking=True)
         cap.graph.replay()
         if cap.graph_opt is not None:
-            self.bucket.all_reduce(self.group)
+            self._trunk_reduced = cap.trunk_reduced
+            self._all_reduce()
             cap.graph_opt.replay()
         self.replays += 1
         ops.STATS.kernels += cap.kernels

@@ -519,7 +519,8 @@ class AlignnRegressor(nn.Module):
         cfg = trunk_mod.TrunkCfg(heads=h, n_layers=nl, eps=[b.norm.eps for b in blocks], p_attn=p_attn, p_out=p_out,
                                  keys=keys, lg_plan=lg_plan, g_plan=g_plan, a_csr=lg.a_csr, w1=lg.w1, b1=lg.b1,
                                  lg_active=lg_active, overlap=bool(getattr(self, "overlap_streams", True)),
-                                 zero_df=zero_df)
+                                 zero_df=zero_df, dp_group=getattr(self, "_dp_group", None),
+                                 dp_done=getattr(self, "_dp_done", None))
         enc = self.angle_encoder
         return trunk_mod.run_trunk(node32, node_b, edge32, edge_b, w8, b8, wc, cvec, wbeta, gamma, beta_ln,
                                    enc[0].weight, enc[0].bias, cfg)

@@ -57,6 +57,9 @@ class TrunkCfg:
     lg_active: int = -1                  # bond rows >= lg_active are isolated in the line graph (< 0: unknown, all active)
     overlap: bool = True                 # run the atom-graph chain on a second stream (fork/join; capturable)
     zero_df: bool = False                # padded batches: bond rows that are no atom-graph edge get no df write
+    dp_group: object = None              # data-parallel process group: the gradients of the FOLDED stacked weights are
+                                         # all-reduced inside the backward, under the angle-encoder gradient kernel
+    dp_done: object = None               # callback() -> None: tells the engine that this backward has reduced them
 
 
 DX_INPLACE = os.environ.get("ALIGNN_DX_INPLACE", "1") == "1"      # dx GEMM accumulates into the incoming gradient buffer
@@ -183,10 +186,17 @@ class _Trunk(torch.autograd.Function):
         dev = dn.device
         f32 = dict(dtype=torch.float32, device=dev)
         nb2 = 2 * nl
-        d_w8 = torch.empty(nb2, 8 * hid, hid, **f32)
-        d_b8 = torch.empty(nb2, 8 * hid, **f32)
-        d_wc = torch.empty(nb2, hid, hid, **f32)
-        d_par = torch.empty(nb2, 6 * hid, **f32)       # per block: dw_beta x3 | dgamma | dbias | dcvec
+        # the gradients of the folded, stacked weights live in ONE flat buffer: under data parallelism it is all-reduced
+        # here, as soon as the last block has written it (the fold backward that turns it into parameter gradients is
+        # linear, so reducing before or after it is the same sum) -- the collective then runs beside the angle-encoder
+        # gradient kernel instead of after the whole backward
+        sizes = (nb2 * 8 * hid * hid, nb2 * 8 * hid, nb2 * hid * hid, nb2 * 6 * hid)
+        gflat = torch.empty(sum(sizes), **f32)
+        o1, o2, o3 = sizes[0], sizes[0] + sizes[1], sizes[0] + sizes[1] + sizes[2]
+        d_w8 = gflat[:o1].view(nb2, 8 * hid, hid)
+        d_b8 = gflat[o1:o2].view(nb2, 8 * hid)
+        d_wc = gflat[o2:o3].view(nb2, hid, hid)
+        d_par = gflat[o3:].view(nb2, 6 * hid)          # per block: dw_beta x3 | dgamma | dbias | dcvec
         # [Ws ; I] of every block at once (the identity block adds the atom-graph feature gradient inside the dx GEMM)
         wtail_all = torch.cat([w8c[:, 7 * hid:], torch.eye(hid, dtype=cd, device=dev).expand(nb2, hid, hid)], dim=1)
         dn = dn.contiguous().float()
@@ -260,13 +270,12 @@ class _Trunk(torch.autograd.Function):
         keep: list = []
         if aux is not None:
             aux.wait_stream(main)
-            for t in (d_w8, d_b8, d_wc):
-                t.record_stream(aux)
+            gflat.record_stream(aux)
         mk = torch.zeros if cfg.zero_df else torch.empty
         tails = [mk(n_bonds, 2 * hid, dtype=cd, device=dev) for _ in range(nl)]            # LG block l: dx_r | df_l
         if side is not None:
             side.wait_stream(main)
-            for t in tails + [dn, d_w8, d_b8, d_wc, d_par, wtail_all]:
+            for t in tails + [dn, gflat, wtail_all]:
                 t.record_stream(side)
         for l in reversed(range(nl)):
             # the incoming dn of the top layer belongs to autograd (never written in place); below it dn / de are this
@@ -286,6 +295,18 @@ class _Trunk(torch.autograd.Function):
         if side is not None:
             main.wait_stream(side)
             dn.record_stream(main)
+        if cfg.dp_group is not None:
+            import torch.distributed as dist
+            if aux is not None:
+                ev = torch.cuda.Event()
+                ev.record(main)                       # every block of both chains has written its slice
+                with torch.cuda.stream(aux):          # ... and the aux stream its weight / bias gradients
+                    aux.wait_event(ev)
+                    dist.all_reduce(gflat, op=dist.ReduceOp.SUM, group=cfg.dp_group)
+            else:
+                dist.all_reduce(gflat, op=dist.ReduceOp.SUM, group=cfg.dp_group)
+            if cfg.dp_done is not None:
+                cfg.dp_done()
         dw1, db1 = ops.raw_lg_angle_grad(cfg.a_csr, cfg.w1, cfg.b1, cfg.lg_plan, coefs, qts, gts)
         if aux is not None:
             main.wait_stream(aux)
