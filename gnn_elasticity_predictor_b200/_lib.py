@@ -87,6 +87,8 @@ SIGNATURES = {
     "alignn_lg_angle_grad_partial_floats": (c_int64, [c_int64, c_int64]),
     "alignn_lg_angle_grad": (c_int, [_P, _P, _P, c_int, _P, c_int, _P, _P, _P, c_int64, c_int64, c_int64, c_int64,
                                      _P, _P, c_int64, c_int64, _P]),
+    "alignn_lg_angle_grad2": (c_int, [_P, _P, _P, c_int, _P, c_int, _P, _P, _P, c_int64, c_int64, c_int64, c_int64,
+                                     _P, _P, c_int64, c_int64, c_int, _P]),
     "alignn_adamw_partial_floats": (c_int64, []),
     "alignn_clip_adamw_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64,
                                        c_float, c_float, c_float, c_float, c_float, c_float, _P]),
@@ -125,7 +127,7 @@ SIGNATURES = {
     "alignn_segment_mean_bwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P]),
 }
 
-ABI_VERSION = 21
+ABI_VERSION = 22
 F32, BF16 = 0, 1
 
 

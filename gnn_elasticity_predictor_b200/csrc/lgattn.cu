@@ -1068,11 +1068,27 @@ extern "C" int64_t alignn_lg_angle_grad_partial_floats(int64_t n_nodes, int64_t 
 }
 
 /* coef / qt / gt: arrays of `n_layers` (<= 4) device pointers (host arrays of pointers). */
+extern "C" int alignn_lg_angle_grad2(const void *a_csr, const float *w1, const float *b1, int in_dim,
+                                     const int32_t *rowptr, int n_layers, const float *const *coef,
+                                     const void *const *qt, const void *const *gt,
+                                     int64_t ldqt, int64_t hsqt, int64_t ldgt, int64_t hsgt,
+                                     float *partials, float *out, int64_t n_nodes, int64_t n_edges, int max_blocks, void *stream);
+
 extern "C" int alignn_lg_angle_grad(const void *a_csr, const float *w1, const float *b1, int in_dim,
                                     const int32_t *rowptr, int n_layers, const float *const *coef,
                                     const void *const *qt, const void *const *gt,
                                     int64_t ldqt, int64_t hsqt, int64_t ldgt, int64_t hsgt,
                                     float *partials, float *out, int64_t n_nodes, int64_t n_edges, void *stream) {
+    return alignn_lg_angle_grad2(a_csr, w1, b1, in_dim, rowptr, n_layers, coef, qt, gt, ldqt, hsqt, ldgt, hsgt, partials, out,
+                                 n_nodes, n_edges, 0, stream);
+}
+
+/* max_blocks > 0: at most that many CTAs (one per SM): the kernel then leaves the other SMs to concurrent streams. */
+extern "C" int alignn_lg_angle_grad2(const void *a_csr, const float *w1, const float *b1, int in_dim,
+                                     const int32_t *rowptr, int n_layers, const float *const *coef,
+                                     const void *const *qt, const void *const *gt,
+                                     int64_t ldqt, int64_t hsqt, int64_t ldgt, int64_t hsgt,
+                                     float *partials, float *out, int64_t n_nodes, int64_t n_edges, int max_blocks, void *stream) {
     if (in_dim < 1 || in_dim > 15 || n_layers < 1 || n_layers > LGA_MAXL || n_nodes < 0 || n_edges < 0) return ALIGNN_ERR_BAD_ARG;
     if (!w1 || !b1 || !out || !partials || !coef || !qt || !gt) return ALIGNN_ERR_BAD_ARG;
     if (n_nodes >= ((int64_t)1 << 31) - 1 || n_edges >= ((int64_t)1 << 31) - 64) return ALIGNN_ERR_BAD_SHAPE;
@@ -1099,6 +1115,7 @@ extern "C" int alignn_lg_angle_grad(const void *a_csr, const float *w1, const fl
     static_assert(SMEM >= LGA_WARPS * 4096 * 4, "reduction buffer aliases the pipeline buffers");
     static_assert(SMEM <= 227 * 1024, "over the per-CTA shared-memory limit");
     int grid = lg_grid(n_nodes, n_edges, LGA_WARPS);
+    if (max_blocks > 0 && max_blocks < grid) grid = max_blocks;
     if (const char *e = getenv("ALIGNN_LGA_BLOCKS")) {           // tuning knob (never more CTAs than the partials buffer holds)
         const int want = atoi(e);
         if (want >= 1 && want < grid) grid = want;

@@ -21,6 +21,7 @@ The step leaves ``param.grad`` populated (views of the flat bucket), so callers 
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -97,7 +98,7 @@ class TrainStep:
                  min_logvar_floor: float = -2.9, loss_scale: float = 1.0, graph: bool = True, graph_warmup: int = 2,
                  optimizer: bool = True, group=None, pad_to_buckets: bool = False, bucket_align: int = 256,
                  data_parallel: bool = True, feature_jitter_std: float = 0.0, allreduce_in_graph: bool = True,
-                 early_allreduce: bool = False):
+                 early_allreduce: bool = False, defer_angle_blocks: int = 116):
         self.model = model
         params = [p for p in model.parameters() if p.requires_grad]
         if not params or not params[0].is_cuda:
@@ -159,6 +160,10 @@ class TrainStep:
             if start is not None:
                 runs.append((start, n_active))
             self._rest_slices = runs
+        # the angle-encoder gradient kernel (once per step, persistent, ~0.26 ms) runs on the trunk's side stream with a
+        # capped grid and is joined HERE after backward(): the encoder / fold backward and the gradient gather run beside it
+        # on the SMs it leaves free.  Only this engine may defer the join (a plain loss.backward() user gets the joined form).
+        self.defer_angle_blocks = int(os.environ.get("ALIGNN_DEFER_ANGLE", defer_angle_blocks))
         self._captured: Dict[Tuple, _Captured] = {}
         self._seen: Dict[Tuple, int] = {}
         self.replays = 0
@@ -171,9 +176,18 @@ class TrainStep:
         self.model.base.build_plans(batch)                 # CSR/CSC sorts of this batch: part of every step
         if self.feature_jitter_std > 0.0 and self.model.training:
             batch = self._jittered(batch)
-        mean, logvar = self.model(batch)
+        base = self.model.base
+        state = {"deferred": False}
+        base._defer_angle_blocks, base._defer_state = self.defer_angle_blocks, state    # read by the forward when it builds
+        try:                                                                          # the trunk program ...
+            mean, logvar = self.model(batch)
+        finally:
+            base._defer_angle_blocks, base._defer_state = 0, None    # ... and by nobody else: a plain backward() joins itself
         loss = fused_gaussian_nll(mean, logvar, tz, self.log_sigma_l2, self.floor, mask=mask, sample_weight=weight)
         (loss * self.loss_scale).backward()
+        if state["deferred"]:                              # join the deferred angle-gradient kernel (trunk.py)
+            from . import trunk as _trunk
+            torch.cuda.current_stream().wait_stream(_trunk._side_stream(self.dev))
         self.bucket.gather()                               # one multi-tensor copy into the flat gradient bucket
         return loss.detach(), mean.detach(), logvar.detach()
 

@@ -520,7 +520,9 @@ class AlignnRegressor(nn.Module):
                                  keys=keys, lg_plan=lg_plan, g_plan=g_plan, a_csr=lg.a_csr, w1=lg.w1, b1=lg.b1,
                                  lg_active=lg_active, overlap=bool(getattr(self, "overlap_streams", True)),
                                  zero_df=zero_df, dp_group=getattr(self, "_dp_group", None),
-                                 dp_done=getattr(self, "_dp_done", None))
+                                 dp_done=getattr(self, "_dp_done", None),
+                                 defer_angle=int(getattr(self, "_defer_angle_blocks", 0)),
+                                 defer_state=getattr(self, "_defer_state", None))
         enc = self.angle_encoder
         return trunk_mod.run_trunk(node32, node_b, edge32, edge_b, w8, b8, wc, cvec, wbeta, gamma, beta_ln,
                                    enc[0].weight, enc[0].bias, cfg)

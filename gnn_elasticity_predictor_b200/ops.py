@@ -693,8 +693,9 @@ def raw_lgattn_bwd(dagg: Tensor, dagg_lp: Tensor, agg: Tensor, q: Tensor, k: Ten
     return coef
 
 
-def raw_lg_angle_grad(a_csr: Tensor, w1: Tensor, b1: Tensor, plan: GraphPlan, coefs, qts, gts):
-    """(dW1 [256, in_dim], db1 [256]) in fp32 from the coefficient tensors of all line-graph layers."""
+def raw_lg_angle_grad(a_csr: Tensor, w1: Tensor, b1: Tensor, plan: GraphPlan, coefs, qts, gts, max_blocks: int = 0):
+    """(dW1 [256, in_dim], db1 [256]) in fp32 from the coefficient tensors of all line-graph layers.  ``max_blocks`` > 0 caps
+    the grid (one CTA per SM) so that work on other streams keeps the remaining SMs."""
     lib = _lib.load()
     in_dim = int(w1.size(1))
     dev = w1.device
@@ -708,9 +709,10 @@ def raw_lg_angle_grad(a_csr: Tensor, w1: Tensor, b1: Tensor, plan: GraphPlan, co
         out = torch.empty((in_dim + 1) * 256, **f32)
         arr = lambda ts: (ctypes.c_void_p * n)(*[t.data_ptr() for t in ts])   # noqa: E731
         with torch.cuda.device(dev), _Launch("lg_angle_grad", 2, (n_nodes, n_edges, n)):
-            rc = lib.alignn_lg_angle_grad(_p(a_csr), _p(w1), _p(b1), in_dim, _p(plan.rowptr), n, arr(c), arr(qq), arr(gg),
-                                          int(qq[0].stride(1)), int(qq[0].stride(0)), int(gg[0].stride(1)),
-                                          int(gg[0].stride(0)), _p(partials), _p(out), n_nodes, n_edges, _stream())
+            rc = lib.alignn_lg_angle_grad2(_p(a_csr), _p(w1), _p(b1), in_dim, _p(plan.rowptr), n, arr(c), arr(qq), arr(gg),
+                                           int(qq[0].stride(1)), int(qq[0].stride(0)), int(gg[0].stride(1)),
+                                           int(gg[0].stride(0)), _p(partials), _p(out), n_nodes, n_edges, int(max_blocks),
+                                           _stream())
         _lib.check(rc, "alignn_lg_angle_grad")
         total = out if lo == 0 and len(coefs) <= 4 else total + out
     dw1 = total[:in_dim * 256].view(in_dim, 256).t().contiguous()

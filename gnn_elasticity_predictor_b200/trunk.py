@@ -60,6 +60,10 @@ class TrunkCfg:
     dp_group: object = None              # data-parallel process group: the gradients of the FOLDED stacked weights are
                                          # all-reduced inside the backward, under the angle-encoder gradient kernel
     dp_done: object = None               # callback() -> None: tells the engine that this backward has reduced them
+    defer_state: object = None           # dict the backward marks with {"deferred": True} when it left the side stream unjoined
+    defer_angle: int = 0                 # > 0: run the angle-encoder gradient kernel on the side stream with at most this
+                                         # many CTAs and do NOT join it here -- the caller (engine.TrainStep) joins the side
+                                         # stream after backward(), so the rest of the backward runs beside the kernel
 
 
 DX_INPLACE = os.environ.get("ALIGNN_DX_INPLACE", "1") == "1"      # dx GEMM accumulates into the incoming gradient buffer
@@ -307,7 +311,23 @@ class _Trunk(torch.autograd.Function):
                 dist.all_reduce(gflat, op=dist.ReduceOp.SUM, group=cfg.dp_group)
             if cfg.dp_done is not None:
                 cfg.dp_done()
-        dw1, db1 = ops.raw_lg_angle_grad(cfg.a_csr, cfg.w1, cfg.b1, cfg.lg_plan, coefs, qts, gts)
+        if cfg.defer_angle > 0 and side is not None and cfg.defer_state is not None:
+            # the kernel is persistent and would hold every SM: capped to `defer_angle` CTAs on the side stream it leaves
+            # the other SMs to the encoder / fold backward and the optimizer prologue that follow on this stream
+            ev = torch.cuda.Event()
+            ev.record(main)
+            for t in coefs + qts + gts + [cfg.a_csr, cfg.w1, cfg.b1]:
+                t.record_stream(side)
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                dw1, db1 = ops.raw_lg_angle_grad(cfg.a_csr, cfg.w1, cfg.b1, cfg.lg_plan, coefs, qts, gts,
+                                                 max_blocks=cfg.defer_angle)
+            dw1.record_stream(main)
+            db1.record_stream(main)
+            if cfg.defer_state is not None:
+                cfg.defer_state["deferred"] = True
+        else:
+            dw1, db1 = ops.raw_lg_angle_grad(cfg.a_csr, cfg.w1, cfg.b1, cfg.lg_plan, coefs, qts, gts)
         if aux is not None:
             main.wait_stream(aux)
         keep.clear()

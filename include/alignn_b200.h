@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define ALIGNN_ABI_VERSION 21
+#define ALIGNN_ABI_VERSION 22
 
 #define ALIGNN_F32 0
 #define ALIGNN_BF16 1
@@ -301,6 +301,13 @@ int alignn_lg_angle_grad(const void *a_csr, const float *w1, const float *b1, in
                          const void *const *qt, const void *const *gt,
                          int64_t ldqt, int64_t hsqt, int64_t ldgt, int64_t hsgt,
                          float *partials, float *out, int64_t n_nodes, int64_t n_edges, void *stream);
+/* the same with a cap on the grid (max_blocks > 0: at most that many CTAs, one per SM, so that concurrent streams keep the
+ * remaining SMs -- the engine runs the tail of the backward beside this kernel); same partials buffer. */
+int alignn_lg_angle_grad2(const void *a_csr, const float *w1, const float *b1, int in_dim,
+                         const int32_t *rowptr, int n_layers, const float *const *coef,
+                         const void *const *qt, const void *const *gt,
+                         int64_t ldqt, int64_t hsqt, int64_t ldgt, int64_t hsgt,
+                         float *partials, float *out, int64_t n_nodes, int64_t n_edges, int max_blocks, void *stream);
 
 /* ---- fused global-norm clip + AdamW over one flat parameter bucket (reference scripts/train.py:690-699, 1516-1540) --
  * params/grads/exp_avg/exp_avg_sq: f32 [n]; shadow_bf16: optional bf16 copy of the updated parameters; partials:
