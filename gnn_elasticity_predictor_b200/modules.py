@@ -406,8 +406,10 @@ class AlignnRegressor(nn.Module):
                         ops.lgattn_enabled(self.hidden, self.heads, enc[0].in_features, cd):
                     # h1 = relu(W1 a + b1) is rebuilt inside the kernels from the packed 32-byte angle rows
                     w1p, b1p = enc[0].weight, enc[0].bias
-                    lg = LgShared(ops.pack_angles(data.lg_edge_attr, lg_plan), w1p.detach().contiguous().float(),
-                                  b1p.detach().contiguous().float(), n_layers)
+                    acsr = getattr(data, "_alignn_acsr", None)             # packed beside the plan build (build_plans)
+                    if acsr is None or acsr.size(0) != n_angles:
+                        acsr = ops.pack_angles(data.lg_edge_attr, lg_plan)
+                    lg = LgShared(acsr, w1p.detach().contiguous().float(), b1p.detach().contiguous().float(), n_layers)
                     w2, b2 = enc[2].weight.float(), enc[2].bias.float()
                     fold_angle = True
                 elif enc is not None and data.lg_edge_attr.numel() > 0 and \
@@ -548,10 +550,24 @@ class AlignnRegressor(nn.Module):
         if side is not None:
             main = torch.cuda.current_stream()
             side.wait_stream(main)
+            acsr = None
             with torch.cuda.stream(side):
                 lg_plan = ops.build_plan(data.lg_edge_index, n_bonds, source_sorted=lg_sorted, key_bound=lg_bound)
+                # the packed 32-byte angle rows of the line-graph kernels only need this plan: packed here, on the side
+                # stream, they are off the main stream's critical path as well
+                enc = self.angle_encoder
+                try:
+                    cd = _ambient_dtype(self.compute_dtype)
+                except RuntimeError:
+                    cd = None
+                if cd is not None and enc is not None and data.lg_edge_attr.numel() > 0 and len(self.edge_blocks) > 0 and \
+                        _streaming_ok(self.edge_blocks[0].conv, data.x, getattr(self, "streaming", None)) and \
+                        ops.lgattn_enabled(self.hidden, self.heads, enc[0].in_features, cd):
+                    acsr = ops.pack_angles(data.lg_edge_attr, lg_plan)
                 ready = torch.cuda.Event()
                 ready.record(side)
+            if acsr is not None:
+                acsr.record_stream(main)
             g_plan = ops.build_plan(data.edge_index, n_atoms, source_sorted=g_sorted)
             pool_plan = ops.build_pool_plan(data.batch, int(n_graphs))
             for t in (lg_plan.rowptr, lg_plan.col, lg_plan.eid, lg_plan.rowptr_t, lg_plan.col_t, lg_plan.eid_t, lg_plan.status):
@@ -565,6 +581,7 @@ class AlignnRegressor(nn.Module):
         try:
             object.__setattr__(data, "_alignn_plans", plans)
             object.__setattr__(data, "_alignn_plans_ready", ready)
+            object.__setattr__(data, "_alignn_acsr", acsr if side is not None else None)
         except Exception:  # noqa: BLE001 -- e.g. a PyG Batch refusing private attributes
             if ready is not None:
                 torch.cuda.current_stream().wait_event(ready)
