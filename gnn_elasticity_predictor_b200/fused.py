@@ -71,6 +71,8 @@ class BlockCfg:
     anchor_dtype: Optional[torch.dtype] = None
     lg: Optional[LgShared] = None      # in-kernel-feature line-graph family (bf16, hidden 256, 4 heads)
     strided: bool = False              # stored-feature tensor-core family with strided operands + device RNG counter
+    active_rows: int = -1              # inference only (no autograd): rows >= active_rows are isolated in this block's graph --
+                                       # q | k | v | qt, the attention kernel and the abar products run on the prefix only
 
 
 class _LinearCS(torch.autograd.Function):
@@ -163,6 +165,38 @@ class _AttnBlock(torch.autograd.Function):
         else:
             feat = None
         w4c, b4c = w4.to(cd), b4.to(cd)
+        if 0 <= cfg.active_rows < n:
+            # Forward-only elision of the isolated rows (PyG-collated line graphs; the fp32 regime of
+            # predict.py / evaluate.py): x_r for every row, everything attention-related for the active prefix.  Nothing
+            # is saved: the caller guarantees that autograd is off.
+            na = int(cfg.active_rows)
+            xr = torch.addmm(b4c[3 * hid:], xb, w4c[3 * hid:].t())            # [n, H]
+            p3 = torch.addmm(b4c[:3 * hid], xb[:na], w4c[:3 * hid].t())       # [na, 3H]: q | k | v
+            wc3 = wc.to(cd).view(h, c, hid)
+            q, k, v = (p3[:, i * hid:(i + 1) * hid] for i in range(3))
+            qt = torch.bmm(q.unflatten(1, (h, c)).transpose(0, 1), wc3)       # [h, na, H]
+            if cfg.lg is not None:
+                lg = cfg.lg
+                aggv, abar, m, z, s = ops.raw_lgattn_fwd(q, k, v, qt, lg.a_csr, lg.w1, lg.b1, plan, h, cfg.p_attn,
+                                                         cfg.seed_attn, cfg.off_attn, rs)
+            elif cfg.strided:
+                aggv, abar, m, z, s = ops.raw_attn_fwd_s(q, k, v, qt, feat, plan, h, cfg.p_attn, cfg.seed_attn,
+                                                         cfg.off_attn, rs)
+            else:
+                aggv, abar, m, z, s = ops.raw_edgeattn_fwd(q, k, v, qt, feat, plan, h, cfg.p_attn, cfg.seed_attn,
+                                                           cfg.off_attn)
+            agge = torch.bmm(abar, wc3.transpose(1, 2))                       # [h, na, C]
+            cv = cvec.detach().contiguous().float() if cvec is not None else None
+            y, y_lp, _, _, _, _ = ops.raw_gate_ln_fwd2(aggv, agge, cv, s if cv is not None else None, h, xr, x32,
+                                                       wbeta.detach().reshape(-1).contiguous().float(),
+                                                       gamma.detach().contiguous().float(),
+                                                       beta_ln.detach().contiguous().float(), cfg.eps, cfg.p_out,
+                                                       cfg.seed_out, cfg.off_out, cfg.want_lp and cd != torch.float32, rs,
+                                                       agg_rows=na)
+            ctx.elided = True
+            if y_lp is not None:
+                ctx.mark_non_differentiable(y_lp)
+            return y, y_lp
         proj = torch.addmm(b4c, xb, w4c.t())                                  # [n, 4H]: q | k | v | skip
         wc3 = wc.to(cd).view(h, c, hid)                                       # Wc[t] : [C, H]
         q, k, v, xr = (proj[:, i * hid:(i + 1) * hid] for i in range(4))
@@ -196,6 +230,9 @@ class _AttnBlock(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy: Optional[Tensor], _dy_lp):
+        if getattr(ctx, "elided", False):
+            raise RuntimeError("this block ran the forward-only (isolated-row elision) path: BlockCfg.active_rows is for "
+                               "inference without autograd")
         xb, feat, proj, qt, abar, agg, m, z, s, beta, mean, rstd, w4c, wc3, cv, wb, gm, bl = ctx.saved_tensors
         plan, cfg, rs = ctx.plan, ctx.cfg, ctx.rs
         cd, h = cfg.cd, cfg.heads

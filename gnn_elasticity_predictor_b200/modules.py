@@ -188,7 +188,8 @@ def _stream_block(conv: TransformerConv, norm: nn.LayerNorm, p_out: float, train
                   xb: Optional[Tensor], feat: Optional[Tensor], anchor: Optional[Tensor], wc: Tensor,
                   cvec: Optional[Tensor], plan: GraphPlan, cd: torch.dtype,
                   accum: Optional[FeatGradAccumulator] = None, is_last_visitor: bool = False, want_lp: bool = True,
-                  lg: Optional[LgShared] = None, w1: Optional[Tensor] = None, b1: Optional[Tensor] = None):
+                  lg: Optional[LgShared] = None, w1: Optional[Tensor] = None, b1: Optional[Tensor] = None,
+                  active_rows: int = -1):
     p_attn = conv.dropout if training else 0.0
     p_o = p_out if training else 0.0
     sa, oa = ops.next_dropout_key() if p_attn > 0.0 else (0, 0)
@@ -196,8 +197,9 @@ def _stream_block(conv: TransformerConv, norm: nn.LayerNorm, p_out: float, train
     cfg = BlockCfg(heads=conv.heads, eps=norm.eps, p_attn=p_attn, p_out=p_o, seed_attn=sa, off_attn=oa, seed_out=so,
                    off_out=oo, cd=cd, want_lp=want_lp, accum=accum, is_last_visitor=is_last_visitor,
                    anchor_dtype=None if anchor is None else anchor.dtype, lg=lg,
-                   strided=lg is None and accum is None and ops.mma_enabled(conv.in_channels, conv.heads, cd))
-    if cfg.lg is not None or cfg.strided:
+                   strided=lg is None and accum is None and ops.mma_enabled(conv.in_channels, conv.heads, cd),
+                   active_rows=active_rows)
+    if (cfg.lg is not None or cfg.strided) and active_rows < 0:
         w8, b8 = _stack8(conv, wc)
         return fused.attn_block8(x32.float(), xb, feat, anchor, w8, b8, wc, cvec, conv.lin_beta.weight, norm.weight,
                                  norm.bias, plan, cfg, w1, b1)
@@ -437,6 +439,12 @@ class AlignnRegressor(nn.Module):
             if edge32 is None:
                 edge32 = edge_b0.float()
             accum = FeatGradAccumulator(n_layers) if run_lg and lg is None else None
+            # inference (no autograd), PyG-collated batch: the line-graph blocks skip the bond rows without neighbours
+            lg_rows = -1
+            lg_active = getattr(data, "lg_active_rows", None)
+            if not torch.is_grad_enabled() and lg_active is not None and getattr(self, "elide_isolated", True) and \
+                    0 <= int(lg_active) < n_bonds:
+                lg_rows = int(lg_active)
 
             edge_b = node_b = None
             for l, (eb, nb) in enumerate(zip(self.edge_blocks, self.node_blocks)):
@@ -452,16 +460,17 @@ class AlignnRegressor(nn.Module):
                         first = l == 0
                         edge32, edge_b = _stream_block(eb.conv, eb.norm, eb.dropout.p, self.training, edge32, edge_b,
                                                        None, None, wc, cvec, lg_plan, cd, is_last_visitor=first, lg=lg,
-                                                       w1=w1p if first else None, b1=b1p if first else None)
+                                                       w1=w1p if first else None, b1=b1p if first else None,
+                                                       active_rows=lg_rows)
                     elif shared_h1:
                         # layer 0 is visited last by backward: it masks the accumulated df and hands it to h1
                         edge32, edge_b = _stream_block(eb.conv, eb.norm, eb.dropout.p, self.training, edge32, edge_b,
                                                        h1.detach(), h1 if (l == 0 and fold_angle) else None, wc, cvec,
                                                        lg_plan, cd, accum=accum if fold_angle else None,
-                                                       is_last_visitor=(l == 0))
+                                                       is_last_visitor=(l == 0), active_rows=lg_rows)
                     else:
                         edge32, edge_b = _stream_block(eb.conv, eb.norm, eb.dropout.p, self.training, edge32, edge_b,
-                                                       h1, h1, wc, cvec, lg_plan, cd)
+                                                       h1, h1, wc, cvec, lg_plan, cd, active_rows=lg_rows)
                 if run_atoms:
                     wc, cvec = nb.folded_edge_projection()
                     feat = edge_b if edge_b is not None else edge32

@@ -255,3 +255,30 @@ def test_generic_width_model_with_dropout_is_not_frozen_by_graph_capture():
         losses = [float(ts.step(batch, tz)[0]) for _ in range(6)]
     assert ts.replays == 0 and ts.eager_steps == 6 and ts.use_graph is False
     assert len({round(x, 6) for x in losses}) >= 5, losses
+
+
+def test_fp32_inference_elides_isolated_rows_without_changing_results():
+    """predict.py / evaluate.py regime (fp32, no autocast, no autograd): with a PyG-collated batch the line-graph blocks run
+    q|k|v|qt, the attention kernel and the abar products on the active prefix of the bond rows only.  Same outputs as with
+    the elision switched off (1e-6: the library GEMMs may tile a shorter M differently) and the elided path refuses
+    autograd."""
+    m = _model(seed=9, layers=2)
+    m.base.compute_dtype = torch.float32
+    m.eval()
+    batch = pkg.synthetic_batch(24, 16, 12, seed=11, lg_inc="pyg").to(DEV)
+    assert batch.lg_active_rows < batch.edge_index.size(1) // 4
+    out = {}
+    with torch.no_grad():
+        for elide in (True, False):
+            m.base.elide_isolated = elide
+            k0 = ops.STATS.kernels
+            out[elide] = m(batch)
+            assert ops.STATS.kernels > k0
+    for a, b in zip(out[True], out[False]):
+        assert float((a - b).abs().max()) <= 1e-6 * max(float(b.abs().max()), 1.0)
+    # with autograd on, the per-block path keeps every row (its backward needs full-size saved tensors)
+    m.base.elide_isolated = True
+    m.train()
+    mean, logvar = m(batch)
+    (mean.sum() + logvar.sum()).backward()
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
