@@ -98,7 +98,7 @@ class TrainStep:
                  min_logvar_floor: float = -2.9, loss_scale: float = 1.0, graph: bool = True, graph_warmup: int = 2,
                  optimizer: bool = True, group=None, pad_to_buckets: bool = False, bucket_align: int = 256,
                  data_parallel: bool = True, feature_jitter_std: float = 0.0, allreduce_in_graph: bool = True,
-                 early_allreduce: bool = False, defer_angle_blocks: int = 116):
+                 early_allreduce: bool = False, defer_angle_blocks: int = 132):
         self.model = model
         params = [p for p in model.parameters() if p.requires_grad]
         if not params or not params[0].is_cuda:
