@@ -165,3 +165,25 @@ def test_stale_library_that_cannot_be_rebuilt_raises(monkeypatch):
         _lib.load()
     monkeypatch.setattr(_lib, "_LIB", None)
     assert _lib.load(rebuild_if_stale=False) is not None             # explicit opt-in still loads the binary
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """``bench.py --impl reference`` (the CPU arm the driver runs beside the B200 arm): one JSON line with the contract keys,
+    >= 10 timed steps, the spread of the step times, and no GPU work."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "1",
+                          "--cpu-sample-graphs", "2"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "graphs/s" and line["higher_is_better"] is True
+    assert line["steps"] >= 10 and line["gpu_launches"] == 0 and line["vs_baseline"] is None
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["spread"]["timed_steps"] == line["steps"]
+    assert line["e2e"] == {"value": line["value"], "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"] and "model" not in line["config"]
