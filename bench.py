@@ -126,9 +126,12 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, window=None):
+        """``window = (t_start, t_end)`` (``time.time()``): the timed region.  The sampler is started before the warm-up steps
+        (nvidia-smi needs > 100 ms to deliver its first line, the timed region of 20 steps is ~100 ms); samples that
+        arrived inside the timed region are used when there are any, else all samples under load (warm-up + timed)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -139,7 +142,13 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        lines, which = [ln for _, ln in self.lines], "warm-up + timed region"
+        if window is not None:
+            inside = [ln for ts, ln in self.lines if window[0] <= ts <= window[1] + 0.12]
+            if inside:
+                lines, which = inside, "timed region"
+        self.window = which
+        for ln in lines:
             parts = [x.strip() for x in ln.split(",")]
             if len(parts) < 6:
                 continue
@@ -151,7 +160,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": which}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -346,22 +355,24 @@ def main_b200(args):
             b_, tz_ = feeds[i % args.members]
             return steppers[i % args.members].step(b_, tz_)
 
+        sampler = ClockSampler(local_rank)
+        if rank == 0 and sample_clocks:
+            sampler.start()                           # before the warm-up: nvidia-smi is slow to deliver its first line
         for i in range(args.warmup):
             fed_step(i)
         barrier()
         ops.STATS.reset()
         ops.STATS.events = True
-        sampler = ClockSampler(local_rank)
-        if rank == 0 and sample_clocks:
-            sampler.start()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        w_start = time.time()
         t0.record()
         for i in range(args.steps):
             fed_step(i)
         t1.record()
         barrier()
-        clk = sampler.stop() if rank == 0 and sample_clocks else None
+        w_end = time.time()
+        clk = sampler.stop((w_start, w_end)) if rank == 0 and sample_clocks else None
         ops.STATS.events = False
         is_graphed = sum(s_.replays for s_ in steppers) > 0
         # graph mode: durations of the event nodes inside the replayed graphs (last replay of every member's graph)
