@@ -268,7 +268,7 @@ conv_bwd_src_kernel(const G *__restrict__ dagg, const T *__restrict__ q, const f
                     const int32_t *__restrict__ eid_t, T *__restrict__ dk, T *__restrict__ dv,
                     int64_t n_nodes, int hidden, int heads, int lph, int64_t ldq, int64_t ldd) {
     constexpr int RPW = 32 / LANES;
-    constexpr int U = 4;                       // edges in flight per lane: the pass is bound by L2 gather bandwidth
+    constexpr int U = 8;                       // edges in flight per lane: the pass is bound by L2 gather bandwidth
     const int lane = threadIdx.x & 31;
     const int sub = lane % LANES;
     const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
