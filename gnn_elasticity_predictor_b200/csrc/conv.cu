@@ -277,25 +277,35 @@ conv_bwd_src_kernel(const G *__restrict__ dagg, const T *__restrict__ q, const f
     const int head = sub / lph;
     const int ch = sub * 8;
     const int beg = __ldg(rowptr_t + row), end = __ldg(rowptr_t + row + 1);
+    // gather addresses as base + u32 index * u32 byte stride: ONE IMAD.WIDE.U32 per address (the 64-bit index arithmetic
+    // of `ptr + (int64)i * ld` was 21 of the 61 instructions per edge, and the pass issues at 60 % of peak)
+    const char *dagg_b = reinterpret_cast<const char *>(dagg + ch);
+    const char *q_b = reinterpret_cast<const char *>(q + ch);
+    const char *at_b = reinterpret_cast<const char *>(coef + head);
+    const char *ds_b = reinterpret_cast<const char *>(coef + heads + head);
+    const uint32_t dagg_ld = (uint32_t)hidden * (uint32_t)sizeof(G);
+    const uint32_t q_ld = (uint32_t)ldq * (uint32_t)sizeof(T);
+    const uint32_t coef_ld = 2u * (uint32_t)heads * (uint32_t)sizeof(float);
+    auto at_row = [](const char *base, uint32_t idx, uint32_t ld) { return base + (uint64_t)idx * ld; };
     F8 dkf, dvf;
 #pragma unroll
     for (int c = 0; c < 8; ++c) dkf.v[c] = dvf.v[c] = 0.f;
     int p = beg;
     for (; p + U <= end; p += U) {
-        int i[U], id[U];
+        uint32_t i[U], id[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            i[u] = __ldg(col_t + p + u);
-            id[u] = __ldg(eid_t + p + u);
+            i[u] = (uint32_t)__ldg(col_t + p + u);
+            id[u] = (uint32_t)__ldg(eid_t + p + u);
         }
         F8 g[U], qq[U];
         float at[U], ds[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            g[u] = ld8(dagg + (int64_t)i[u] * hidden + ch);
-            qq[u] = ld8(q + (int64_t)i[u] * ldq + ch);
-            at[u] = __ldg(coef + (int64_t)id[u] * 2 * heads + head);
-            ds[u] = __ldg(coef + (int64_t)id[u] * 2 * heads + heads + head);
+            g[u] = ld8(reinterpret_cast<const G *>(at_row(dagg_b, i[u], dagg_ld)));
+            qq[u] = ld8(reinterpret_cast<const T *>(at_row(q_b, i[u], q_ld)));
+            at[u] = __ldg(reinterpret_cast<const float *>(at_row(at_b, id[u], coef_ld)));
+            ds[u] = __ldg(reinterpret_cast<const float *>(at_row(ds_b, id[u], coef_ld)));
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {        // accumulation in edge order: same sums as the one-at-a-time loop
@@ -307,12 +317,12 @@ conv_bwd_src_kernel(const G *__restrict__ dagg, const T *__restrict__ q, const f
         }
     }
     for (; p < end; ++p) {
-        const int i0 = __ldg(col_t + p);
-        const int id0 = __ldg(eid_t + p);
-        const F8 g0 = ld8(dagg + (int64_t)i0 * hidden + ch);
-        const F8 q0 = ld8(q + (int64_t)i0 * ldq + ch);
-        const float at0 = __ldg(coef + (int64_t)id0 * 2 * heads + head);
-        const float ds0 = __ldg(coef + (int64_t)id0 * 2 * heads + heads + head);
+        const uint32_t i0 = (uint32_t)__ldg(col_t + p);
+        const uint32_t id0 = (uint32_t)__ldg(eid_t + p);
+        const F8 g0 = ld8(reinterpret_cast<const G *>(at_row(dagg_b, i0, dagg_ld)));
+        const F8 q0 = ld8(reinterpret_cast<const T *>(at_row(q_b, i0, q_ld)));
+        const float at0 = __ldg(reinterpret_cast<const float *>(at_row(at_b, id0, coef_ld)));
+        const float ds0 = __ldg(reinterpret_cast<const float *>(at_row(ds_b, id0, coef_ld)));
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             dvf.v[c] = fmaf(at0, g0.v[c], dvf.v[c]);
